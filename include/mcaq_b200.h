@@ -1,0 +1,148 @@
+/*
+ * mcaq_b200.h -- C ABI of libmcaq_b200.so: the B200-native (sm_100a) implementation of the
+ * MCAQ-YOLO hot path (tile-wise spatial adaptive quantization + morphological complexity).
+ *
+ * Every entry point takes plain device pointers and sizes, launches asynchronously on the
+ * caller's stream (a cudaStream_t passed as void*), never synchronises and never allocates,
+ * so every call is CUDA-graph capturable.  Return value: 0 on success, a positive
+ * cudaError_t when a launch failed, a negative MCAQ_E* code for bad arguments.
+ *
+ * Reference interfaces these replace (paths under the reference's mcaq_yolo/):
+ *   ops/src/mcaq_kernel.cu:102-123   launch_spatial_quantization      (kept, same signature)
+ *   ops/src/mcaq_ops.cpp:22-77       mcaq_cuda_ops.spatial_quantize   (Python shim on top)
+ *   core/quantization.py:319-353,409-434,636-746   ranges / EMA / compose / STE backward
+ *   core/morphology.py:826-873,939-973             phi tiles, complexity MLP, bilateral
+ *   core/bit_allocation.py:42-80,218-280           linear / MLP bit mappers (eval)
+ *   core/quantization.py:213-239                   learned soft mask
+ */
+#ifndef MCAQ_B200_H
+#define MCAQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCAQ_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MCAQ_API __attribute__((visibility("default")))
+#else
+#define MCAQ_API
+#endif
+
+/* element type of feature maps */
+#define MCAQ_F32  0
+#define MCAQ_BF16 1
+
+/* error codes (negative) */
+#define MCAQ_EINVAL   (-1)   /* bad size / null pointer */
+#define MCAQ_EALIGN   (-2)   /* pointer not 16-byte aligned */
+#define MCAQ_ETOOBIG  (-3)   /* plane does not fit the on-chip budget of the morphology kernel */
+#define MCAQ_EDTYPE   (-4)
+
+/* number of floats in the constant block expected by the morphology kernels, and the
+ * packed-parameter block sizes of the three small networks (see mcaq_b200/constants.py) */
+#define MCAQ_CONSTS_FLOATS     192
+#define MCAQ_CMLP_FLOATS       2881   /* complexity_mlp: 8-64-LN-32-LN-1            */
+#define MCAQ_MAPPER_FLOATS     4609   /* mapping_network with BN folded to (alpha,beta) */
+#define MCAQ_SOFTMASK_FLOATS   195    /* conv3x3(2->8)+b, conv1x1(8->2)+b, 5x5 smooth  */
+
+MCAQ_API int mcaq_abi_version(void);
+MCAQ_API const char* mcaq_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  one HBM sweep of x (NCHW, contiguous):
+ *     sum_plane[b,h,w] = sum_c x        (torch CPU cascade order, see oracle.cascade_sum)
+ *     abs_plane[b,h,w] = sum_c |x|
+ *     keys[0..C)  = ordered-int key of min over (b,h,w) per channel   (atomicMin)
+ *     keys[C..2C) = ordered-int key of max                            (atomicMax)
+ * keys may be NULL (frozen calibration: ranges not needed).  Call mcaq_ranges_reset first.
+ * Replaces: x.mean(1) morphology.py:837, x.abs().mean(1) quantization.py:224,
+ *           x.amin/amax quantization.py:333-334, 425-426, 653-654.
+ */
+MCAQ_API int mcaq_ranges_reset(int32_t* keys, int C, void* stream);
+MCAQ_API int mcaq_reduce_planes(const void* x, int dtype, int B, int C, int H, int W,
+                       float* sum_plane, float* abs_plane, int32_t* keys, void* stream);
+
+/* keys -> packed[0..C) = min, packed[C..2C) = -max  (one MIN all-reduce merges ranks) */
+MCAQ_API int mcaq_ranges_decode(const int32_t* keys, int C, float* packed, void* stream);
+
+/* EMA update of running_min/max (quantization.py:340-347); first!=0 adopts the batch stats */
+MCAQ_API int mcaq_ranges_ema(const float* packed, int C, double momentum, int first,
+                    float* running_min, float* running_max, void* stream);
+
+/* qtable[(b-2)*C + c] = {scale, zero_point} for b = 2..8 (quantization.py:41-66).
+ * Ranges come either from `packed` (min, -max) or from running_min/max (packed == NULL). */
+MCAQ_API int mcaq_build_qtable(const float* packed, const float* running_min, const float* running_max,
+                      int C, float* qtable /* 7*C*2 floats */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  y = m * dequant(quant_b(x)) with b = bit of the pixel's tile (nearest rule of
+ *     F.interpolate), per-channel scale/zero-point from qtable.  x, y: NCHW, dtype f32/bf16;
+ *     y may alias x (in place).  mask (B,H,W) fp32 or NULL.  codes (int8, same shape) or NULL.
+ * Replaces: quantization.py:729-744 (_forward_pytorch, eval) and mcaq_kernel.cu:12-99.
+ */
+MCAQ_API int mcaq_tile_quantize(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                       const float* bit_map, int Ht, int Wt, const float* qtable,
+                       const float* mask, int8_t* codes, void* stream);
+
+/* Training forward (fractional bits, quantization.py:699-727, 742-744):
+ *   pre = (1-f) Q_floor(b)(x) + f Q_floor(b)+1(x),  y = pre * m                              */
+MCAQ_API int mcaq_tile_quantize_train_fwd(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                                 const float* bit_map, int Ht, int Wt, const float* qtable,
+                                 const float* mask, void* stream);
+
+/* Training backward (STE, quantization.py:101-118 + autograd of the compose):
+ *   dx   = g*m*(1-f) + g*m*f
+ *   dbit[b,ty,tx] += sum_{c, pixels of tile} g*m*(Q_hi - Q_lo)     (dbit must be zeroed)
+ *   dmask[b,h,w]   = sum_c g*pre                                    (NULL when no mask)     */
+MCAQ_API int mcaq_tile_quantize_train_bwd(const void* grad_y, const void* x, void* grad_x, int dtype,
+                                 int B, int C, int H, int W,
+                                 const float* bit_map, int Ht, int Wt, const float* qtable,
+                                 const float* mask, float* dbit, float* dmask, void* stream);
+
+/* The reference's launcher, same argument list (mcaq_kernel.cu:102-111, MCAQPlugin.cpp:15-24).
+ * Semantics follow the reference's PyTorch path (round-half-even, IEEE division). */
+MCAQ_API void launch_spatial_quantization(const float* input, const float* bit_map,
+                                 const float* min_vals, const float* max_vals,
+                                 const float* mask, float* output,
+                                 int N, int C, int H, int W, int tile_h, int tile_w,
+                                 int n_tiles_h, int n_tiles_w, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  per-image morphology on the on-chip gray plane (one CTA per image).
+ *   in : sum_plane (B,H,W) from K1, C, grid_size, consts (MCAQ_CONSTS_FLOATS floats, device)
+ *   out: phi (B,ht,wt,8) fp32                                     morphology.py:826-873
+ *   optional debug outputs (NULL to skip): gray (B,Hc,Wc) fp32, edge_bits / bin_bits
+ *   (B,Hc,ceil(Wc/32)) uint32 bit planes, lbp_hist (B,ht,wt,10) int32, counts
+ *   (B,ht,wt,12) int32 = {edge, area, perim, euler_x4, N_2, N_4, N_8, N_16, N_32, otsu_bin,0,0}.
+ */
+MCAQ_API int mcaq_morph_phi(const float* sum_plane, int B, int C, int H, int W, int grid_size,
+                   const float* consts, float* phi,
+                   float* gray_dbg, uint32_t* edge_bits_dbg, uint32_t* bin_bits_dbg,
+                   int32_t* lbp_hist_dbg, int32_t* counts_dbg, void* stream);
+
+/* phi -> complexity (MLP + LayerNorm + sigmoid, 5x5 bilateral, clamp)  morphology.py:959-968 */
+MCAQ_API int mcaq_complexity(const float* phi, int B, int ht, int wt, const float* cmlp, const float* consts,
+                    float* complexity_raw /* nullable */, float* complexity, void* stream);
+
+/* complexity -> bit map, eval semantics (integer bits unless continuous != 0).
+ * mapper == NULL selects LinearBitMapper (2/98 % quantiles).  bit_allocation.py:42-80, 218-280 */
+MCAQ_API int mcaq_bit_mapper(const float* complexity, int B, int ht, int wt, const float* mapper,
+                    float temperature, int use_temperature, int continuous,
+                    float min_bits, float max_bits, float eps_spread, float* bit_map, void* stream);
+
+/* soft mask m (B,H,W) from bit map + abs_plane  (quantization.py:213-239) */
+MCAQ_API int mcaq_soft_mask(const float* bit_map, int Ht, int Wt, const float* abs_plane,
+                   int B, int C, int H, int W, const float* softmask, float* mask_tiles /* nullable */,
+                   float* mask, void* stream);
+
+/* tile size rule of the analyzer (morphology.py:359-376) */
+MCAQ_API int mcaq_tile_size(int H, int grid_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCAQ_B200_H */

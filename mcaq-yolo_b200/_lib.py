@@ -1,0 +1,68 @@
+"""ctypes binding of libmcaq_b200.so (declared in include/mcaq_b200.h)."""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libmcaq_b200.so")
+
+MCAQ_F32, MCAQ_BF16 = 0, 1
+
+# name -> (restype, argtypes): one entry per symbol declared in include/mcaq_b200.h
+PROTOTYPES = {
+    "mcaq_abi_version": (c_int, []),
+    "mcaq_error_string": (c_char_p, [c_int]),
+    "mcaq_tile_size": (c_int, [c_int, c_int]),
+    "mcaq_ranges_reset": (c_int, [c_void_p, c_int, c_void_p]),
+    "mcaq_reduce_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcaq_ranges_decode": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "mcaq_ranges_ema": (c_int, [c_void_p, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "mcaq_build_qtable": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mcaq_tile_quantize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcaq_tile_quantize_train_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mcaq_tile_quantize_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p]),
+    "launch_spatial_quantization": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mcaq_morph_phi": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcaq_complexity": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "mcaq_bit_mapper": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_int, c_int,
+                                c_float, c_float, c_float, c_void_p, c_void_p]),
+    "mcaq_soft_mask": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class McaqLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise McaqLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the MCAQ B200 path has no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)          # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().mcaq_error_string(rc)
+        raise RuntimeError(f"{what} failed: {msg.decode() if msg else rc} (code {rc})")

@@ -1,0 +1,99 @@
+// Shared device helpers for the MCAQ sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "mcaq_b200.h"
+
+#define MCAQ_LAUNCH_CHECK()                                   \
+  do {                                                        \
+    cudaError_t e__ = cudaGetLastError();                     \
+    if (e__ != cudaSuccess) return (int)e__;                  \
+  } while (0)
+
+namespace mcaq {
+
+// ---- order-preserving float <-> int key (for integer atomicMin/Max and REDUX) -------------
+__device__ __forceinline__ int float_key(float f) {
+  int b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float key_float(int k) {
+  return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
+}
+#define MCAQ_KEY_POS_INF 0x7f800000            /* float_key(+inf) */
+#define MCAQ_KEY_NEG_INF ((int)0x807fffff)     /* float_key(-inf) */
+
+// ---- 128-bit streaming loads / stores -----------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_plain(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- element traits: VEC elements per 16-byte vector --------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static constexpr int VEC = 4;
+  __device__ __forceinline__ static void unpack(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  __device__ __forceinline__ static uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]),
+                      __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+  __device__ __forceinline__ static float load1(const float* p) { return *p; }
+  __device__ __forceinline__ static void store1(float* p, float v) { *p = v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  // bf16 -> fp32 is exact: the 16 bits are the high half of the fp32 pattern
+  __device__ __forceinline__ static void unpack(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+  }
+  __device__ __forceinline__ static uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // round-to-nearest-even
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __device__ __forceinline__ static uint4 pack(const float* f) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+  __device__ __forceinline__ static float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  __device__ __forceinline__ static void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// ---- F.interpolate(mode='nearest') source index: min(floor(dst * (float)in/out), in-1) -----
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+  int i = (int)floorf(__fmul_rn((float)dst, scale));
+  return i < in_size - 1 ? i : in_size - 1;
+}
+
+// quantiser for one element; every operation is a separate IEEE fp32 rounding
+// (quantization.py:597-600): q = clamp(rint(x/scale + zp)), deq = (q - zp) * scale
+__device__ __forceinline__ float quant_code(float x, float scale, float zp, float qmin, float qmax) {
+  float t = __fadd_rn(__fdiv_rn(x, scale), zp);
+  float q = rintf(t);
+  return fminf(fmaxf(q, qmin), qmax);
+}
+__device__ __forceinline__ float dequant(float q, float scale, float zp) {
+  return __fmul_rn(__fsub_rn(q, zp), scale);
+}
+
+}  // namespace mcaq

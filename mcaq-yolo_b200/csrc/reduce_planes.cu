@@ -1,0 +1,310 @@
+// K1: one HBM sweep of an NCHW feature map producing
+//   sum_c x, sum_c |x| per pixel (fp32, torch-CPU cascade order) and per-channel min/max.
+//
+// Layout of the work: a "strip" is 32 consecutive 16-byte pixel vectors of one image; warp g
+// of a CTA owns one 16-channel chunk of the strip per pass (16 independent LDG.128 in flight
+// per thread), sums it sequentially (chunk partial P_g), reduces the chunk's per-channel
+// min/max across the warp with REDUX on order-preserving integer keys, and parks P_g in shared
+// memory.  The CTA then folds the partials in chunk order exactly like ATen's multi_row_sum
+// (acc1 += P_g, acc2 += acc1 every 16 chunks) so the planes are bit-identical to
+// x.mean(1) * C on the reference's CPU path.  CTAs are persistent over strips; per-channel
+// ranges are kept in shared memory and flushed with 2*C global atomics per CTA at the end.
+//
+// HBM traffic: reads x once (B*C*H*W*s bytes), writes 8 bytes per pixel.
+#include "common.cuh"
+
+namespace mcaq {
+
+// raw (still packed) vector kept in registers between the load burst and its use
+template <typename T, int VEC>
+struct VecIO {
+  static_assert(VEC == Elem<T>::VEC, "vector width");
+  typedef uint4 Raw;
+  __device__ __forceinline__ static Raw load(const T* p) { return ldg_stream(p); }
+  __device__ __forceinline__ static Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ static void unpack(const Raw& r, float* f) { Elem<T>::unpack(r, f); }
+};
+template <typename T>
+struct VecIO<T, 1> {
+  typedef float Raw;
+  __device__ __forceinline__ static Raw load(const T* p) { return Elem<T>::load1(p); }
+  __device__ __forceinline__ static Raw zero() { return 0.f; }
+  __device__ __forceinline__ static void unpack(const Raw& r, float* f) { f[0] = r; }
+};
+
+template <typename T, int VEC, int G, bool RANGES>
+__global__ void __launch_bounds__(32 * G)
+reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
+                     float* __restrict__ sum_plane, float* __restrict__ abs_plane,
+                     int* __restrict__ keys, int strips_per_image, long long total_strips) {
+  constexpr int NT = 32 * G;
+  constexpr int STRIP = 32 * VEC;                 // pixels per strip
+  constexpr int NOUT = (2 * STRIP + NT - 1) / NT; // outputs owned per thread in the fold
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* part = reinterpret_cast<float*>(smem_raw);           // [2][G][STRIP]
+  int* smin = reinterpret_cast<int*>(part + 2 * G * STRIP);   // [C]
+  int* smax = smin + C;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nfull = C >> 4;                       // full 16-channel chunks
+  const int tail = C & 15;
+  const int ngroups = nfull + (tail ? 1 : 0);
+  const int npass = (ngroups + G - 1) / G;
+  const int nvec = (HW + VEC - 1) / VEC;          // VEC==1 or HW % VEC == 0
+
+  if (RANGES) {
+    for (int c = threadIdx.x; c < C; c += NT) { smin[c] = MCAQ_KEY_POS_INF; smax[c] = MCAQ_KEY_NEG_INF; }
+    __syncthreads();
+  }
+
+  for (long long strip = blockIdx.x; strip < total_strips; strip += gridDim.x) {
+    const int b = (int)(strip / strips_per_image);
+    const int sv = (int)(strip - (long long)b * strips_per_image);
+    const int v = sv * 32 + lane;
+    const bool active = v < nvec;
+    const T* xb = x + ((long long)b * C) * HW + (long long)v * VEC;
+
+    float acc0[NOUT], acc1[NOUT], acc2[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; acc2[k] = 0.f; }
+
+    for (int pass = 0; pass < npass; ++pass) {
+      const int gi = pass * G + warp;             // chunk index of this warp
+      const int c0 = gi << 4;
+      float s[VEC], a[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { s[e] = 0.f; a[e] = 0.f; }
+      if (gi < ngroups) {
+        const int nch = (gi < nfull) ? 16 : tail;
+        typename VecIO<T, VEC>::Raw raw[16];
+        if (nch == 16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            raw[j] = active ? VecIO<T, VEC>::load(xb + (long long)(c0 + j) * HW) : VecIO<T, VEC>::zero();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            raw[j] = (active && j < nch) ? VecIO<T, VEC>::load(xb + (long long)(c0 + j) * HW)
+                                         : VecIO<T, VEC>::zero();
+        }
+        int mymin = MCAQ_KEY_POS_INF, mymax = MCAQ_KEY_NEG_INF;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float d[VEC];
+          VecIO<T, VEC>::unpack(raw[j], d);
+          float lo = d[0], hi = d[0];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            // 0 + x0 == x0, so starting from 0 reproduces the sequential chunk sum
+            s[e] = __fadd_rn(s[e], d[e]);
+            a[e] = __fadd_rn(a[e], fabsf(d[e]));
+            lo = fminf(lo, d[e]);
+            hi = fmaxf(hi, d[e]);
+          }
+          if (RANGES) {
+            const bool ok = active && j < nch;
+            int kmin = __reduce_min_sync(0xffffffffu, ok ? float_key(lo) : MCAQ_KEY_POS_INF);
+            int kmax = __reduce_max_sync(0xffffffffu, ok ? float_key(hi) : MCAQ_KEY_NEG_INF);
+            if (lane == j) { mymin = kmin; mymax = kmax; }
+          }
+        }
+        if (RANGES && lane < nch) {               // this warp is the only owner of channel c0+lane
+          const int c = c0 + lane;
+          smin[c] = min(smin[c], mymin);
+          smax[c] = max(smax[c], mymax);
+        }
+      }
+      // park the chunk partial: part[plane][warp][lane*VEC + e]
+      float* ps = part + (0 * G + warp) * STRIP + lane * VEC;
+      float* pa = part + (1 * G + warp) * STRIP + lane * VEC;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { ps[e] = s[e]; pa[e] = a[e]; }
+      __syncthreads();
+      // fold in chunk order (ATen multi_row_sum, level_step 16)
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        const int o = threadIdx.x + k * NT;
+        if (o < 2 * STRIP) {
+          const int plane = o / STRIP, q = o - plane * STRIP;
+          for (int w = 0; w < G; ++w) {
+            const int g2 = pass * G + w;
+            if (g2 >= ngroups) break;
+            const float p = part[(plane * G + w) * STRIP + q];
+            if (g2 < nfull) {
+              acc1[k] = __fadd_rn(acc1[k], p);
+              if (((g2 + 1) & 15) == 0) { acc2[k] = __fadd_rn(acc2[k], acc1[k]); acc1[k] = 0.f; }
+            } else {
+              acc0[k] = p;                        // tail chunk (C % 16 channels)
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // final = ((acc0 + acc1) + acc2) [+ acc3 == 0 for C < 4096]
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+      const int o = threadIdx.x + k * NT;
+      if (o < 2 * STRIP) {
+        const int plane = o / STRIP, q = o - plane * STRIP;
+        const long long pix = (long long)sv * STRIP + q;
+        if (pix < HW) {
+          const float r = __fadd_rn(__fadd_rn(acc0[k], acc1[k]), acc2[k]);
+          float* dst = plane ? abs_plane : sum_plane;
+          dst[(long long)b * HW + pix] = r;
+        }
+      }
+    }
+  }
+
+  if (RANGES) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += NT) {
+      atomicMin(keys + c, smin[c]);
+      atomicMax(keys + C + c, smax[c]);
+    }
+  }
+}
+
+__global__ void ranges_reset_kernel(int* keys, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) { keys[i] = MCAQ_KEY_POS_INF; keys[C + i] = MCAQ_KEY_NEG_INF; }
+}
+
+__global__ void ranges_decode_kernel(const int* keys, int C, float* packed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) { packed[i] = key_float(keys[i]); packed[C + i] = -key_float(keys[C + i]); }
+}
+
+// running <- momentum*running + (1-momentum)*new, separate mul/add roundings like torch
+__global__ void ranges_ema_kernel(const float* packed, int C, float momentum, float one_minus, int first,
+                                  float* rmin, float* rmax) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  const float mn = packed[i], mx = -packed[C + i];
+  if (first) { rmin[i] = mn; rmax[i] = mx; return; }
+  rmin[i] = __fadd_rn(__fmul_rn(momentum, rmin[i]), __fmul_rn(one_minus, mn));
+  rmax[i] = __fadd_rn(__fmul_rn(momentum, rmax[i]), __fmul_rn(one_minus, mx));
+}
+
+// qtable[(b-2)*C + c] = {scale, zp}   (quantization.py:41-66)
+__global__ void build_qtable_kernel(const float* packed, const float* rmin, const float* rmax, int C,
+                                    float2* qtable) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 7 * C) return;
+  const int bi = i / C, c = i - bi * C, bits = bi + 2;
+  const float mn = packed ? packed[c] : rmin[c];
+  const float mx = packed ? -packed[C + c] : rmax[c];
+  const float qmin = -(float)(1 << (bits - 1));
+  const float qmax = (float)((1 << (bits - 1)) - 1);
+  float rng = fmaxf(__fsub_rn(mx, mn), 1e-8f);
+  const float scale = __fdiv_rn(rng, __fsub_rn(qmax, qmin));
+  float zp = __fsub_rn(qmin, __fdiv_rn(mn, scale));
+  zp = fminf(fmaxf(zp, qmin), qmax);
+  qtable[i] = make_float2(scale, zp);
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <typename T, int VEC, int G>
+static int launch_reduce(const T* x, int B, int C, int HW, float* sp, float* ap, int* keys, cudaStream_t st) {
+  const int nvec = (HW + VEC - 1) / VEC;
+  const int spi = (nvec + 31) / 32;
+  const long long total = (long long)B * spi;
+  const size_t smem = (size_t)2 * G * 32 * VEC * sizeof(float) + (size_t)2 * C * sizeof(int);
+  // persistent CTAs: a few per SM so 16 loads x 32*G threads cover the HBM latency
+  const int per_sm = G >= 8 ? 4 : (G >= 4 ? 8 : 16);
+  long long grid = (long long)num_sms() * per_sm;
+  if (grid > total) grid = total;
+  if (grid < 1) grid = 1;
+  if (keys) {
+    auto k = reduce_planes_kernel<T, VEC, G, true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<(unsigned)grid, 32 * G, smem, st>>>(x, B, C, HW, sp, ap, keys, spi, total);
+  } else {
+    auto k = reduce_planes_kernel<T, VEC, G, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<(unsigned)grid, 32 * G, smem, st>>>(x, B, C, HW, sp, ap, keys, spi, total);
+  }
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, int VEC>
+static int dispatch_groups(const T* x, int B, int C, int HW, float* sp, float* ap, int* keys, cudaStream_t st) {
+  const int ngroups = (C + 15) / 16;
+  if (ngroups >= 8) return launch_reduce<T, VEC, 8>(x, B, C, HW, sp, ap, keys, st);
+  if (ngroups >= 3) return launch_reduce<T, VEC, 4>(x, B, C, HW, sp, ap, keys, st);
+  if (ngroups == 2) return launch_reduce<T, VEC, 2>(x, B, C, HW, sp, ap, keys, st);
+  return launch_reduce<T, VEC, 1>(x, B, C, HW, sp, ap, keys, st);
+}
+
+}  // namespace mcaq
+
+using namespace mcaq;
+
+extern "C" int mcaq_ranges_reset(int32_t* keys, int C, void* stream) {
+  if (!keys || C <= 0) return MCAQ_EINVAL;
+  ranges_reset_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(keys, C);
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcaq_reduce_planes(const void* x, int dtype, int B, int C, int H, int W,
+                                  float* sum_plane, float* abs_plane, int32_t* keys, void* stream) {
+  if (!x || !sum_plane || !abs_plane || B <= 0 || C <= 0 || H <= 0 || W <= 0) return MCAQ_EINVAL;
+  if (C >= 4096) return MCAQ_EINVAL;             // third cascade level not implemented
+  const long long hw = (long long)H * W;
+  if (hw > 0x7fffffffLL) return MCAQ_EINVAL;
+  const int HW = (int)hw;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool aligned = ((uintptr_t)x & 15) == 0;
+  if (dtype == MCAQ_F32) {
+    const float* p = (const float*)x;
+    if (aligned && HW % 4 == 0) return dispatch_groups<float, 4>(p, B, C, HW, sum_plane, abs_plane, keys, st);
+    return dispatch_groups<float, 1>(p, B, C, HW, sum_plane, abs_plane, keys, st);
+  } else if (dtype == MCAQ_BF16) {
+    const __nv_bfloat16* p = (const __nv_bfloat16*)x;
+    if (aligned && HW % 8 == 0) return dispatch_groups<__nv_bfloat16, 8>(p, B, C, HW, sum_plane, abs_plane, keys, st);
+    return dispatch_groups<__nv_bfloat16, 1>(p, B, C, HW, sum_plane, abs_plane, keys, st);
+  }
+  return MCAQ_EDTYPE;
+}
+
+extern "C" int mcaq_ranges_decode(const int32_t* keys, int C, float* packed, void* stream) {
+  if (!keys || !packed || C <= 0) return MCAQ_EINVAL;
+  ranges_decode_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(keys, C, packed);
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcaq_ranges_ema(const float* packed, int C, double momentum, int first,
+                               float* running_min, float* running_max, void* stream) {
+  if (!packed || !running_min || !running_max || C <= 0) return MCAQ_EINVAL;
+  // momentum and (1 - momentum) are Python doubles in the reference; each is rounded to fp32
+  // when it meets the fp32 tensor (quantization.py:346)
+  const float one_minus = (float)(1.0 - momentum);
+  ranges_ema_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(packed, C, (float)momentum, one_minus,
+                                                                      first, running_min, running_max);
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcaq_build_qtable(const float* packed, const float* running_min, const float* running_max,
+                                 int C, float* qtable, void* stream) {
+  if (!qtable || C <= 0 || (!packed && (!running_min || !running_max))) return MCAQ_EINVAL;
+  build_qtable_kernel<<<(7 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      packed, running_min, running_max, C, (float2*)qtable);
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}

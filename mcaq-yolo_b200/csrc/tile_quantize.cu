@@ -1,0 +1,477 @@
+// K3: fused bit-map quantize / de-quantize (+ soft-mask multiply) over an NCHW feature map,
+// plus the fractional-bit training forward and its straight-through backward.
+//
+// Thread = one 16-byte pixel vector (4 fp32 / 8 bf16 pixels of one row) x a chunk of channels:
+// the tile's bit-width, the mask vector and the (qmin, qmax) pair are computed once per thread
+// and reused for every channel; per channel the thread does one LDG.128, a float2 table lookup
+// {scale, zero_point}[bits][c] (L1-resident, warp-uniform when the warp's pixels share a
+// bit-width), the IEEE quantise/de-quantise chain and one STG.128.
+//
+// HBM traffic: reads x once and writes y once (2*s bytes per element); mask / bit map / table
+// are 1/C of that and stay in L1/L2.
+#include "common.cuh"
+
+namespace mcaq {
+
+constexpr int QCHUNK = 16;   // channels per thread
+constexpr int QUNROLL = 4;   // independent loads in flight per thread
+constexpr int QTHREADS = 128;
+
+struct QGeom {
+  int B, C, H, W, HW, Ht, Wt;
+  float sy, sx;              // (float)Ht/H, (float)Wt/W
+  long long nvec_total;      // B * HW / VEC
+  int nvec;                  // HW / VEC
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_elems(const T* p, float* f, bool inplace) {
+  if (VEC == 1) { f[0] = Elem<T>::load1(p); return; }
+  uint4 r = inplace ? ldg_plain(p) : ldg_stream(p);
+  Elem<T>::unpack(r, f);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void store_elems(T* p, const float* f) {
+  if (VEC == 1) { Elem<T>::store1(p, f[0]); return; }
+  stg_stream(p, Elem<T>::pack(f));
+}
+
+// per-thread pixel context: bit index per element (0..6), uniform flag, mask values
+template <int VEC>
+struct PixCtx {
+  int bidx[VEC];
+  float m[VEC];
+  bool uniform;
+};
+
+template <int VEC, bool HAS_MASK>
+__device__ __forceinline__ void make_ctx(const QGeom& g, int b, int pix, const float* __restrict__ bit_map,
+                                         const float* __restrict__ mask, PixCtx<VEC>& ctx) {
+  const int h = pix / g.W;
+  const int w0 = pix - h * g.W;
+  const int ty = nearest_src(h, g.sy, g.Ht);
+  const float* brow = bit_map + ((long long)b * g.Ht + ty) * g.Wt;
+  ctx.uniform = true;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    // VEC > 1 requires W % VEC == 0, so the vector never leaves row h
+    const int tx = nearest_src(w0 + e, g.sx, g.Wt);
+    float bf = rintf(__ldg(brow + tx));
+    bf = fminf(fmaxf(bf, 2.f), 8.f);
+    ctx.bidx[e] = (int)bf - 2;
+    if (ctx.bidx[e] != ctx.bidx[0]) ctx.uniform = false;
+    ctx.m[e] = 1.f;
+  }
+  if (HAS_MASK) {
+    const float* mp = mask + (long long)b * g.HW + pix;
+    if constexpr (VEC == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(mp));
+      ctx.m[0] = v.x; ctx.m[1] = v.y; ctx.m[2] = v.z; ctx.m[3] = v.w;
+    } else if constexpr (VEC == 8) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(mp));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
+      ctx.m[0] = v0.x; ctx.m[1] = v0.y; ctx.m[2] = v0.z; ctx.m[3] = v0.w;
+      ctx.m[4] = v1.x; ctx.m[5] = v1.y; ctx.m[6] = v1.z; ctx.m[7] = v1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) ctx.m[e] = __ldg(mp + e);
+    }
+  }
+}
+
+__device__ __forceinline__ void bit_limits(int bidx, float& qmin, float& qmax) {
+  const int half = 1 << (bidx + 1);            // 2^(bits-1)
+  qmin = -(float)half;
+  qmax = (float)(half - 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// inference
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC, bool HAS_MASK, bool CODES>
+__global__ void __launch_bounds__(QTHREADS)
+tile_quantize_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
+                     const float* __restrict__ bit_map, const float2* __restrict__ qtable,
+                     const float* __restrict__ mask, int8_t* __restrict__ codes, bool inplace) {
+  const long long gv = (long long)blockIdx.x * QTHREADS + threadIdx.x;
+  if (gv >= g.nvec_total) return;
+  const int b = (int)(gv / g.nvec);
+  const int v = (int)(gv - (long long)b * g.nvec);
+  const int pix = v * VEC;
+  PixCtx<VEC> ctx;
+  make_ctx<VEC, HAS_MASK>(g, b, pix, bit_map, mask, ctx);
+  float qmin0, qmax0;
+  bit_limits(ctx.bidx[0], qmin0, qmax0);
+
+  const int c_begin = blockIdx.y * QCHUNK;
+  const int c_end = min(c_begin + QCHUNK, g.C);
+  const long long base = ((long long)b * g.C) * g.HW + pix;
+  const float2* trow0 = qtable + (long long)ctx.bidx[0] * g.C;
+
+  for (int c0 = c_begin; c0 < c_end; c0 += QUNROLL) {
+    float xv[QUNROLL][VEC];
+    float2 sz[QUNROLL];
+#pragma unroll
+    for (int u = 0; u < QUNROLL; ++u) {
+      const int c = c0 + u;
+      if (c < c_end) {
+        load_elems<T, VEC>(x + base + (long long)c * g.HW, xv[u], inplace);
+        sz[u] = __ldg(trow0 + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < QUNROLL; ++u) {
+      const int c = c0 + u;
+      if (c >= c_end) break;
+      float out[VEC];
+      int8_t cd[VEC];
+      if (ctx.uniform) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float q = quant_code(xv[u][e], sz[u].x, sz[u].y, qmin0, qmax0);
+          float d = dequant(q, sz[u].x, sz[u].y);
+          if (HAS_MASK) d = __fmul_rn(d, ctx.m[e]);
+          out[e] = d;
+          if (CODES) cd[e] = (int8_t)(int)q;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          float qmin, qmax;
+          bit_limits(ctx.bidx[e], qmin, qmax);
+          const float2 p = __ldg(qtable + (long long)ctx.bidx[e] * g.C + c);
+          const float q = quant_code(xv[u][e], p.x, p.y, qmin, qmax);
+          float d = dequant(q, p.x, p.y);
+          if (HAS_MASK) d = __fmul_rn(d, ctx.m[e]);
+          out[e] = d;
+          if (CODES) cd[e] = (int8_t)(int)q;
+        }
+      }
+      store_elems<T, VEC>(y + base + (long long)c * g.HW, out);
+      if (CODES) {
+        int8_t* cp = codes + base + (long long)c * g.HW;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) cp[e] = cd[e];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// training forward: pre = (1-f)*Q_lo + f*Q_hi ; y = pre*m   (quantization.py:709-727, 742-744)
+// ---------------------------------------------------------------------------------------------
+struct FracCtx {
+  int lo_idx, hi_idx;     // table rows of floor(b) and min(floor(b)+1, 8)
+  float f, omf;           // frac and (1 - frac)
+};
+
+__device__ __forceinline__ FracCtx frac_ctx(float bits) {
+  FracCtx fc;
+  const float bf = floorf(bits);
+  fc.f = __fsub_rn(bits, bf);
+  fc.omf = __fsub_rn(1.f, fc.f);
+  int lo = (int)bf;
+  lo = lo < 2 ? 2 : (lo > 8 ? 8 : lo);
+  fc.lo_idx = lo - 2;
+  fc.hi_idx = (lo + 1 <= 8) ? lo - 1 : lo - 2;   // q_hi = q_lo when floor(b)+1 > 8
+  return fc;
+}
+
+__device__ __forceinline__ void frac_quant(float xv, const float2& plo, const float2& phi, const FracCtx& fc,
+                                           float& qlo, float& qhi) {
+  float mn, mx;
+  bit_limits(fc.lo_idx, mn, mx);
+  qlo = dequant(quant_code(xv, plo.x, plo.y, mn, mx), plo.x, plo.y);
+  bit_limits(fc.hi_idx, mn, mx);
+  qhi = dequant(quant_code(xv, phi.x, phi.y, mn, mx), phi.x, phi.y);
+}
+
+template <typename T, int VEC, bool HAS_MASK>
+__global__ void __launch_bounds__(QTHREADS)
+tile_quantize_train_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
+                               const float* __restrict__ bit_map, const float2* __restrict__ qtable,
+                               const float* __restrict__ mask) {
+  const long long gv = (long long)blockIdx.x * QTHREADS + threadIdx.x;
+  if (gv >= g.nvec_total) return;
+  const int b = (int)(gv / g.nvec);
+  const int v = (int)(gv - (long long)b * g.nvec);
+  const int pix = v * VEC;
+  const int h = pix / g.W, w0 = pix - h * g.W;
+  const int ty = nearest_src(h, g.sy, g.Ht);
+  const float* brow = bit_map + ((long long)b * g.Ht + ty) * g.Wt;
+  FracCtx fc[VEC];
+  float m[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    fc[e] = frac_ctx(__ldg(brow + nearest_src(w0 + e, g.sx, g.Wt)));
+    m[e] = HAS_MASK ? __ldg(mask + (long long)b * g.HW + pix + e) : 1.f;
+  }
+  const int c_begin = blockIdx.y * QCHUNK;
+  const int c_end = min(c_begin + QCHUNK, g.C);
+  const long long base = ((long long)b * g.C) * g.HW + pix;
+  for (int c = c_begin; c < c_end; ++c) {
+    float xv[VEC], out[VEC];
+    load_elems<T, VEC>(x + base + (long long)c * g.HW, xv, false);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float2 plo = __ldg(qtable + (long long)fc[e].lo_idx * g.C + c);
+      const float2 phi = __ldg(qtable + (long long)fc[e].hi_idx * g.C + c);
+      float qlo, qhi;
+      frac_quant(xv[e], plo, phi, fc[e], qlo, qhi);
+      float pre = __fadd_rn(__fmul_rn(fc[e].omf, qlo), __fmul_rn(fc[e].f, qhi));
+      out[e] = HAS_MASK ? __fmul_rn(pre, m[e]) : pre;
+    }
+    store_elems<T, VEC>(y + base + (long long)c * g.HW, out);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// training backward.  One CTA = (image b, tile row ty, tile col tx) x channel chunk so that the
+// d(bit_map) reduction is a plain block reduction followed by ONE atomicAdd per CTA, and
+// d(mask) is accumulated over the chunk in registers and added atomically per pixel.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool HAS_MASK>
+__global__ void __launch_bounds__(256)
+tile_quantize_train_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, T* __restrict__ gx, QGeom g,
+                               const float* __restrict__ bit_map, const float2* __restrict__ qtable,
+                               const float* __restrict__ mask, float* __restrict__ dbit,
+                               float* __restrict__ dmask, int cchunk) {
+  // grid.x enumerates pixels of image b in blocks of 256; grid.y = channel chunk; grid.z = b
+  const int b = blockIdx.z;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  const bool ok = pix < g.HW;
+  int ty = 0, tx = 0;
+  FracCtx fc = frac_ctx(2.f);
+  float m = 1.f;
+  if (ok) {
+    const int h = pix / g.W, w = pix - h * g.W;
+    ty = nearest_src(h, g.sy, g.Ht);
+    tx = nearest_src(w, g.sx, g.Wt);
+    fc = frac_ctx(__ldg(bit_map + ((long long)b * g.Ht + ty) * g.Wt + tx));
+    if (HAS_MASK) m = __ldg(mask + (long long)b * g.HW + pix);
+  }
+  const int c_begin = blockIdx.y * cchunk;
+  const int c_end = min(c_begin + cchunk, g.C);
+  const long long base = ((long long)b * g.C) * g.HW + pix;
+  float acc_bit = 0.f, acc_m = 0.f;
+  if (ok) {
+    for (int c = c_begin; c < c_end; ++c) {
+      const long long off = base + (long long)c * g.HW;
+      const float gv = Elem<T>::load1(gy + off);
+      const float xv = Elem<T>::load1(x + off);
+      const float2 plo = __ldg(qtable + (long long)fc.lo_idx * g.C + c);
+      const float2 phi = __ldg(qtable + (long long)fc.hi_idx * g.C + c);
+      float qlo, qhi;
+      frac_quant(xv, plo, phi, fc, qlo, qhi);
+      const float gm = HAS_MASK ? __fmul_rn(gv, m) : gv;
+      // dx = g*m*(1-f) + g*m*f  (autograd of the two STE branches, quantization.py:725-727)
+      const float dx = __fadd_rn(__fmul_rn(gm, fc.omf), __fmul_rn(gm, fc.f));
+      Elem<T>::store1(gx + off, dx);
+      acc_bit = fmaf(gm, __fsub_rn(qhi, qlo), acc_bit);
+      if (HAS_MASK) {
+        const float pre = __fadd_rn(__fmul_rn(fc.omf, qlo), __fmul_rn(fc.f, qhi));
+        acc_m = fmaf(gv, pre, acc_m);
+      }
+    }
+    if (HAS_MASK) atomicAdd(dmask + (long long)b * g.HW + pix, acc_m);
+  }
+  // d(bit_map): segmented warp reduction over contiguous runs of lanes in the same tile, then one
+  // atomicAdd per run (tile_w >= 4, so at most 8 runs per warp)
+  const int lane = threadIdx.x & 31;
+  const int tile_id = ok ? ty * g.Wt + tx : -1;
+  float v = acc_bit;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float t = __shfl_down_sync(0xffffffffu, v, off);
+    const int idn = __shfl_down_sync(0xffffffffu, tile_id, off);
+    if (lane + off < 32 && idn == tile_id) v += t;
+  }
+  const int idp = __shfl_up_sync(0xffffffffu, tile_id, 1);
+  const bool head = lane == 0 || idp != tile_id;
+  if (ok && head) atomicAdd(dbit + ((long long)b * g.Ht + ty) * g.Wt + tx, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reference-compatible launcher: builds {scale, zp} per (bit, channel) on the fly from
+// min/max (no workspace in that signature), one CTA-level table in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(256)
+spatial_quant_compat_kernel(const float* __restrict__ x, const float* __restrict__ bit_map,
+                            const float* __restrict__ mn, const float* __restrict__ mx,
+                            const float* __restrict__ mask, float* __restrict__ y, QGeom g) {
+  extern __shared__ float2 tab[];                      // [7][cchunk]
+  const int cchunk = QCHUNK;
+  const int c_begin = blockIdx.y * cchunk;
+  const int c_end = min(c_begin + cchunk, g.C);
+  for (int i = threadIdx.x; i < 7 * cchunk; i += blockDim.x) {
+    const int bi = i / cchunk, c = c_begin + (i - bi * cchunk);
+    if (c < c_end) {
+      float qmin, qmax;
+      bit_limits(bi, qmin, qmax);
+      const float rng = fmaxf(__fsub_rn(mx[c], mn[c]), 1e-8f);
+      const float scale = __fdiv_rn(rng, __fsub_rn(qmax, qmin));
+      float zp = __fsub_rn(qmin, __fdiv_rn(mn[c], scale));
+      tab[i] = make_float2(scale, fminf(fmaxf(zp, qmin), qmax));
+    }
+  }
+  __syncthreads();
+  const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // pixel over B*HW
+  if (gp >= (long long)g.B * g.HW) return;
+  const int b = (int)(gp / g.HW);
+  const int pix = (int)(gp - (long long)b * g.HW);
+  PixCtx<1> ctx;
+  make_ctx<1, HAS_MASK>(g, b, pix, bit_map, mask, ctx);
+  float qmin, qmax;
+  bit_limits(ctx.bidx[0], qmin, qmax);
+  const long long base = ((long long)b * g.C) * g.HW + pix;
+  for (int c = c_begin; c < c_end; ++c) {
+    const float2 p = tab[ctx.bidx[0] * cchunk + (c - c_begin)];
+    const float q = quant_code(__ldg(x + base + (long long)c * g.HW), p.x, p.y, qmin, qmax);
+    float d = dequant(q, p.x, p.y);
+    if (HAS_MASK) d = __fmul_rn(d, ctx.m[0]);
+    y[base + (long long)c * g.HW] = d;
+  }
+}
+
+static QGeom make_geom(int B, int C, int H, int W, int Ht, int Wt, int VEC) {
+  QGeom g;
+  g.B = B; g.C = C; g.H = H; g.W = W; g.HW = H * W; g.Ht = Ht; g.Wt = Wt;
+  g.sy = (float)Ht / (float)H;
+  g.sx = (float)Wt / (float)W;
+  g.nvec = (H * W) / VEC;
+  g.nvec_total = (long long)B * g.nvec;
+  return g;
+}
+
+template <typename T, int VEC>
+static int launch_quant(const T* x, T* y, int B, int C, int H, int W, const float* bit_map, int Ht, int Wt,
+                        const float* qtable, const float* mask, int8_t* codes, cudaStream_t st) {
+  QGeom g = make_geom(B, C, H, W, Ht, Wt, VEC);
+  dim3 grid((unsigned)((g.nvec_total + QTHREADS - 1) / QTHREADS), (unsigned)((C + QCHUNK - 1) / QCHUNK));
+  const bool inplace = (const void*)x == (const void*)y;
+  const float2* qt = (const float2*)qtable;
+  if (mask) {
+    if (codes) tile_quantize_kernel<T, VEC, true, true><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+    else tile_quantize_kernel<T, VEC, true, false><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+  } else {
+    if (codes) tile_quantize_kernel<T, VEC, false, true><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+    else tile_quantize_kernel<T, VEC, false, false><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+  }
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, int VEC>
+static int launch_train_fwd(const T* x, T* y, int B, int C, int H, int W, const float* bit_map, int Ht, int Wt,
+                            const float* qtable, const float* mask, cudaStream_t st) {
+  QGeom g = make_geom(B, C, H, W, Ht, Wt, VEC);
+  dim3 grid((unsigned)((g.nvec_total + QTHREADS - 1) / QTHREADS), (unsigned)((C + QCHUNK - 1) / QCHUNK));
+  const float2* qt = (const float2*)qtable;
+  if (mask) tile_quantize_train_fwd_kernel<T, VEC, true><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask);
+  else tile_quantize_train_fwd_kernel<T, VEC, false><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask);
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int launch_train_bwd(const T* gy, const T* x, T* gx, int B, int C, int H, int W, const float* bit_map,
+                            int Ht, int Wt, const float* qtable, const float* mask, float* dbit, float* dmask,
+                            cudaStream_t st) {
+  QGeom g = make_geom(B, C, H, W, Ht, Wt, 1);
+  const int cchunk = 32;
+  dim3 grid((unsigned)((g.HW + 255) / 256), (unsigned)((C + cchunk - 1) / cchunk), (unsigned)B);
+  const float2* qt = (const float2*)qtable;
+  if (mask) tile_quantize_train_bwd_kernel<T, true><<<grid, 256, 0, st>>>(gy, x, gx, g, bit_map, qt, mask, dbit, dmask, cchunk);
+  else tile_quantize_train_bwd_kernel<T, false><<<grid, 256, 0, st>>>(gy, x, gx, g, bit_map, qt, mask, dbit, dmask, cchunk);
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+static bool vec_ok(const void* a, const void* b, int HW, int W, int VEC, const void* mask) {
+  return ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)mask & 15) == 0 &&
+         HW % VEC == 0 && W % VEC == 0;
+}
+
+}  // namespace mcaq
+
+using namespace mcaq;
+
+static int check_common(const void* x, const void* y, int B, int C, int H, int W, const float* bit_map, int Ht,
+                        int Wt, const float* qtable) {
+  if (!x || !y || !bit_map || !qtable) return MCAQ_EINVAL;
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0) return MCAQ_EINVAL;
+  if ((long long)H * W > 0x7fffffffLL) return MCAQ_EINVAL;
+  return 0;
+}
+
+extern "C" int mcaq_tile_quantize(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                                  const float* bit_map, int Ht, int Wt, const float* qtable,
+                                  const float* mask, int8_t* codes, void* stream) {
+  int rc = check_common(x, y, B, C, H, W, bit_map, Ht, Wt, qtable);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MCAQ_F32) {
+    if (vec_ok(x, y, H * W, W, 4, mask))
+      return launch_quant<float, 4>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
+    return launch_quant<float, 1>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
+  } else if (dtype == MCAQ_BF16) {
+    typedef __nv_bfloat16 bf;
+    if (vec_ok(x, y, H * W, W, 8, mask))
+      return launch_quant<bf, 8>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
+    return launch_quant<bf, 1>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
+  }
+  return MCAQ_EDTYPE;
+}
+
+extern "C" int mcaq_tile_quantize_train_fwd(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                                            const float* bit_map, int Ht, int Wt, const float* qtable,
+                                            const float* mask, void* stream) {
+  int rc = check_common(x, y, B, C, H, W, bit_map, Ht, Wt, qtable);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MCAQ_F32) {
+    if (vec_ok(x, y, H * W, W, 4, nullptr))
+      return launch_train_fwd<float, 4>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
+    return launch_train_fwd<float, 1>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
+  } else if (dtype == MCAQ_BF16) {
+    typedef __nv_bfloat16 bf;
+    if (vec_ok(x, y, H * W, W, 8, nullptr))
+      return launch_train_fwd<bf, 8>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
+    return launch_train_fwd<bf, 1>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
+  }
+  return MCAQ_EDTYPE;
+}
+
+extern "C" int mcaq_tile_quantize_train_bwd(const void* grad_y, const void* x, void* grad_x, int dtype,
+                                            int B, int C, int H, int W, const float* bit_map, int Ht, int Wt,
+                                            const float* qtable, const float* mask, float* dbit, float* dmask,
+                                            void* stream) {
+  int rc = check_common(x, grad_x, B, C, H, W, bit_map, Ht, Wt, qtable);
+  if (rc) return rc;
+  if (!grad_y || !dbit || (mask && !dmask)) return MCAQ_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MCAQ_F32)
+    return launch_train_bwd<float>((const float*)grad_y, (const float*)x, (float*)grad_x, B, C, H, W, bit_map,
+                                   Ht, Wt, qtable, mask, dbit, dmask, st);
+  if (dtype == MCAQ_BF16) {
+    typedef __nv_bfloat16 bf;
+    return launch_train_bwd<bf>((const bf*)grad_y, (const bf*)x, (bf*)grad_x, B, C, H, W, bit_map, Ht, Wt,
+                                qtable, mask, dbit, dmask, st);
+  }
+  return MCAQ_EDTYPE;
+}
+
+extern "C" void launch_spatial_quantization(const float* input, const float* bit_map, const float* min_vals,
+                                            const float* max_vals, const float* mask, float* output, int N,
+                                            int C, int H, int W, int tile_h, int tile_w, int n_tiles_h,
+                                            int n_tiles_w, void* stream) {
+  (void)tile_h; (void)tile_w;   // the tile of a pixel follows F.interpolate's nearest rule on (H, n_tiles_h)
+  if (!input || !output || N <= 0 || C <= 0 || H <= 0 || W <= 0) return;
+  QGeom g = make_geom(N, C, H, W, n_tiles_h, n_tiles_w, 1);
+  dim3 grid((unsigned)(((long long)N * H * W + 255) / 256), (unsigned)((C + QCHUNK - 1) / QCHUNK));
+  const size_t smem = 7 * QCHUNK * sizeof(float2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mask) spatial_quant_compat_kernel<true><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g);
+  else spatial_quant_compat_kernel<false><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g);
+}

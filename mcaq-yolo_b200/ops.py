@@ -1,0 +1,257 @@
+"""Tensor-level wrappers over the C ABI (include/mcaq_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every function below
+validates its arguments, allocates outputs with the caching allocator and forwards raw
+pointers to libmcaq_b200.so on `torch.cuda.current_stream()`.  Nothing synchronises, so all
+of it is CUDA-graph capturable.  No CPU fallback: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import MCAQ_BF16, MCAQ_F32, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return MCAQ_F32
+    if t.dtype == torch.bfloat16:
+        return MCAQ_BF16
+    raise TypeError(f"mcaq_b200 supports float32 / bfloat16 feature maps, got {t.dtype}")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mcaq_b200 ops need CUDA tensors (there is no CPU fallback in this package)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t if t.dtype == torch.float32 else t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def tile_size(H: int, grid_size: int) -> int:
+    """morphology.py:359-376."""
+    return _lib.load().mcaq_tile_size(int(H), int(grid_size))
+
+
+# ----------------------------------------------------------------------------- K1
+def reduce_planes(x: torch.Tensor, want_ranges: bool = True):
+    """One sweep of x (B,C,H,W): returns (sum_c x, sum_c |x|, keys) with keys the int32 (2C,)
+    ordered-int min/max accumulators (None when want_ranges is False)."""
+    _need_cuda(x)
+    if x.dim() != 4:
+        raise ValueError("expected (B,C,H,W)")
+    x = x if x.is_contiguous() else x.contiguous()
+    B, C, H, W = x.shape
+    lib = _lib.load()
+    s = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
+    a = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
+    keys = None
+    if want_ranges:
+        keys = torch.empty((2 * C,), device=x.device, dtype=torch.int32)
+        check(lib.mcaq_ranges_reset(keys.data_ptr(), C, _stream()), "mcaq_ranges_reset")
+    check(lib.mcaq_reduce_planes(x.data_ptr(), _dtype_code(x), B, C, H, W, s.data_ptr(), a.data_ptr(),
+                                 _ptr(keys), _stream()), "mcaq_reduce_planes")
+    return s, a, keys
+
+
+def ranges_decode(keys: torch.Tensor) -> torch.Tensor:
+    """keys -> packed (2C,) fp32 = [min, -max] (a single MIN all-reduce merges ranks)."""
+    C = keys.numel() // 2
+    packed = torch.empty((2 * C,), device=keys.device, dtype=torch.float32)
+    check(_lib.load().mcaq_ranges_decode(keys.data_ptr(), C, packed.data_ptr(), _stream()), "mcaq_ranges_decode")
+    return packed
+
+
+def ranges_ema(packed: torch.Tensor, running_min: torch.Tensor, running_max: torch.Tensor,
+               momentum: float, first: bool):
+    """In-place EMA of running_min/max (quantization.py:340-347)."""
+    C = packed.numel() // 2
+    assert running_min.numel() == C and running_max.numel() == C
+    assert running_min.is_contiguous() and running_max.is_contiguous()
+    check(_lib.load().mcaq_ranges_ema(packed.data_ptr(), C, float(momentum), int(bool(first)),
+                                      running_min.data_ptr(), running_max.data_ptr(), _stream()),
+          "mcaq_ranges_ema")
+
+
+def build_qtable(packed: torch.Tensor | None = None, running_min: torch.Tensor | None = None,
+                 running_max: torch.Tensor | None = None) -> torch.Tensor:
+    """(7, C, 2) table of {scale, zero_point} for bits 2..8 (quantization.py:41-66)."""
+    if packed is not None:
+        C = packed.numel() // 2
+        dev = packed.device
+    else:
+        running_min, running_max = _f32c(running_min).reshape(-1), _f32c(running_max).reshape(-1)
+        C = running_min.numel()
+        dev = running_min.device
+    qt = torch.empty((7, C, 2), device=dev, dtype=torch.float32)
+    check(_lib.load().mcaq_build_qtable(_ptr(packed), _ptr(running_min), _ptr(running_max), C, qt.data_ptr(),
+                                        _stream()), "mcaq_build_qtable")
+    return qt
+
+
+# ----------------------------------------------------------------------------- K3
+def _bitmap_args(x, bit_map):
+    B, C, H, W = x.shape
+    if bit_map.dim() != 3 or bit_map.shape[0] != B:
+        raise RuntimeError(f"bit_map must be (B,Ht,Wt) with B={B}, got {tuple(bit_map.shape)}")
+    return B, C, H, W, int(bit_map.shape[1]), int(bit_map.shape[2])
+
+
+def tile_quantize(x: torch.Tensor, bit_map: torch.Tensor, qtable: torch.Tensor,
+                  mask: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                  want_codes: bool = False):
+    """y = m * Q_{b_T(p)}(x) (Eq.19; quantization.py:729-744).  `out` may be x (in place)."""
+    _need_cuda(x, bit_map, qtable, mask)
+    x = x if x.is_contiguous() else x.contiguous()
+    B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
+    bit_map = _f32c(bit_map)
+    if qtable.shape != (7, C, 2):
+        raise RuntimeError(f"qtable must be (7,{C},2)")
+    if mask is not None:
+        mask = _f32c(mask)
+        if mask.numel() != B * H * W:
+            raise RuntimeError("mask must be (N, 1, H, W)")
+    y = torch.empty_like(x) if out is None else out
+    codes = torch.empty(x.shape, device=x.device, dtype=torch.int8) if want_codes else None
+    check(_lib.load().mcaq_tile_quantize(x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W,
+                                         bit_map.data_ptr(), Ht, Wt, qtable.data_ptr(), _ptr(mask),
+                                         _ptr(codes), _stream()), "mcaq_tile_quantize")
+    return (y, codes) if want_codes else y
+
+
+def tile_quantize_train_fwd(x, bit_map, qtable, mask=None):
+    _need_cuda(x, bit_map, qtable, mask)
+    x = x if x.is_contiguous() else x.contiguous()
+    B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
+    bit_map = _f32c(bit_map)
+    mask = None if mask is None else _f32c(mask)
+    y = torch.empty_like(x)
+    check(_lib.load().mcaq_tile_quantize_train_fwd(x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W,
+                                                   bit_map.data_ptr(), Ht, Wt, qtable.data_ptr(), _ptr(mask),
+                                                   _stream()), "mcaq_tile_quantize_train_fwd")
+    return y
+
+
+def tile_quantize_train_bwd(grad_y, x, bit_map, qtable, mask=None):
+    """Returns (dx, dbit (B,Ht,Wt) fp32, dmask (B,H,W) fp32 or None)."""
+    _need_cuda(grad_y, x, bit_map, qtable, mask)
+    x = x if x.is_contiguous() else x.contiguous()
+    grad_y = grad_y if grad_y.is_contiguous() else grad_y.contiguous()
+    if grad_y.dtype != x.dtype:
+        grad_y = grad_y.to(x.dtype)
+    B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
+    bit_map = _f32c(bit_map)
+    mask = None if mask is None else _f32c(mask)
+    dx = torch.empty_like(x)
+    dbit = torch.zeros((B, Ht, Wt), device=x.device, dtype=torch.float32)
+    dmask = torch.zeros((B, H, W), device=x.device, dtype=torch.float32) if mask is not None else None
+    check(_lib.load().mcaq_tile_quantize_train_bwd(grad_y.data_ptr(), x.data_ptr(), dx.data_ptr(),
+                                                   _dtype_code(x), B, C, H, W, bit_map.data_ptr(), Ht, Wt,
+                                                   qtable.data_ptr(), _ptr(mask), dbit.data_ptr(), _ptr(dmask),
+                                                   _stream()), "mcaq_tile_quantize_train_bwd")
+    return dx, dbit, dmask
+
+
+def spatial_quantize(input: torch.Tensor, bit_map: torch.Tensor, min_vals: torch.Tensor,
+                     max_vals: torch.Tensor, tile_h: int, tile_w: int,
+                     mask: torch.Tensor | None = None) -> torch.Tensor:
+    """The reference's extension op `mcaq_cuda_ops.spatial_quantize` (ops/src/mcaq_ops.cpp:22-77):
+    same arguments, same checks (RuntimeError on shape mismatch), new fp32 output allocation."""
+    _need_cuda(input, bit_map, min_vals, max_vals, mask)
+    if input.dim() != 4:
+        raise RuntimeError("input must be (N, C, H, W)")
+    if input.dtype != torch.float32:
+        raise RuntimeError("expected scalar type Float")      # data_ptr<float>() in the reference
+    N, C, H, W = input.shape
+    if min_vals.numel() != C or max_vals.numel() != C:
+        raise RuntimeError(f"min_vals/max_vals must have one entry per channel (C={C}), got "
+                           f"{min_vals.numel()} — expand per-tensor stats before calling")
+    if mask is not None and mask.numel() != N * H * W:
+        raise RuntimeError("mask must be (N, 1, H, W)")
+    input = input.contiguous()
+    bit_map = _f32c(bit_map)
+    mn, mx = _f32c(min_vals).reshape(-1), _f32c(max_vals).reshape(-1)
+    mask = None if mask is None else _f32c(mask)
+    out = torch.empty_like(input)
+    _lib.load().launch_spatial_quantization(input.data_ptr(), bit_map.data_ptr(), mn.data_ptr(), mx.data_ptr(),
+                                            _ptr(mask), out.data_ptr(), N, C, H, W, int(tile_h), int(tile_w),
+                                            int(bit_map.shape[1]), int(bit_map.shape[2]), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- K2
+def morph_phi(sum_plane: torch.Tensor, C: int, grid_size: int, consts: torch.Tensor, debug: bool = False):
+    """phi tiles (B,ht,wt,8) from the channel-sum plane (morphology.py:826-873)."""
+    _need_cuda(sum_plane, consts)
+    B, H, W = sum_plane.shape
+    tile = tile_size(H, grid_size)
+    ht, wt = H // tile, W // tile
+    Hc, Wc = ht * tile, wt * tile
+    dev = sum_plane.device
+    phi = torch.empty((B, ht, wt, 8), device=dev, dtype=torch.float32)
+    dbg = {}
+    if debug:
+        ww = (Wc + 31) // 32
+        dbg = dict(gray=torch.empty((B, Hc, Wc), device=dev, dtype=torch.float32),
+                   edge_bits=torch.zeros((B, Hc, ww), device=dev, dtype=torch.int32),
+                   bin_bits=torch.zeros((B, Hc, ww), device=dev, dtype=torch.int32),
+                   lbp_hist=torch.zeros((B, ht, wt, 10), device=dev, dtype=torch.int32),
+                   counts=torch.zeros((B, ht, wt, 12), device=dev, dtype=torch.int32))
+    check(_lib.load().mcaq_morph_phi(sum_plane.data_ptr(), B, int(C), H, W, int(grid_size), consts.data_ptr(),
+                                     phi.data_ptr(), _ptr(dbg.get("gray")), _ptr(dbg.get("edge_bits")),
+                                     _ptr(dbg.get("bin_bits")), _ptr(dbg.get("lbp_hist")),
+                                     _ptr(dbg.get("counts")), _stream()), "mcaq_morph_phi")
+    return (phi, dbg) if debug else phi
+
+
+def complexity(phi: torch.Tensor, cmlp: torch.Tensor, consts: torch.Tensor, want_raw: bool = False):
+    """phi -> complexity map (B,ht,wt): MLP, bilateral filter, clamp (morphology.py:959-968)."""
+    _need_cuda(phi, cmlp, consts)
+    B, ht, wt, _ = phi.shape
+    phi = _f32c(phi)
+    out = torch.empty((B, ht, wt), device=phi.device, dtype=torch.float32)
+    raw = torch.empty_like(out) if want_raw else None
+    check(_lib.load().mcaq_complexity(phi.data_ptr(), B, ht, wt, cmlp.data_ptr(), consts.data_ptr(), _ptr(raw),
+                                      out.data_ptr(), _stream()), "mcaq_complexity")
+    return (out, raw) if want_raw else out
+
+
+def bit_mapper(cmap: torch.Tensor, mapper: torch.Tensor | None, temperature, continuous: bool,
+               min_bits: float = 2.0, max_bits: float = 8.0, eps_spread: float = 1e-3) -> torch.Tensor:
+    """Eval-mode bit mapper; mapper=None selects the linear (quantile) mapper."""
+    _need_cuda(cmap, mapper)
+    cmap = _f32c(cmap)
+    B, ht, wt = cmap.shape
+    out = torch.empty_like(cmap)
+    use_t = temperature is not None
+    t = max(float(temperature), 0.1) if use_t else 1.0
+    check(_lib.load().mcaq_bit_mapper(cmap.data_ptr(), B, ht, wt, _ptr(mapper), t, int(use_t), int(continuous),
+                                      float(min_bits), float(max_bits), float(eps_spread), out.data_ptr(),
+                                      _stream()), "mcaq_bit_mapper")
+    return out
+
+
+def soft_mask(bit_map: torch.Tensor, abs_plane: torch.Tensor, C: int, softmask: torch.Tensor,
+              want_tiles: bool = False):
+    """m (B,H,W) (quantization.py:213-239) from the bit map and the sum_c|x| plane."""
+    _need_cuda(bit_map, abs_plane, softmask)
+    bit_map = _f32c(bit_map)
+    B, H, W = abs_plane.shape
+    Ht, Wt = int(bit_map.shape[1]), int(bit_map.shape[2])
+    m = torch.empty((B, H, W), device=abs_plane.device, dtype=torch.float32)
+    mt = torch.empty((B, Ht, Wt), device=abs_plane.device, dtype=torch.float32) if want_tiles else None
+    check(_lib.load().mcaq_soft_mask(bit_map.data_ptr(), Ht, Wt, abs_plane.data_ptr(), B, int(C), H, W,
+                                     softmask.data_ptr(), _ptr(mt), m.data_ptr(), _stream()), "mcaq_soft_mask")
+    return (m, mt) if want_tiles else m
