@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- MCAQ complexity + quantize hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                     (CPU arm: oracle port on host cores)
+
+A step = one pass of the hot path (K1 channel sweep, K2 morphology, complexity MLP, bit mapper,
+soft mask, K3 quantize) over the C3/C4/C5 feature maps of one batch.  Workload at every N is
+BASELINE.json configs[1] per GPU: YOLOv8n @ 640x640, batch 64, bf16 feature maps
+(64x80x80, 128x40x40, 256x20x20), grid 8, bits 2..8, synthetic data, fixture weights.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "MCAQ complexity+quantize throughput (C3/C4/C5 hooks, whole job)"
+UNIT = "images/s"
+
+WORKLOADS = {
+    # name: (per-GPU batch, [(C, H, W)...], dtype, grid)
+    "yolov8n_640_b64_bf16": (64, [(64, 80, 80), (128, 40, 40), (256, 20, 20)], "bf16", 8),
+    "yolov8s_1280_b32_f32": (32, [(128, 160, 160), (256, 80, 80), (512, 40, 40)], "f32", 8),
+    "yolov8n_640_b1_f32": (1, [(64, 80, 80), (128, 40, 40), (256, 20, 20)], "f32", 8),
+}
+INPUT_SETS = 4          # rotating input sets: 4 x 92 MB > 126 MB L2, so no step starts L2-warm
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="yolov8n_640_b64_bf16", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle)
+def _oracle_worker(job):
+    """One bounded sample: the oracle's hook_forward over the three scales for `nimg` images."""
+    shapes, nimg, seed, grid = job
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import mcaq_oracle as o
+    from golden_util import weights
+    from inputs import feature_map
+    W = weights()
+    xs = [feature_map("smooth", nimg, C, H, Wd, seed + i) for i, (C, H, Wd) in enumerate(shapes)]
+    t0 = time.perf_counter()
+    for x in xs:
+        o.hook_forward(x, W["analyzer"], W["mapper"], W["quantizer"], grid, 1.0)
+    return time.perf_counter() - t0
+
+
+def cpu_sample(shapes, grid, seconds, procs):
+    """images/s of the oracle port on `procs` host processes (each its own 2-image batches)."""
+    import multiprocessing as mp
+    nimg = 2
+    t_one = _oracle_worker((shapes, nimg, 0, grid))
+    rounds = max(1, int(seconds / max(t_one, 1e-3)))
+    if procs == 1:
+        t0 = time.perf_counter()
+        for r in range(rounds):
+            _oracle_worker((shapes, nimg, r, grid))
+        dt = time.perf_counter() - t0
+        return nimg * rounds / dt, nimg * rounds, dt
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_oracle_worker, [(shapes, nimg, 1000 + i, grid) for i in range(procs)])   # warm imports
+        t0 = time.perf_counter()
+        pool.map(_oracle_worker, [(shapes, nimg, i, grid) for i in range(procs * rounds)])
+        dt = time.perf_counter() - t0
+    return nimg * procs * rounds / dt, nimg * procs * rounds, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, shapes, dtype, grid = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    # each "step" is a bounded sample; steps + warmup sized to finish within a few minutes
+    per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, nimg, dt = cpu_sample(shapes, grid, per_step, procs)
+        if i >= args.warmup:
+            vals.append((v, nimg, dt))
+    nimg = sum(v[1] for v in vals)
+    dt = sum(v[2] for v in vals)
+    value = nimg / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, len(vals)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "grid": grid, "note": "oracle port (numpy) of the reference's "
+                   "pure-PyTorch CPU path; the Python reference itself cannot travel to the GPU box"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{nimg} images in 2-image batches over {procs} processes, {dt:.1f} s"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the native arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mcaq_yolo_b200 import modules as M
+    from mcaq_yolo_b200 import ops
+    from golden_util import weights
+
+    B, shapes, dtype_name, grid = WORKLOADS[args.workload]
+    tdtype = torch.bfloat16 if dtype_name == "bf16" else torch.float32
+    esize = 2 if dtype_name == "bf16" else 4
+    W = weights()
+    analyzer, mapper, _ = M.build_fixture_modules(W, device=dev, grid_size=grid)
+    quantizers = []
+    for _ in shapes:
+        _, _, q = M.build_fixture_modules(W, device=dev, grid_size=grid)
+        quantizers.append(q)
+
+    # synthetic low-frequency feature maps, seeded per rank; INPUT_SETS rotating copies
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+
+    def synth(C, H, Wd):
+        coarse = torch.randn(B, C, H // 8 + 2, Wd // 8 + 2, device=dev, generator=gen)
+        up = torch.nn.functional.interpolate(coarse, size=(H, Wd), mode="bilinear", align_corners=False)
+        bias = torch.randn(1, C, 1, 1, device=dev, generator=gen) * 0.5
+        x = up * 1.6 + 0.1 * torch.randn(B, C, H, Wd, device=dev, generator=gen) + bias + 0.3
+        return x.to(tdtype).contiguous()
+
+    sets = [[synth(*s) for s in shapes] for _ in range(INPUT_SETS)]
+    elems = sum(C * H * Wd for C, H, Wd in shapes)
+    alg_bytes_step = 3 * esize * elems * B            # K1 read + K3 read + K3 write
+
+    def step(feats):
+        outs = []
+        for x, q in zip(feats, quantizers):
+            rec = M.mcaq_hook_forward(x, analyzer, mapper, q, temperature=1.0)
+            outs.append(rec)
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        # ---- warm-up (eager) primes host-side caches, then optional CUDA-graph capture ------
+        for i in range(max(3, args.warmup)):
+            step(sets[i % INPUT_SETS])
+        torch.cuda.synchronize()
+        ops.LAUNCHES = 0
+        step(sets[0])
+        launches_per_step = ops.LAUNCHES
+        graphs = None
+        if not args.no_graph:
+            try:
+                graphs, keep = [], []
+                for s in sets:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        keep.append(step(s))
+                    graphs.append(g)
+                for g in graphs:
+                    g.replay()
+                torch.cuda.synchronize()
+            except Exception as e:       # capture unsupported (e.g. NCCL in graph): time eager launches
+                sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager\n")
+                graphs = None
+                torch.cuda.synchronize()
+
+        def run_step(i):
+            if graphs is not None:
+                graphs[i % INPUT_SETS].replay()
+            else:
+                step(sets[i % INPUT_SETS])
+
+        for i in range(args.warmup):
+            run_step(i)
+        # ---- timed region: exactly K steps, device time, max over ranks -----------------------
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            run_step(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        ms_per_step = ms_total / args.steps
+        value = world * B * args.steps / (ms_total * 1e-3)
+
+        # ---- roofline attribution: eager steps with CUDA events around every launch -----------
+        times = {}
+        pending = {}
+
+        def hook(name, phase):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            if phase == 0:
+                pending[name] = ev
+            else:
+                times.setdefault(name, []).append((pending.pop(name), ev))
+
+        call_idx = {"n": 0}
+        per_call = []
+        for i in range(3):
+            step(sets[i % INPUT_SETS])
+        torch.cuda.synchronize()
+        ops.EVENT_HOOK = hook
+        nprof = min(args.steps, 20)
+        for i in range(nprof):
+            step(sets[i % INPUT_SETS])
+        ops.EVENT_HOOK = None
+        torch.cuda.synchronize()
+        kern_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in times.items()}
+        # launches of one kernel name come in scale order C3, C4, C5 within a step
+        nsc = len(shapes)
+        tq = kern_ms.get("mcaq_tile_quantize", [])
+        tq_c3 = tq[0::nsc]
+        dom_ms = statistics.mean(tq_c3) if tq_c3 else float("nan")
+        C3 = shapes[0]
+        dom_bytes = 2 * esize * B * C3[0] * C3[1] * C3[2]
+        k1 = kern_ms.get("mcaq_reduce_planes", [])
+        k1_c3 = statistics.mean(k1[0::nsc]) if k1 else float("nan")
+        step_kernel_ms = sum(sum(v) for v in kern_ms.values()) / nprof
+        shares = {k: round(sum(v) / nprof / step_kernel_ms, 4) for k, v in kern_ms.items()}
+
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "tile_quantize_kernel (K3) on C3 %dx%dx%dx%d %s" % (B, *C3, dtype_name),
+            "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms, "peak_source": peak_src,
+            "k1_reduce_planes_c3": {"achieved": (esize * B * C3[0] * C3[1] * C3[2]) / (k1_c3 * 1e-3) / 1e9,
+                                    "avg_launch_ms": k1_c3},
+            "whole_step": {"algorithmic_bytes": alg_bytes_step,
+                           "achieved": alg_bytes_step / (ms_per_step * 1e-3) / 1e9,
+                           "frac": alg_bytes_step / (ms_per_step * 1e-3) / 1e9 / peak},
+            "kernel_time_shares": shares,
+        }
+
+        # ---- end to end through the public module API with HOST buffers ---------------------------
+        host_in = [torch.empty((B, C, H, Wd), dtype=tdtype).pin_memory() for C, H, Wd in shapes]
+        for h, d in zip(host_in, sets[0]):
+            h.copy_(d)
+        host_out = [torch.empty_like(h).pin_memory() for h in host_in]
+        host_bits = [None] * len(shapes)
+        dev_in = [torch.empty_like(d) for d in sets[0]]
+
+        def e2e_step():
+            for h, d in zip(host_in, dev_in):
+                d.copy_(h, non_blocking=True)
+            recs = step(dev_in)
+            for i, r in enumerate(recs):
+                host_out[i].copy_(r["features_q"], non_blocking=True)
+                if host_bits[i] is None:
+                    host_bits[i] = torch.empty(r["bit_map"].shape, dtype=torch.float32).pin_memory()
+                host_bits[i].copy_(r["bit_map"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the caller reads the results on the host
+
+        for _ in range(3):
+            e2e_step()
+        nsteps_e2e = min(args.steps, 20)
+        barrier()
+        t0 = time.perf_counter()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(nsteps_e2e):
+            e2e_step()
+        a1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        te = torch.tensor([max(a0.elapsed_time(a1) * 1e-3, wall if world == 1 else 0.0)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = world * B * nsteps_e2e / float(te.item())
+        h2d = sum(h.numel() * h.element_size() for h in host_in)
+        d2h = sum(h.numel() * h.element_size() for h in host_out) + sum(hb.numel() * 4 for hb in host_bits)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 arithmetic on %s feature maps" % dtype_name, "data": "synthetic",
+        "config": {"workload": args.workload, "per_gpu_batch": B, "shapes_CHW": shapes, "grid": grid, "bits": "2-8",
+                   "mapper": "MLP (fixture weights)", "soft_mask": True, "ranges": "dynamic per batch"
+                   + (" (all-reduced MIN over ranks)" if world > 1 else ""),
+                   "l2": "%d rotating input sets (%.0f MB) > 126 MB L2, no flush" % (INPUT_SETS, INPUT_SETS * esize * elems * B / 1e6),
+                   "launch": "cuda-graph replay" if graphs is not None else "eager"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": nsteps_e2e, "api": "mcaq_hook_forward(analyzer, mapper, quantizer) per scale, pinned host buffers"},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, nimg, dt = cpu_sample(shapes, grid, args.cpu_seconds, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{nimg} images (2-image fp32 batches, same shapes), {dt:.1f} s, numpy oracle"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

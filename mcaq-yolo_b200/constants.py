@@ -64,13 +64,29 @@ def _flat(*tensors) -> torch.Tensor:
     return torch.cat([t.detach().reshape(-1).float() for t in tensors]).contiguous()
 
 
+def _cached(owner, tag: str, tensors, build):
+    """Re-pack only when a parameter/buffer changed (in-place updates bump `_version`,
+    re-assignment changes the data pointer); keeps the hot path free of packing kernels."""
+    key = tuple((t.data_ptr(), t._version) for t in tensors)
+    cache = owner.__dict__.setdefault("_mcaq_pack_cache", {})
+    hit = cache.get(tag)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    out = build()
+    cache[tag] = (key, out)
+    return out
+
+
 def pack_complexity_mlp(seq) -> torch.Tensor:
     """`complexity_mlp` Sequential(Linear(8,64), LN, ReLU, Linear(64,32), LN, ReLU, Linear(32,1), Sigmoid)."""
-    out = _flat(seq[0].weight, seq[0].bias, seq[1].weight, seq[1].bias,
-                seq[3].weight, seq[3].bias, seq[4].weight, seq[4].bias,
-                seq[6].weight, seq[6].bias)
-    assert out.numel() == CMLP_FLOATS, out.numel()
-    return out
+    ts = [seq[0].weight, seq[0].bias, seq[1].weight, seq[1].bias, seq[3].weight, seq[3].bias,
+          seq[4].weight, seq[4].bias, seq[6].weight, seq[6].bias]
+
+    def build():
+        out = _flat(*ts)
+        assert out.numel() == CMLP_FLOATS, out.numel()
+        return out
+    return _cached(seq, "cmlp", ts, build)
 
 
 def fold_batchnorm(bn):
@@ -84,19 +100,31 @@ def fold_batchnorm(bn):
 
 def pack_mapping_network(seq) -> torch.Tensor:
     """`mapping_network` Sequential(3x[Linear, BatchNorm1d, ReLU], Linear(32,1), Sigmoid), eval BN."""
-    parts = []
+    ts = []
     for li, bi in ((0, 1), (3, 4), (6, 7)):
-        a, b = fold_batchnorm(seq[bi])
-        parts += [seq[li].weight, seq[li].bias, a, b]
-    parts += [seq[9].weight, seq[9].bias]
-    out = _flat(*parts)
-    assert out.numel() == MAPPER_FLOATS, out.numel()
-    return out
+        ts += [seq[li].weight, seq[li].bias, seq[bi].weight, seq[bi].bias, seq[bi].running_mean,
+               seq[bi].running_var]
+    ts += [seq[9].weight, seq[9].bias]
+
+    def build():
+        parts = []
+        for li, bi in ((0, 1), (3, 4), (6, 7)):
+            a, b = fold_batchnorm(seq[bi])
+            parts += [seq[li].weight, seq[li].bias, a, b]
+        parts += [seq[9].weight, seq[9].bias]
+        out = _flat(*parts)
+        assert out.numel() == MAPPER_FLOATS, out.numel()
+        return out
+    return _cached(seq, "mapper", ts, build)
 
 
 def pack_soft_mask(soft_mask) -> torch.Tensor:
     """LearnedSoftMask: net[0] conv3x3(2->8), net[2] conv1x1(8->2), smooth_kernel (1,1,5,5)."""
-    out = _flat(soft_mask.net[0].weight, soft_mask.net[0].bias, soft_mask.net[2].weight,
-                soft_mask.net[2].bias, soft_mask.smooth_kernel)
-    assert out.numel() == SOFTMASK_FLOATS, out.numel()
-    return out
+    ts = [soft_mask.net[0].weight, soft_mask.net[0].bias, soft_mask.net[2].weight,
+          soft_mask.net[2].bias, soft_mask.smooth_kernel]
+
+    def build():
+        out = _flat(*ts)
+        assert out.numel() == SOFTMASK_FLOATS, out.numel()
+        return out
+    return _cached(soft_mask, "softmask", ts, build)

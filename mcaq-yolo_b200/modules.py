@@ -48,6 +48,23 @@ class _SweepCache:
 _SWEEP = _SweepCache()
 
 
+def allreduce_ranges(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """Merge per-rank channel ranges: `packed` = [min_c..., -max_c...], so ONE MIN all-reduce of
+    2C floats yields the ranges of the whole (sharded) batch -- the only collective the inference
+    path needs, and none at all once calibration is frozen."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.MIN, group=group)
+    return packed
+
+
+def shard_batch(n: int, rank: int, world: int):
+    """Contiguous batch slice of rank `rank` (images are independent)."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
 def channel_sweep(x: torch.Tensor, want_ranges: bool = True):
     """(sum_c x, sum_c |x|, range keys) of a (B,C,H,W) map: one HBM pass, reused by the next
     consumer of the same tensor."""
@@ -269,11 +286,13 @@ class LearnedSoftMask(nn.Module):
             act = F.adaptive_avg_pool2d((abs_plane / C).unsqueeze(1), (Ht, Wt))
             act = act / (act.amax(dim=(2, 3), keepdim=True) + 1e-8)
         bits_norm = ((bit_map.unsqueeze(1).float() - 2.0) / 6.0).clamp(0.0, 1.0)
-        logits = self.net(torch.cat([bits_norm, act], dim=1))
-        m = torch.softmax(logits, dim=1)[:, :1]
-        m = F.interpolate(m, size=(H, W), mode="nearest")
-        p = self.kernel_size // 2
-        return F.conv2d(F.pad(m, (p, p, p, p), mode="replicate"), self.smooth_kernel)
+        # full fp32 convolutions (cuDNN's default TF32 would cost ~1e-3 relative on m)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            logits = self.net(torch.cat([bits_norm, act], dim=1))
+            m = torch.softmax(logits, dim=1)[:, :1]
+            m = F.interpolate(m, size=(H, W), mode="nearest")
+            p = self.kernel_size // 2
+            return F.conv2d(F.pad(m, (p, p, p, p), mode="replicate"), self.smooth_kernel)
 
 
 class _FractionalQuant(torch.autograd.Function):
@@ -354,10 +373,8 @@ class SpatialAdaptiveQuantization(nn.Module):
         """packed [min, -max] of this batch (all ranks when a process group is attached)."""
         _, _, keys = channel_sweep(x, want_ranges=True)
         packed = ops.ranges_decode(keys)
-        if self.sync_ranges and torch.distributed.is_available() and torch.distributed.is_initialized():
-            pg = self.process_group
-            if torch.distributed.get_world_size(pg) > 1:
-                torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.MIN, group=pg)
+        if self.sync_ranges:
+            allreduce_ranges(packed, self.process_group)
         return packed
 
     @torch.no_grad()

@@ -40,6 +40,27 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+# Optional per-launch hook `f(name, phase)` (phase 0 before, 1 after the launch); bench.py sets
+# it to bracket kernels with CUDA events for the roofline attribution pass.  LAUNCHES counts
+# kernel launches issued through this module.
+EVENT_HOOK = None
+LAUNCHES = 0
+
+
+def _call(name: str, *args):
+    global LAUNCHES
+    fn = getattr(_lib.load(), name)
+    LAUNCHES += 1
+    if EVENT_HOOK is None:
+        rc = fn(*args)
+    else:
+        EVENT_HOOK(name, 0)
+        rc = fn(*args)
+        EVENT_HOOK(name, 1)
+    if rc is not None:
+        check(rc, name)
+
+
 def tile_size(H: int, grid_size: int) -> int:
     """morphology.py:359-376."""
     return _lib.load().mcaq_tile_size(int(H), int(grid_size))
@@ -54,15 +75,14 @@ def reduce_planes(x: torch.Tensor, want_ranges: bool = True):
         raise ValueError("expected (B,C,H,W)")
     x = x if x.is_contiguous() else x.contiguous()
     B, C, H, W = x.shape
-    lib = _lib.load()
     s = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
     a = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
     keys = None
     if want_ranges:
         keys = torch.empty((2 * C,), device=x.device, dtype=torch.int32)
-        check(lib.mcaq_ranges_reset(keys.data_ptr(), C, _stream()), "mcaq_ranges_reset")
-    check(lib.mcaq_reduce_planes(x.data_ptr(), _dtype_code(x), B, C, H, W, s.data_ptr(), a.data_ptr(),
-                                 _ptr(keys), _stream()), "mcaq_reduce_planes")
+        _call("mcaq_ranges_reset", keys.data_ptr(), C, _stream())
+    _call("mcaq_reduce_planes", x.data_ptr(), _dtype_code(x), B, C, H, W, s.data_ptr(), a.data_ptr(),
+                                 _ptr(keys), _stream())
     return s, a, keys
 
 
@@ -70,7 +90,7 @@ def ranges_decode(keys: torch.Tensor) -> torch.Tensor:
     """keys -> packed (2C,) fp32 = [min, -max] (a single MIN all-reduce merges ranks)."""
     C = keys.numel() // 2
     packed = torch.empty((2 * C,), device=keys.device, dtype=torch.float32)
-    check(_lib.load().mcaq_ranges_decode(keys.data_ptr(), C, packed.data_ptr(), _stream()), "mcaq_ranges_decode")
+    _call("mcaq_ranges_decode", keys.data_ptr(), C, packed.data_ptr(), _stream())
     return packed
 
 
@@ -80,9 +100,8 @@ def ranges_ema(packed: torch.Tensor, running_min: torch.Tensor, running_max: tor
     C = packed.numel() // 2
     assert running_min.numel() == C and running_max.numel() == C
     assert running_min.is_contiguous() and running_max.is_contiguous()
-    check(_lib.load().mcaq_ranges_ema(packed.data_ptr(), C, float(momentum), int(bool(first)),
-                                      running_min.data_ptr(), running_max.data_ptr(), _stream()),
-          "mcaq_ranges_ema")
+    _call("mcaq_ranges_ema", packed.data_ptr(), C, float(momentum), int(bool(first)),
+                                      running_min.data_ptr(), running_max.data_ptr(), _stream())
 
 
 def build_qtable(packed: torch.Tensor | None = None, running_min: torch.Tensor | None = None,
@@ -96,8 +115,8 @@ def build_qtable(packed: torch.Tensor | None = None, running_min: torch.Tensor |
         C = running_min.numel()
         dev = running_min.device
     qt = torch.empty((7, C, 2), device=dev, dtype=torch.float32)
-    check(_lib.load().mcaq_build_qtable(_ptr(packed), _ptr(running_min), _ptr(running_max), C, qt.data_ptr(),
-                                        _stream()), "mcaq_build_qtable")
+    _call("mcaq_build_qtable", _ptr(packed), _ptr(running_min), _ptr(running_max), C, qt.data_ptr(),
+                                        _stream())
     return qt
 
 
@@ -125,9 +144,9 @@ def tile_quantize(x: torch.Tensor, bit_map: torch.Tensor, qtable: torch.Tensor,
             raise RuntimeError("mask must be (N, 1, H, W)")
     y = torch.empty_like(x) if out is None else out
     codes = torch.empty(x.shape, device=x.device, dtype=torch.int8) if want_codes else None
-    check(_lib.load().mcaq_tile_quantize(x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W,
+    _call("mcaq_tile_quantize", x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W,
                                          bit_map.data_ptr(), Ht, Wt, qtable.data_ptr(), _ptr(mask),
-                                         _ptr(codes), _stream()), "mcaq_tile_quantize")
+                                         _ptr(codes), _stream())
     return (y, codes) if want_codes else y
 
 
@@ -138,9 +157,9 @@ def tile_quantize_train_fwd(x, bit_map, qtable, mask=None):
     bit_map = _f32c(bit_map)
     mask = None if mask is None else _f32c(mask)
     y = torch.empty_like(x)
-    check(_lib.load().mcaq_tile_quantize_train_fwd(x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W,
+    _call("mcaq_tile_quantize_train_fwd", x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W,
                                                    bit_map.data_ptr(), Ht, Wt, qtable.data_ptr(), _ptr(mask),
-                                                   _stream()), "mcaq_tile_quantize_train_fwd")
+                                                   _stream())
     return y
 
 
@@ -157,10 +176,10 @@ def tile_quantize_train_bwd(grad_y, x, bit_map, qtable, mask=None):
     dx = torch.empty_like(x)
     dbit = torch.zeros((B, Ht, Wt), device=x.device, dtype=torch.float32)
     dmask = torch.zeros((B, H, W), device=x.device, dtype=torch.float32) if mask is not None else None
-    check(_lib.load().mcaq_tile_quantize_train_bwd(grad_y.data_ptr(), x.data_ptr(), dx.data_ptr(),
+    _call("mcaq_tile_quantize_train_bwd", grad_y.data_ptr(), x.data_ptr(), dx.data_ptr(),
                                                    _dtype_code(x), B, C, H, W, bit_map.data_ptr(), Ht, Wt,
                                                    qtable.data_ptr(), _ptr(mask), dbit.data_ptr(), _ptr(dmask),
-                                                   _stream()), "mcaq_tile_quantize_train_bwd")
+                                                   _stream())
     return dx, dbit, dmask
 
 
@@ -185,7 +204,7 @@ def spatial_quantize(input: torch.Tensor, bit_map: torch.Tensor, min_vals: torch
     mn, mx = _f32c(min_vals).reshape(-1), _f32c(max_vals).reshape(-1)
     mask = None if mask is None else _f32c(mask)
     out = torch.empty_like(input)
-    _lib.load().launch_spatial_quantization(input.data_ptr(), bit_map.data_ptr(), mn.data_ptr(), mx.data_ptr(),
+    _call("launch_spatial_quantization", input.data_ptr(), bit_map.data_ptr(), mn.data_ptr(), mx.data_ptr(),
                                             _ptr(mask), out.data_ptr(), N, C, H, W, int(tile_h), int(tile_w),
                                             int(bit_map.shape[1]), int(bit_map.shape[2]), _stream())
     return out
@@ -209,10 +228,10 @@ def morph_phi(sum_plane: torch.Tensor, C: int, grid_size: int, consts: torch.Ten
                    bin_bits=torch.zeros((B, Hc, ww), device=dev, dtype=torch.int32),
                    lbp_hist=torch.zeros((B, ht, wt, 10), device=dev, dtype=torch.int32),
                    counts=torch.zeros((B, ht, wt, 12), device=dev, dtype=torch.int32))
-    check(_lib.load().mcaq_morph_phi(sum_plane.data_ptr(), B, int(C), H, W, int(grid_size), consts.data_ptr(),
+    _call("mcaq_morph_phi", sum_plane.data_ptr(), B, int(C), H, W, int(grid_size), consts.data_ptr(),
                                      phi.data_ptr(), _ptr(dbg.get("gray")), _ptr(dbg.get("edge_bits")),
                                      _ptr(dbg.get("bin_bits")), _ptr(dbg.get("lbp_hist")),
-                                     _ptr(dbg.get("counts")), _stream()), "mcaq_morph_phi")
+                                     _ptr(dbg.get("counts")), _stream())
     return (phi, dbg) if debug else phi
 
 
@@ -223,8 +242,8 @@ def complexity(phi: torch.Tensor, cmlp: torch.Tensor, consts: torch.Tensor, want
     phi = _f32c(phi)
     out = torch.empty((B, ht, wt), device=phi.device, dtype=torch.float32)
     raw = torch.empty_like(out) if want_raw else None
-    check(_lib.load().mcaq_complexity(phi.data_ptr(), B, ht, wt, cmlp.data_ptr(), consts.data_ptr(), _ptr(raw),
-                                      out.data_ptr(), _stream()), "mcaq_complexity")
+    _call("mcaq_complexity", phi.data_ptr(), B, ht, wt, cmlp.data_ptr(), consts.data_ptr(), _ptr(raw),
+                                      out.data_ptr(), _stream())
     return (out, raw) if want_raw else out
 
 
@@ -237,9 +256,9 @@ def bit_mapper(cmap: torch.Tensor, mapper: torch.Tensor | None, temperature, con
     out = torch.empty_like(cmap)
     use_t = temperature is not None
     t = max(float(temperature), 0.1) if use_t else 1.0
-    check(_lib.load().mcaq_bit_mapper(cmap.data_ptr(), B, ht, wt, _ptr(mapper), t, int(use_t), int(continuous),
+    _call("mcaq_bit_mapper", cmap.data_ptr(), B, ht, wt, _ptr(mapper), t, int(use_t), int(continuous),
                                       float(min_bits), float(max_bits), float(eps_spread), out.data_ptr(),
-                                      _stream()), "mcaq_bit_mapper")
+                                      _stream())
     return out
 
 
@@ -252,6 +271,6 @@ def soft_mask(bit_map: torch.Tensor, abs_plane: torch.Tensor, C: int, softmask: 
     Ht, Wt = int(bit_map.shape[1]), int(bit_map.shape[2])
     m = torch.empty((B, H, W), device=abs_plane.device, dtype=torch.float32)
     mt = torch.empty((B, Ht, Wt), device=abs_plane.device, dtype=torch.float32) if want_tiles else None
-    check(_lib.load().mcaq_soft_mask(bit_map.data_ptr(), Ht, Wt, abs_plane.data_ptr(), B, int(C), H, W,
-                                     softmask.data_ptr(), _ptr(mt), m.data_ptr(), _stream()), "mcaq_soft_mask")
+    _call("mcaq_soft_mask", bit_map.data_ptr(), Ht, Wt, abs_plane.data_ptr(), B, int(C), H, W,
+                                     softmask.data_ptr(), _ptr(mt), m.data_ptr(), _stream())
     return (m, mt) if want_tiles else m

@@ -1,0 +1,174 @@
+"""GPU tests of the host-side mirror (mcaq_yolo_b200.modules): the reference's module/hook API
+running on the sm_100a kernels, against the oracle and the committed reference outputs."""
+import numpy as np
+import pytest
+import torch
+
+import mcaq_oracle as o
+from golden_util import Case, bit_ambiguous, sha, weights
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-4, 2e-6
+
+CASES = ["c3_v8n_smooth", "c4_v8n_smooth", "c5_v8n_smooth", "crop_50", "rect_24x40", "c3_grid4", "c3_grid16"]
+
+
+@pytest.fixture(scope="module")
+def M():
+    from mcaq_yolo_b200 import modules
+    return modules
+
+
+@pytest.fixture(scope="module")
+def W():
+    return weights()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_hook_forward_matches_reference(name, M, W):
+    c = Case(name)
+    x = c.x()
+    a, m, q = M.build_fixture_modules(W, "cuda", grid_size=c.grid)
+    with torch.no_grad():
+        rec = M.mcaq_hook_forward(torch.from_numpy(x).cuda(), a, m, q, temperature=1.0, layer=4)
+    d = {}
+    r = o.hook_forward(x, W["analyzer"], W["mapper"], W["quantizer"], c.grid, 1.0, detail=d)
+    amb = bit_ambiguous(d["bits_pre_round"])
+    bm = rec["bit_map"].cpu().numpy()
+    assert int(((bm != c["bit_map_mlp"]) & ~amb).sum()) == 0
+    np.testing.assert_allclose(rec["complexity"].cpu().numpy(), c["complexity"], rtol=RTOL, atol=ATOL)
+    y = rec["features_q"].cpu().numpy()
+    if np.array_equal(bm, c["bit_map_mlp"]):
+        np.testing.assert_allclose(y[:, ::3, ::5, ::7], c["y_sub"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(y, r["y"], rtol=RTOL, atol=ATOL)
+    assert rec["layer"] == 4 and y.shape == x.shape
+
+
+def test_linear_mapper_and_score_image(M, W):
+    c = Case("c3_v8n_smooth")
+    x = torch.from_numpy(c.x()).cuda()
+    a, m, q = M.build_fixture_modules(W, "cuda", linear_mapper=True)
+    with torch.no_grad():
+        cpx = a(x)
+        b = m(cpx, 1.0)
+        s = a.score_image(x)
+    assert np.array_equal(b.cpu().numpy(), c["bit_map_linear"])
+    np.testing.assert_allclose(s.cpu().numpy(), c["score"], rtol=RTOL, atol=ATOL)
+    # reference known answers (tests/test_smoke.py:199-211)
+    flat = torch.full((1, 8, 8), 0.5, device="cuda")
+    assert torch.all(m(flat) == 5)
+    assert float(m(torch.zeros(1, 8, 8, device="cuda")).max()) == 2
+    assert float(m(torch.ones(1, 8, 8, device="cuda")).min()) == 8
+
+
+def test_frozen_calibration_and_ema(M, W):
+    """calibrate (training=True under eval, models/mcaq_yolo.py:446) -> freeze -> frozen ranges."""
+    c = Case("c4_v8n_smooth")
+    x = c.x()
+    a, m, q = M.build_fixture_modules(W, "cuda")
+    xt = torch.from_numpy(x).cuda()
+    bm = torch.from_numpy(c["bit_map_rand"]).cuda()
+    with torch.no_grad():
+        q(xt, bm, training=True)
+        assert np.array_equal(q.running_min.cpu().numpy().ravel(), c["train_run_min"])
+        q(xt * 1.5 + 0.25, bm, training=True)
+    np.testing.assert_allclose(q.running_min.cpu().numpy().ravel(), c["ema2_min"], rtol=1e-6)
+    assert int(q.num_batches_tracked) == 2
+    q.freeze_calibration()
+    frozen = q.running_min.clone()
+    with torch.no_grad():
+        q(xt * 100, bm, training=True)
+        assert torch.equal(q.running_min, frozen), "stats moved after freeze"
+        y = q(xt, bm, training=False)
+    mn, mx = q.running_min.cpu().numpy().ravel(), q.running_max.cpu().numpy().ravel()
+    _, ab = o.channel_sums(x)
+    mo = o.soft_mask(c["bit_map_rand"], ab, c.C, W["quantizer"])
+    yo, _ = o.quantize_eval(x, c["bit_map_rand"], mn, mx, mo)
+    np.testing.assert_allclose(y.cpu().numpy(), yo, rtol=RTOL, atol=ATOL)
+    # checkpoint round trip keeps the lazily created buffers (quantization.py:297-312)
+    q2 = M.SpatialAdaptiveQuantization().cuda()
+    q2.load_state_dict(q.state_dict())
+    assert torch.equal(q2.running_min, q.running_min) and q2._is_frozen()
+
+
+def test_training_step_gradients(M, W):
+    """Train-mode hook: continuous bits, fractional quantiser, gradients reach x, the bit map
+    (fractional + soft-mask paths) and the soft-mask net; compared with the reference's autograd."""
+    c = Case("small_smooth")
+    x = torch.from_numpy(c.x()).cuda().requires_grad_(True)
+    g = torch.from_numpy(c.grad()).cuda()
+    a, m, q = M.build_fixture_modules(W, "cuda")
+    q.train()
+    bf = torch.from_numpy(c["bit_map_frac"]).cuda().requires_grad_(True)
+    y = q(x, bf, training=True)
+    y.backward(g)
+    np.testing.assert_allclose(y.detach().cpu().numpy()[:, ::3, ::5, ::7], c["train_y_sub"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(x.grad.cpu().numpy()[:, ::3, ::5, ::7], c["train_dx_sub"], rtol=RTOL, atol=ATOL)
+    ref = c["train_dbit_total"]
+    np.testing.assert_allclose(bf.grad.cpu().numpy(), ref, rtol=5e-3, atol=5e-3 * np.abs(ref).max())
+    assert q.soft_mask.net[0].weight.grad is not None and float(q.soft_mask.net[0].weight.grad.abs().sum()) > 0
+    # analyzer + mapper in train mode: gradient reaches both MLPs (tests/test_smoke.py:50-59, 87-96)
+    a.train(); m.train()
+    cpx = a(x.detach())
+    bits = m(cpx, 10.0, return_continuous=True)
+    (bits.mean() - 4.0).pow(2).backward()
+    assert any(p.grad is not None and float(p.grad.abs().sum()) > 0 for p in a.complexity_mlp.parameters())
+    assert any(p.grad is not None and float(p.grad.abs().sum()) > 0 for p in m.mapping_network.parameters())
+
+
+def test_cuda_graph_capture_and_bf16(M, W):
+    """The whole eval hook is capturable (no host syncs) and bf16 maps keep codes exact."""
+    c = Case("c3_v8n_smooth")
+    xb = torch.from_numpy(c.x()).cuda().to(torch.bfloat16)
+    a, m, q = M.build_fixture_modules(W, "cuda")
+    with torch.no_grad():
+        eager = M.mcaq_hook_forward(xb, a, m, q)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            rec = M.mcaq_hook_forward(xb, a, m, q)
+        g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(rec["bit_map"], eager["bit_map"]) and torch.equal(rec["features_q"], eager["features_q"])
+    xu = xb.float().cpu().numpy()
+    r = o.hook_forward(xu, W["analyzer"], W["mapper"], W["quantizer"], 8, 1.0)
+    assert np.array_equal(rec["bit_map"].cpu().numpy(), r["bit_map"])
+    assert torch.equal(rec["features_q"].cpu(), torch.from_numpy(r["y"]).to(torch.bfloat16)) or \
+        np.allclose(rec["features_q"].float().cpu().numpy(), r["y"], rtol=1e-2, atol=1e-2)
+
+
+def test_reference_cuda_parity_test_shape(M):
+    """The reference's own parity test (tests/test_smoke.py:226-246) through the shimmed
+    `mcaq_cuda_ops.spatial_quantize`: randn(2,8,32,32), randint bit map, atol 1e-4."""
+    mod = M.install_mcaq_cuda_ops()
+    import mcaq_cuda_ops
+    assert mcaq_cuda_ops is mod
+    torch.manual_seed(0)
+    for smooth in (False, True):
+        q = M.SpatialAdaptiveQuantization(smooth_transitions=smooth).cuda().eval()
+        x = torch.randn(2, 8, 32, 32, device="cuda")
+        bit_map = torch.randint(2, 9, (2, 4, 4), device="cuda").float()
+        with torch.no_grad():
+            mask = q.soft_mask(bit_map, x).float().contiguous() if smooth else None
+            out = mcaq_cuda_ops.spatial_quantize(x.contiguous(), bit_map, x.amin(dim=(0, 2, 3), keepdim=True),
+                                                 x.amax(dim=(0, 2, 3), keepdim=True), 8, 8, mask)
+            mn = x.amin(dim=(0, 2, 3)).cpu().numpy()
+            mx = x.amax(dim=(0, 2, 3)).cpu().numpy()
+            yo, _ = o.quantize_eval(x.cpu().numpy(), bit_map.cpu().numpy(), mn, mx,
+                                    None if mask is None else mask[:, 0].cpu().numpy())
+        assert np.allclose(out.cpu().numpy(), yo, atol=1e-4)
+        assert np.array_equal(out.cpu().numpy(), yo)
+
+
+def test_install_swaps_modules(M, W):
+    class Fake(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            a, m, q = M.build_fixture_modules(W, "cuda")
+            self.complexity_analyzer, self.bit_mapper = a, m
+            self.quantizers = torch.nn.ModuleDict({"4": q})
+    f = Fake()
+    before = {k: v.clone() for k, v in f.state_dict().items()}
+    M.install(f)
+    after = f.state_dict()
+    assert set(before) == set(after) and all(torch.equal(before[k], after[k]) for k in before)
