@@ -139,6 +139,15 @@ MCAQ_API int mcaq_soft_mask(const float* bit_map, int Ht, int Wt, const float* a
                    int B, int C, int H, int W, const float* softmask, float* mask_tiles /* nullable */,
                    float* mask, void* stream);
 
+/* Self test of the quantiser's division (RN(x/scale) by Markstein's correction with RN(1/scale))
+ * against div.rn: sweeps numerators with bit patterns first + i*stride, i < count, for every
+ * scale; *mismatches must be zeroed by the caller. */
+MCAQ_API int mcaq_selftest_division(const float* scales, int nscales, unsigned first, unsigned stride, /* mismatches[2]: count, one example */
+                                    unsigned long long count, unsigned long long* mismatches, void* stream);
+
+/* debug: device buffer of 16 clock64() stamps per image written by mcaq_morph_phi (NULL disables) */
+MCAQ_API void mcaq_debug_stage_clocks(long long* dev_buf);
+
 /* tile size rule of the analyzer (morphology.py:359-376) */
 MCAQ_API int mcaq_tile_size(int H, int grid_size);
 

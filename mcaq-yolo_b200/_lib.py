@@ -1,7 +1,7 @@
 """ctypes binding of libmcaq_b200.so (declared in include/mcaq_b200.h)."""
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_uint, c_ulonglong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libmcaq_b200.so")
@@ -13,6 +13,8 @@ PROTOTYPES = {
     "mcaq_abi_version": (c_int, []),
     "mcaq_error_string": (c_char_p, [c_int]),
     "mcaq_tile_size": (c_int, [c_int, c_int]),
+    "mcaq_selftest_division": (c_int, [c_void_p, c_int, c_uint, c_uint, c_ulonglong, c_void_p, c_void_p]),
+    "mcaq_debug_stage_clocks": (None, [c_void_p]),
     "mcaq_ranges_reset": (c_int, [c_void_p, c_int, c_void_p]),
     "mcaq_reduce_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),

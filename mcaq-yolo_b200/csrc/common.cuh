@@ -92,6 +92,20 @@ __device__ __forceinline__ float quant_code(float x, float scale, float zp, floa
   float q = rintf(t);
   return fminf(fmaxf(q, qmin), qmax);
 }
+// Same code with the division done as Markstein's correction step: with rinv = RN(1/scale),
+//   q0 = RN(x*rinv), r = x - q0*scale (exact, FMA), q = RN(q0 + r*rinv) == RN(x/scale)
+// for finite operands in the normal range (|x| < 2^90 here; tests/test_gpu_division.py sweeps it
+// against div.rn).  Three FMA-pipe instructions instead of div.rn's check-and-branch sequence.
+__device__ __forceinline__ float div_markstein(float x, float scale, float rinv) {
+  const float q0 = __fmul_rn(x, rinv);
+  const float r = fmaf(-q0, scale, x);
+  return fmaf(r, rinv, q0);
+}
+__device__ __forceinline__ float quant_code_fast(float x, float scale, float zp, float rinv, float qmin,
+                                                 float qmax) {
+  const float t = __fadd_rn(div_markstein(x, scale, rinv), zp);
+  return fminf(fmaxf(rintf(t), qmin), qmax);
+}
 __device__ __forceinline__ float dequant(float q, float scale, float zp) {
   return __fmul_rn(__fsub_rn(q, zp), scale);
 }

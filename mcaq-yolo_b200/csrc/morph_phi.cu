@@ -87,7 +87,8 @@ __device__ __forceinline__ void sobel_at(const float* p, int r, int x, int Hc, i
 __global__ void __launch_bounds__(MORPH_THREADS, 1)
 morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* __restrict__ consts,
                  float* __restrict__ phi_out, float* __restrict__ gray_dbg, uint32_t* __restrict__ edge_dbg,
-                 uint32_t* __restrict__ bin_dbg, int* __restrict__ lbp_dbg, int* __restrict__ counts_dbg) {
+                 uint32_t* __restrict__ bin_dbg, int* __restrict__ lbp_dbg, int* __restrict__ counts_dbg,
+                 long long* __restrict__ clk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NP = g.Hc * g.Wc;
   const int NW = g.Hc * g.WW;
@@ -111,6 +112,8 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   const int tshift = 31 - __clz(tile);
   const float ntile2 = (float)(tile * tile);
 
+#define STAGE_CLOCK(k) do { if (clk && tid == 0) clk[(long long)b * 16 + (k)] = clock64(); } while (0)
+  STAGE_CLOCK(0);
   for (int i = tid; i < MCAQ_CONSTS_FLOATS; i += NT) kc[i] = consts[i];
 
   // ---- S0: gray = sum / C over the cropped plane, per-image min / max --------------------
@@ -144,6 +147,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   for (int i = tid; i < 256; i += NT) hist[i] = 0;
   __syncthreads();
 
+  STAGE_CLOCK(1);
   // ---- S3: adaptive threshold, 11x11 Gaussian mean with replicate borders -----------------
   //      (morphology.py:550-573): bin = g255 > local_mean - 2
   for (int slot = warp; slot < NW; slot += nwarps) {
@@ -169,6 +173,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
     if (lane == 0) BIN[slot] = word;
   }
   __syncthreads();
+  STAGE_CLOCK(2);
   for (int i = tid; i < g.ntiles * 10; i += NT) lbp_hist[i] = 0;
   __syncthreads();
 
@@ -215,6 +220,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   }
   __syncthreads();
 
+  STAGE_CLOCK(3);
   // ---- S5: phi2 (LBP entropy, morphology.py:648-652) and phi3 (654-670) per tile -----------
   for (int t = tid; t < g.ntiles; t += NT) {
     const int ty = t / wt, tx = t - ty * wt;
@@ -242,6 +248,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   }
   __syncthreads();
 
+  STAGE_CLOCK(4);
   // ---- S6: 5x5 Gaussian blur (zero padding) -> P1, Otsu histogram (morphology.py:485-493) --
   for (int slot = warp; slot < NW; slot += nwarps) {
     const int r = slot / WW, k = slot - r * WW;
@@ -269,6 +276,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   }
   __syncthreads();
 
+  STAGE_CLOCK(5);
   // ---- S7: Otsu threshold (morphology.py:397-418), one warp ----------------------------------
   if (warp == 0) {
     int cnt[8];
@@ -327,6 +335,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   const int otsu_bin = __float_as_int(red[1]);
   const float thr_lo = __fmul_rn(0.5f, thr255);
 
+  STAGE_CLOCK(6);
   // ---- S8: L1 gradient magnitude of Sobel(255 * blur) -> P0 (morphology.py:496-497) -------
   for (int i = tid; i < NP; i += NT) {
     const int r = i / Wc, x = i - r * Wc;
@@ -336,6 +345,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   }
   __syncthreads();
 
+  STAGE_CLOCK(7);
   // ---- S9: non-maximum suppression + double threshold (morphology.py:426-449, 500-502) ----
   const float rad2deg = kc[K_RAD2DEG];
   for (int slot = warp; slot < NW; slot += nwarps) {
@@ -365,6 +375,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   }
   __syncthreads();
 
+  STAGE_CLOCK(8);
   // ---- S10: hysteresis = 8 constrained 3x3 dilations (morphology.py:504-509) ---------------
   uint32_t* EA = STRONG;
   uint32_t* EB = reinterpret_cast<uint32_t*>(P1);               // P1 is dead from here on
@@ -386,6 +397,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   }
   const uint32_t* EDGE = EA;                                      // == STRONG after 8 swaps
 
+  STAGE_CLOCK(9);
   // ---- S11: integer tile counts ------------------------------------------------------------
   // acc[t][0..8] = edge, area, perim, euler_x4, N_2, N_4, N_8, N_16, N_32   (aliases P0)
   int* acc = reinterpret_cast<int*>(P0);
@@ -440,6 +452,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
       if (e4) atomicAdd(&acc[t * 9 + 3], e4);
     }
   }
+  STAGE_CLOCK(10);
   // dyadic box counts (morphology.py:595-601): one thread per (tile, box row of the scale)
   for (int t = tid; t < g.ntiles; t += NT) {
     const int ty = t / wt, tx = t - ty * wt;
@@ -461,6 +474,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
   }
   __syncthreads();
 
+  STAGE_CLOCK(11);
   // ---- S12: phi1, phi4, phi5, interactions (morphology.py:852-864) --------------------------
   for (int t = tid; t < g.ntiles; t += NT) {
     const int* a = acc + t * 9;
@@ -506,6 +520,7 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
       c[9] = otsu_bin; c[10] = 0; c[11] = 0;
     }
   }
+  STAGE_CLOCK(12);
   if (edge_dbg)
     for (int i = tid; i < NW; i += NT) edge_dbg[(long long)b * NW + i] = EDGE[i];
   if (bin_dbg)
@@ -515,6 +530,10 @@ morph_phi_kernel(const float* __restrict__ sum_plane, MorphGeom g, const float* 
 }  // namespace mcaq
 
 using namespace mcaq;
+
+static long long* g_stage_clk = nullptr;
+// debug: device buffer of 16 clock64() stamps per image (NULL disables); see tools/stage_clocks.py
+extern "C" void mcaq_debug_stage_clocks(long long* dev_buf) { g_stage_clk = dev_buf; }
 
 extern "C" int mcaq_morph_phi(const float* sum_plane, int B, int C, int H, int W, int grid_size,
                               const float* consts, float* phi, float* gray_dbg, uint32_t* edge_bits_dbg,
@@ -559,7 +578,7 @@ extern "C" int mcaq_morph_phi(const float* sum_plane, int B, int C, int H, int W
   if (NP <= 1024) threads = 128;
   else if (NP <= 4096) threads = 256;
   morph_phi_kernel<<<B, threads, smem, st>>>(sum_plane, g, consts, phi, gray_dbg, edge_bits_dbg, bin_bits_dbg,
-                                             lbp_hist_dbg, counts_dbg);
+                                             lbp_hist_dbg, counts_dbg, g_stage_clk);
   MCAQ_LAUNCH_CHECK();
   return 0;
 }

@@ -158,6 +158,102 @@ tile_quantize_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
 }
 
 // ---------------------------------------------------------------------------------------------
+// inference, vector path.  Requirements (checked by the dispatcher): H*W % VEC == 0, W % 4 == 0,
+// W % Wt == 0 and (W / Wt) % 4 == 0, so every aligned group of 4 pixels lies in one row and one
+// tile.  A thread owns one 16-byte pixel vector = VEC/4 such segments and walks QV_CHUNK
+// channels with QV_UNROLL independent LDG.128 in flight; the CTA's {scale, zero_point} rows for
+// its channel chunk sit in shared memory (row stride 17 float2: lanes with different bit-widths
+// hit different banks).
+// ---------------------------------------------------------------------------------------------
+constexpr int QV_THREADS = 256;
+constexpr int QV_CHUNK = 16;
+constexpr int QV_UNROLL = 8;
+constexpr int QV_ROW = QV_CHUNK + 1;
+
+template <typename T, int VEC, bool HAS_MASK, bool CODES>
+__global__ void __launch_bounds__(QV_THREADS)
+tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
+                         const float* __restrict__ bit_map, const float2* __restrict__ qtable,
+                         const float* __restrict__ mask, int8_t* __restrict__ codes, bool inplace) {
+  constexpr int NSEG = VEC / 4;
+  __shared__ float4 tab[7 * QV_ROW];               // {scale, zero_point, RN(1/scale), -}
+  const int c_begin = blockIdx.y * QV_CHUNK;
+  const int nch = min(QV_CHUNK, g.C - c_begin);
+  for (int i = threadIdx.x; i < 7 * QV_CHUNK; i += QV_THREADS) {
+    const int bi = i / QV_CHUNK, cl = i - bi * QV_CHUNK;
+    if (cl < nch) {
+      const float2 p = __ldg(qtable + (long long)bi * g.C + c_begin + cl);
+      tab[bi * QV_ROW + cl] = make_float4(p.x, p.y, __frcp_rn(p.x), 0.f);
+    }
+  }
+  __syncthreads();
+  const long long gv = (long long)blockIdx.x * QV_THREADS + threadIdx.x;
+  if (gv >= g.nvec_total) return;
+  const int b = (int)(gv / g.nvec);
+  const int v = (int)(gv - (long long)b * g.nvec);
+  const int pix = v * VEC;
+  const int h0 = pix / g.W, w0 = pix - h0 * g.W;
+  int trow[NSEG];
+  float qmin[NSEG], qmax[NSEG], m[VEC];
+#pragma unroll
+  for (int s = 0; s < NSEG; ++s) {
+    int hs = h0, ws = w0 + 4 * s;
+    if (ws >= g.W) { ws -= g.W; hs += 1; }
+    const int ty = nearest_src(hs, g.sy, g.Ht), tx = nearest_src(ws, g.sx, g.Wt);
+    float bf = rintf(__ldg(bit_map + ((long long)b * g.Ht + ty) * g.Wt + tx));
+    bf = fminf(fmaxf(bf, 2.f), 8.f);
+    const int bidx = (int)bf - 2;
+    trow[s] = bidx * QV_ROW;
+    bit_limits(bidx, qmin[s], qmax[s]);
+    if (HAS_MASK) {
+      const float4 mv = __ldg(reinterpret_cast<const float4*>(mask + (long long)b * g.HW + pix) + s);
+      m[4 * s + 0] = mv.x; m[4 * s + 1] = mv.y; m[4 * s + 2] = mv.z; m[4 * s + 3] = mv.w;
+    }
+  }
+  const long long base = ((long long)b * g.C + c_begin) * g.HW + pix;
+  const T* xp = x + base;
+  T* yp = y + base;
+#pragma unroll 1
+  for (int c0 = 0; c0 < nch; c0 += QV_UNROLL) {
+    uint4 raw[QV_UNROLL];
+#pragma unroll
+    for (int u = 0; u < QV_UNROLL; ++u) {
+      if (c0 + u < nch) {
+        const T* p = xp + (long long)(c0 + u) * g.HW;
+        raw[u] = inplace ? ldg_plain(p) : ldg_stream(p);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < QV_UNROLL; ++u) {
+      if (c0 + u >= nch) break;
+      float xv[VEC], out[VEC];
+      Elem<T>::unpack(raw[u], xv);
+      uint32_t cpack[NSEG];
+#pragma unroll
+      for (int s = 0; s < NSEG; ++s) {
+        const float4 p = tab[trow[s] + c0 + u];
+        uint32_t cp = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float q = quant_code_fast(xv[4 * s + e], p.x, p.y, p.z, qmin[s], qmax[s]);
+          float d = dequant(q, p.x, p.y);
+          if (HAS_MASK) d = __fmul_rn(d, m[4 * s + e]);
+          out[4 * s + e] = d;
+          if (CODES) cp |= ((uint32_t)(int)q & 0xffu) << (8 * e);
+        }
+        cpack[s] = cp;
+      }
+      stg_stream(yp + (long long)(c0 + u) * g.HW, Elem<T>::pack(out));
+      if (CODES) {
+        uint32_t* cdst = reinterpret_cast<uint32_t*>(codes + base + (long long)(c0 + u) * g.HW);
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) cdst[s] = cpack[s];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // training forward: pre = (1-f)*Q_lo + f*Q_hi ; y = pre*m   (quantization.py:709-727, 742-744)
 // ---------------------------------------------------------------------------------------------
 struct FracCtx {
@@ -348,15 +444,27 @@ template <typename T, int VEC>
 static int launch_quant(const T* x, T* y, int B, int C, int H, int W, const float* bit_map, int Ht, int Wt,
                         const float* qtable, const float* mask, int8_t* codes, cudaStream_t st) {
   QGeom g = make_geom(B, C, H, W, Ht, Wt, VEC);
-  dim3 grid((unsigned)((g.nvec_total + QTHREADS - 1) / QTHREADS), (unsigned)((C + QCHUNK - 1) / QCHUNK));
   const bool inplace = (const void*)x == (const void*)y;
   const float2* qt = (const float2*)qtable;
+  if (VEC > 1) {
+    dim3 grid((unsigned)((g.nvec_total + QV_THREADS - 1) / QV_THREADS), (unsigned)((C + QV_CHUNK - 1) / QV_CHUNK));
+    if (mask) {
+      if (codes) tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), true, true><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+      else tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), true, false><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+    } else {
+      if (codes) tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), false, true><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+      else tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), false, false><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+    }
+    MCAQ_LAUNCH_CHECK();
+    return 0;
+  }
+  dim3 grid((unsigned)((g.nvec_total + QTHREADS - 1) / QTHREADS), (unsigned)((C + QCHUNK - 1) / QCHUNK));
   if (mask) {
-    if (codes) tile_quantize_kernel<T, VEC, true, true><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
-    else tile_quantize_kernel<T, VEC, true, false><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+    if (codes) tile_quantize_kernel<T, 1, true, true><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+    else tile_quantize_kernel<T, 1, true, false><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
   } else {
-    if (codes) tile_quantize_kernel<T, VEC, false, true><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
-    else tile_quantize_kernel<T, VEC, false, false><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+    if (codes) tile_quantize_kernel<T, 1, false, true><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+    else tile_quantize_kernel<T, 1, false, false><<<grid, QTHREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
   }
   MCAQ_LAUNCH_CHECK();
   return 0;
@@ -393,6 +501,13 @@ static bool vec_ok(const void* a, const void* b, int HW, int W, int VEC, const v
          HW % VEC == 0 && W % VEC == 0;
 }
 
+// inference vector path: every aligned 4-pixel segment must lie in one row and one tile
+static bool seg_ok(const void* a, const void* b, const void* mask, const void* codes, int HW, int W, int Wt,
+                   int VEC) {
+  return ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)mask & 15) == 0 &&
+         ((uintptr_t)codes & 7) == 0 && HW % VEC == 0 && W % 4 == 0 && W % Wt == 0 && (W / Wt) % 4 == 0;
+}
+
 }  // namespace mcaq
 
 using namespace mcaq;
@@ -412,12 +527,12 @@ extern "C" int mcaq_tile_quantize(const void* x, void* y, int dtype, int B, int 
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MCAQ_F32) {
-    if (vec_ok(x, y, H * W, W, 4, mask))
+    if (seg_ok(x, y, mask, codes, H * W, W, Wt, 4))
       return launch_quant<float, 4>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
     return launch_quant<float, 1>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
   } else if (dtype == MCAQ_BF16) {
     typedef __nv_bfloat16 bf;
-    if (vec_ok(x, y, H * W, W, 8, mask))
+    if (seg_ok(x, y, mask, codes, H * W, W, Wt, 8))
       return launch_quant<bf, 8>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
     return launch_quant<bf, 1>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
   }
