@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--workload", default="yolov8n_640_b64_bf16", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-streams", action="store_true", help="run the three scales on one stream")
+    ap.add_argument("--unfused", action="store_true", help="module-by-module path (9 launches per scale)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -203,12 +205,13 @@ def run_native(args):
     elems = sum(C * H * Wd for C, H, Wd in shapes)
     alg_bytes_step = 3 * esize * elems * B            # K1 read + K3 read + K3 write
 
+    from mcaq_yolo_b200.fused import FusedHotPath
+    hot = FusedHotPath(analyzer, mapper, quantizers, temperature=1.0, streams=not args.no_streams)
+
     def step(feats):
-        outs = []
-        for x, q in zip(feats, quantizers):
-            rec = M.mcaq_hook_forward(x, analyzer, mapper, q, temperature=1.0)
-            outs.append(rec)
-        return outs
+        if args.unfused:
+            return [M.mcaq_hook_forward(x, analyzer, mapper, q, temperature=1.0) for x, q in zip(feats, quantizers)]
+        return hot.run(feats)
 
     def barrier():
         if world > 1:
@@ -268,41 +271,57 @@ def run_native(args):
         ms_per_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total * 1e-3)
 
-        # ---- roofline attribution: eager steps with CUDA events around every launch -----------
-        times = {}
-        pending = {}
+        # ---- roofline attribution: each kernel of each scale timed live with CUDA events around a
+        #      CUDA-graph replay of INPUT_SETS back-to-back launches over the rotating inputs (cold
+        #      L2; a graph keeps the queue full so host launch latency is not measured)
+        from mcaq_yolo_b200 import constants as KC
+        from mcaq_yolo_b200.fused import ScaleWorkspace
 
-        def hook(name, phase):
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            if phase == 0:
-                pending[name] = ev
-            else:
-                times.setdefault(name, []).append((pending.pop(name), ev))
+        def graph_time(fn, reps=10):
+            for i in range(INPUT_SETS):
+                fn(i)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(INPUT_SETS):
+                    fn(i)
+            g.replay()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                g.replay()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b) / INPUT_SETS)
+            return statistics.mean(ts)
 
-        call_idx = {"n": 0}
-        per_call = []
-        for i in range(3):
-            step(sets[i % INPUT_SETS])
-        torch.cuda.synchronize()
-        ops.EVENT_HOOK = hook
-        nprof = min(args.steps, 20)
-        for i in range(nprof):
-            step(sets[i % INPUT_SETS])
-        ops.EVENT_HOOK = None
-        torch.cuda.synchronize()
-        kern_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in times.items()}
-        # launches of one kernel name come in scale order C3, C4, C5 within a step
-        nsc = len(shapes)
-        tq = kern_ms.get("mcaq_tile_quantize", [])
-        tq_c3 = tq[0::nsc]
-        dom_ms = statistics.mean(tq_c3) if tq_c3 else float("nan")
+        cm = KC.pack_complexity_mlp(analyzer.complexity_mlp)
+        mp_ = KC.pack_mapping_network(mapper.mapping_network)
+        kern_ms = {}
+        for si, (C, H, Wd) in enumerate(shapes):
+            xs_ = [sets[j][si] for j in range(INPUT_SETS)]
+            ws = ScaleWorkspace(C, dev)
+            sm_ = KC.pack_soft_mask(quantizers[si].soft_mask)
+            planes = [ops.reduce_planes(x, want_ranges=False)[:2] for x in xs_]
+            fr = [ops.morph_fused(p[0], p[1], C, grid, cm, mp_, sm_, 1.0) for p in planes]
+            pk = ops.ranges_decode(ops.reduce_planes(xs_[0])[2])
+            ys_ = [torch.empty_like(x) for x in xs_]
+            tag = "C%d" % (3 + si)
+            kern_ms["K1_reduce_planes_" + tag] = graph_time(
+                lambda i: ops._call("mcaq_reduce_planes", xs_[i].data_ptr(), ops._dtype_code(xs_[i]), B, C, H, Wd,
+                                    planes[i][0].data_ptr(), planes[i][1].data_ptr(), ws.keys.data_ptr(), ops._stream()))
+            kern_ms["K2_morph_fused_" + tag] = graph_time(
+                lambda i: ops.morph_fused(planes[i][0], planes[i][1], C, grid, cm, mp_, sm_, 1.0, keys=ws.keys))
+            kern_ms["K3_tile_quantize_" + tag] = graph_time(
+                lambda i: ops.tile_quantize_ranges(xs_[i], fr[i]["bit_map"], pk, None, None, fr[i]["mask"], out=ys_[i]))
         C3 = shapes[0]
+        dom_ms = kern_ms["K3_tile_quantize_C3"]
         dom_bytes = 2 * esize * B * C3[0] * C3[1] * C3[2]
-        k1 = kern_ms.get("mcaq_reduce_planes", [])
-        k1_c3 = statistics.mean(k1[0::nsc]) if k1 else float("nan")
-        step_kernel_ms = sum(sum(v) for v in kern_ms.values()) / nprof
-        shares = {k: round(sum(v) / nprof / step_kernel_ms, 4) for k, v in kern_ms.items()}
+        k1_c3 = kern_ms["K1_reduce_planes_C3"]
+        tot_kernel_ms = sum(kern_ms.values())
+        shares = {k: round(v / tot_kernel_ms, 4) for k, v in kern_ms.items()}
 
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -313,14 +332,18 @@ def run_native(args):
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "tile_quantize_kernel (K3) on C3 %dx%dx%dx%d %s" % (B, *C3, dtype_name),
+            "traffic": None, "kernel": "tile_quantize_vec_kernel (K3) on C3 %dx%dx%dx%d %s" % (B, *C3, dtype_name),
             "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms, "peak_source": peak_src,
+            "how": "CUDA events around a graph replay of %d launches over rotating inputs (cold L2)" % INPUT_SETS,
             "k1_reduce_planes_c3": {"achieved": (esize * B * C3[0] * C3[1] * C3[2]) / (k1_c3 * 1e-3) / 1e9,
-                                    "avg_launch_ms": k1_c3},
+                                    "avg_launch_ms": k1_c3,
+                                    "frac": (esize * B * C3[0] * C3[1] * C3[2]) / (k1_c3 * 1e-3) / 1e9 / peak},
             "whole_step": {"algorithmic_bytes": alg_bytes_step,
                            "achieved": alg_bytes_step / (ms_per_step * 1e-3) / 1e9,
                            "frac": alg_bytes_step / (ms_per_step * 1e-3) / 1e9 / peak},
+            "kernel_ms": {k: round(v, 5) for k, v in kern_ms.items()},
             "kernel_time_shares": shares,
+            "serial_kernel_sum_ms": tot_kernel_ms,
         }
 
         # ---- end to end through the public module API with HOST buffers ---------------------------
@@ -369,10 +392,12 @@ def run_native(args):
                    "mapper": "MLP (fixture weights)", "soft_mask": True, "ranges": "dynamic per batch"
                    + (" (all-reduced MIN over ranks)" if world > 1 else ""),
                    "l2": "%d rotating input sets (%.0f MB) > 126 MB L2, no flush" % (INPUT_SETS, INPUT_SETS * esize * elems * B / 1e6),
-                   "launch": "cuda-graph replay" if graphs is not None else "eager"},
+                   "launch": ("cuda-graph replay" if graphs is not None else "eager")
+                   + (", module-by-module" if args.unfused else ", fused K1/K2/K3 per scale")
+                   + ("" if args.no_streams or args.unfused else ", one stream per scale")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": nsteps_e2e, "api": "mcaq_hook_forward(analyzer, mapper, quantizer) per scale, pinned host buffers"},
+                "steps": nsteps_e2e, "api": "FusedHotPath.run(feats) (the hook bodies install() registers), pinned host buffers"},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": roofline,

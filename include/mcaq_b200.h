@@ -88,6 +88,15 @@ MCAQ_API int mcaq_tile_quantize(const void* x, void* y, int dtype, int B, int C,
                        const float* bit_map, int Ht, int Wt, const float* qtable,
                        const float* mask, int8_t* codes, void* stream);
 
+/* Same as mcaq_tile_quantize with the per-channel ranges given directly (packed = [min, -max]
+ * as written by mcaq_ranges_decode / mcaq_morph_fused, or running_min/running_max when packed is
+ * NULL): each CTA derives its {scale, zero_point} rows itself, so no table kernel is launched.
+ * qtable_ws (7*C*2 floats) is only used for geometries the vector kernel does not cover. */
+MCAQ_API int mcaq_tile_quantize_ranges(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                                       const float* bit_map, int Ht, int Wt, const float* packed,
+                                       const float* running_min, const float* running_max,
+                                       float* qtable_ws, const float* mask, void* stream);
+
 /* Training forward (fractional bits, quantization.py:699-727, 742-744):
  *   pre = (1-f) Q_floor(b)(x) + f Q_floor(b)+1(x),  y = pre * m                              */
 MCAQ_API int mcaq_tile_quantize_train_fwd(const void* x, void* y, int dtype, int B, int C, int H, int W,
@@ -113,7 +122,8 @@ MCAQ_API void launch_spatial_quantization(const float* input, const float* bit_m
 
 /* ------------------------------------------------------------------------------------------
  * K2  per-image morphology on the on-chip gray plane (one CTA per image).
- *   in : sum_plane (B,H,W) from K1, C, grid_size, consts (MCAQ_CONSTS_FLOATS floats, device)
+ *   in : sum_plane (B,H,W) from K1, C, grid_size (consts: reserved, may be NULL -- the stencils
+ *        are compiled in from csrc/mcaq_consts.cuh)
  *   out: phi (B,ht,wt,8) fp32                                     morphology.py:826-873
  *   optional debug outputs (NULL to skip): gray (B,Hc,Wc) fp32, edge_bits / bin_bits
  *   (B,Hc,ceil(Wc/32)) uint32 bit planes, lbp_hist (B,ht,wt,10) int32, counts
@@ -123,6 +133,18 @@ MCAQ_API int mcaq_morph_phi(const float* sum_plane, int B, int C, int H, int W, 
                    const float* consts, float* phi,
                    float* gray_dbg, uint32_t* edge_bits_dbg, uint32_t* bin_bits_dbg,
                    int32_t* lbp_hist_dbg, int32_t* counts_dbg, void* stream);
+
+/* K2 fused: everything between the two HBM sweeps of the inference hook in ONE launch
+ * (models/mcaq_yolo.py:426-447): phi -> complexity (MLP, bilateral) -> bit map (MLP mapper, or
+ * LinearBitMapper when linear_mapper != 0) -> soft mask m (B,H,W) (skipped when softmask NULL).
+ * If keys != NULL, CTA 0 also decodes K1's range keys into packed_ranges ([min, -max], 2C floats)
+ * and re-arms the keys for the next sweep.  phi may be NULL. */
+MCAQ_API int mcaq_morph_fused(const float* sum_plane, const float* abs_plane, int B, int C, int H, int W,
+                              int grid_size, int32_t* keys, float* packed_ranges, const float* cmlp,
+                              const float* mapper, int linear_mapper, const float* softmask,
+                              float temperature, int use_temperature, int continuous, float min_bits,
+                              float max_bits, float eps_spread, float* phi, float* complexity,
+                              float* bit_map, float* mask, void* stream);
 
 /* phi -> complexity (MLP + LayerNorm + sigmoid, 5x5 bilateral, clamp)  morphology.py:959-968 */
 MCAQ_API int mcaq_complexity(const float* phi, int B, int ht, int wt, const float* cmlp, const float* consts,

@@ -23,6 +23,12 @@ PROTOTYPES = {
     "mcaq_build_qtable": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mcaq_tile_quantize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcaq_tile_quantize_ranges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                          c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p]),
+    "mcaq_morph_fused": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_float, c_float,
+                                 c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcaq_tile_quantize_train_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                              c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mcaq_tile_quantize_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

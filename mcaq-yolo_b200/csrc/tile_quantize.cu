@@ -165,6 +165,25 @@ tile_quantize_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
 // its channel chunk sit in shared memory (row stride 17 float2: lanes with different bit-widths
 // hit different banks).
 // ---------------------------------------------------------------------------------------------
+// per-channel ranges given directly (no table kernel): packed = [min_c..., -max_c...] or running stats
+struct QRanges {
+  const float* packed;
+  const float* rmin;
+  const float* rmax;
+};
+
+// {scale, zero_point} of (channel c, bits bi+2)  (quantization.py:41-66)
+__device__ __forceinline__ float2 qparams_from_ranges(const QRanges& rg, int C, int c, int bi) {
+  const float mn = rg.packed ? __ldg(rg.packed + c) : __ldg(rg.rmin + c);
+  const float mx = rg.packed ? -__ldg(rg.packed + C + c) : __ldg(rg.rmax + c);
+  float qmin, qmax;
+  bit_limits(bi, qmin, qmax);
+  const float rng = fmaxf(__fsub_rn(mx, mn), 1e-8f);
+  const float scale = __fdiv_rn(rng, __fsub_rn(qmax, qmin));
+  const float zp = __fsub_rn(qmin, __fdiv_rn(mn, scale));
+  return make_float2(scale, fminf(fmaxf(zp, qmin), qmax));
+}
+
 constexpr int QV_THREADS = 256;
 constexpr int QV_CHUNK = 16;
 constexpr int QV_UNROLL = 8;
@@ -174,7 +193,8 @@ template <typename T, int VEC, bool HAS_MASK, bool CODES>
 __global__ void __launch_bounds__(QV_THREADS)
 tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
                          const float* __restrict__ bit_map, const float2* __restrict__ qtable,
-                         const float* __restrict__ mask, int8_t* __restrict__ codes, bool inplace) {
+                         const float* __restrict__ mask, int8_t* __restrict__ codes, bool inplace,
+                         QRanges rg) {
   constexpr int NSEG = VEC / 4;
   __shared__ float4 tab[7 * QV_ROW];               // {scale, zero_point, RN(1/scale), -}
   const int c_begin = blockIdx.y * QV_CHUNK;
@@ -182,7 +202,9 @@ tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
   for (int i = threadIdx.x; i < 7 * QV_CHUNK; i += QV_THREADS) {
     const int bi = i / QV_CHUNK, cl = i - bi * QV_CHUNK;
     if (cl < nch) {
-      const float2 p = __ldg(qtable + (long long)bi * g.C + c_begin + cl);
+      float2 p;
+      if (qtable) p = __ldg(qtable + (long long)bi * g.C + c_begin + cl);
+      else p = qparams_from_ranges(rg, g.C, c_begin + cl, bi);
       tab[bi * QV_ROW + cl] = make_float4(p.x, p.y, __frcp_rn(p.x), 0.f);
     }
   }
@@ -442,18 +464,19 @@ static QGeom make_geom(int B, int C, int H, int W, int Ht, int Wt, int VEC) {
 
 template <typename T, int VEC>
 static int launch_quant(const T* x, T* y, int B, int C, int H, int W, const float* bit_map, int Ht, int Wt,
-                        const float* qtable, const float* mask, int8_t* codes, cudaStream_t st) {
+                        const float* qtable, const float* mask, int8_t* codes, cudaStream_t st,
+                        QRanges rg = QRanges{nullptr, nullptr, nullptr}) {
   QGeom g = make_geom(B, C, H, W, Ht, Wt, VEC);
   const bool inplace = (const void*)x == (const void*)y;
   const float2* qt = (const float2*)qtable;
   if (VEC > 1) {
     dim3 grid((unsigned)((g.nvec_total + QV_THREADS - 1) / QV_THREADS), (unsigned)((C + QV_CHUNK - 1) / QV_CHUNK));
     if (mask) {
-      if (codes) tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), true, true><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
-      else tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), true, false><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+      if (codes) tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), true, true><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
+      else tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), true, false><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
     } else {
-      if (codes) tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), false, true><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
-      else tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), false, false><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace);
+      if (codes) tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), false, true><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
+      else tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), false, false><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
     }
     MCAQ_LAUNCH_CHECK();
     return 0;
@@ -537,6 +560,34 @@ extern "C" int mcaq_tile_quantize(const void* x, void* y, int dtype, int B, int 
     return launch_quant<bf, 1>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
   }
   return MCAQ_EDTYPE;
+}
+
+extern "C" int mcaq_tile_quantize_ranges(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                                         const float* bit_map, int Ht, int Wt, const float* packed,
+                                         const float* running_min, const float* running_max,
+                                         float* qtable_ws, const float* mask, void* stream) {
+  if (!packed && (!running_min || !running_max)) return MCAQ_EINVAL;
+  float dummy = 0.f;
+  int rc = check_common(x, y, B, C, H, W, bit_map, Ht, Wt, &dummy);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  QRanges rg{packed, running_min, running_max};
+  const bool vec = dtype == MCAQ_F32 ? seg_ok(x, y, mask, nullptr, H * W, W, Wt, 4)
+                                     : seg_ok(x, y, mask, nullptr, H * W, W, Wt, 8);
+  if (vec) {
+    if (dtype == MCAQ_F32)
+      return launch_quant<float, 4>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, nullptr, mask, nullptr, st, rg);
+    if (dtype == MCAQ_BF16) {
+      typedef __nv_bfloat16 bf;
+      return launch_quant<bf, 8>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, nullptr, mask, nullptr, st, rg);
+    }
+    return MCAQ_EDTYPE;
+  }
+  // odd geometry: materialise the table in the caller's workspace, then the scalar kernel
+  if (!qtable_ws) return MCAQ_EINVAL;
+  rc = mcaq_build_qtable(packed, running_min, running_max, C, qtable_ws, stream);
+  if (rc) return rc;
+  return mcaq_tile_quantize(x, y, dtype, B, C, H, W, bit_map, Ht, Wt, qtable_ws, mask, nullptr, stream);
 }
 
 extern "C" int mcaq_tile_quantize_train_fwd(const void* x, void* y, int dtype, int B, int C, int H, int W,

@@ -465,9 +465,11 @@ def install_mcaq_cuda_ops():
     return mod
 
 
-def install(model, device=None):
+def install(model, device=None, fused: bool = True):
     """Swap the three hot-path objects of a reference MCAQYOLO (or any object exposing
-    `complexity_analyzer`, `bit_mapper`, `quantizers`) for the native ones, keeping their weights."""
+    `complexity_analyzer`, `bit_mapper`, `quantizers`) for the native ones, keeping their weights.
+    With `fused` (default) the reference's hook closures (`model._mcaq_hooks`) are replaced by
+    `fused.FusedMcaqHook`, same protocol, three launches per scale at inference."""
     dev = device or next(model.complexity_analyzer.parameters()).device
     a_old = model.complexity_analyzer
     a_new = MorphologicalComplexityAnalyzer(grid_size=a_old.grid_size, device=dev)
@@ -493,6 +495,14 @@ def install(model, device=None):
         q_new.load_state_dict(q_old.state_dict())
         q_new.train(q_old.training)
         model.quantizers[key] = q_new
+    hooks = getattr(model, "_mcaq_hooks", None)
+    if fused and hooks is not None and hasattr(model, "backbone_out_indices"):
+        from .fused import FusedMcaqHook
+        for h in hooks:
+            h.remove()
+        layers = list(model.model.model)
+        model._mcaq_hooks = [layers[idx].register_forward_hook(FusedMcaqHook(model, idx))
+                             for idx in model.backbone_out_indices if 0 <= idx < len(layers)]
     return model
 
 

@@ -27,7 +27,7 @@ kernel == oracle bit-for-bit on every discrete quantity):
 * `nn.Linear` is a sequential FMA chain over k starting from 0 with the bias
   added last (bit-identical to torch CPU for out_features > 1).
 * tile float sums are "row then column": each tile row left-to-right, then
-  the row sums top-to-bottom.
+  the row sums top-to-bottom; LayerNorm statistics use a 32-lane butterfly tree.
 * Otsu cumulative sums accumulate in fp64 and round to fp32 per element
   (what torch.cumsum does on CPU; exact, hence order independent).
 * transcendental functions are evaluated in fp64 and rounded to fp32.
@@ -583,17 +583,29 @@ def linear(x: np.ndarray, W: np.ndarray, b: np.ndarray) -> np.ndarray:
     return (acc + b[None, :]).astype(f32)
 
 
+def tree_sum32(v: np.ndarray) -> np.ndarray:
+    """Sum of 32 values per row in xor-butterfly order (step 16, 8, 4, 2, 1) -- the order a warp
+    shuffle reduction produces; all lanes end with identical bits.  v: (N,32) -> (N,)."""
+    idx = np.arange(32)
+    v = v.astype(f32)
+    for o in (16, 8, 4, 2, 1):
+        v = (v + v[:, idx ^ o]).astype(f32)
+    return v[:, 0]
+
+
 def layer_norm(x: np.ndarray, g: np.ndarray, b: np.ndarray, eps: float = 1e-5):
+    """nn.LayerNorm over the last axis (D = 32 or 64).  Statistics are reduced with a 32-lane
+    butterfly (elements k and k+32 pre-added for D = 64); torch's own CPU order (vectorised
+    Welford) is not reproducible outside torch, the difference stays at the 1e-7 level."""
     N, D = x.shape
-    s = np.zeros(N, dtype=f32)
-    for k in range(D):
-        s = s + x[:, k]
-    mean = (s / f32(D)).astype(f32)
+    assert D in (32, 64), D
+
+    def fold(a):
+        return a.astype(f32) if D == 32 else (a[:, :32] + a[:, 32:]).astype(f32)
+
+    mean = (tree_sum32(fold(x)) / f32(D)).astype(f32)
     d = (x - mean[:, None]).astype(f32)
-    v = np.zeros(N, dtype=f32)
-    for k in range(D):
-        v = v + (d[:, k] * d[:, k]).astype(f32)
-    var = (v / f32(D)).astype(f32)
+    var = (tree_sum32(fold((d * d).astype(f32))) / f32(D)).astype(f32)
     rstd = (f32(1.0) / sqrt32(var + f32(eps))).astype(f32)
     return (((d * rstd[:, None]).astype(f32) * g[None, :]).astype(f32) + b[None, :]).astype(f32)
 

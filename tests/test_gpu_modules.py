@@ -172,3 +172,106 @@ def test_install_swaps_modules(M, W):
     M.install(f)
     after = f.state_dict()
     assert set(before) == set(after) and all(torch.equal(before[k], after[k]) for k in before)
+
+
+# ------------------------------------------------------------------------------ fused 3-launch path
+@pytest.mark.parametrize("name", CASES + ["c3_v8s1280_smooth", "small_noise"])
+@pytest.mark.parametrize("linear", [False, True])
+def test_fused_hook_equals_module_path(name, linear, M, W):
+    """K1 -> K2 fused -> K3 (three launches) must reproduce the module-by-module path bit for bit,
+    including the range-key re-arming across consecutive calls."""
+    from mcaq_yolo_b200 import fused
+    c = Case(name)
+    a, m, q = M.build_fixture_modules(W, "cuda", grid_size=c.grid, linear_mapper=linear)
+    x = torch.from_numpy(c.x()).cuda()
+    x2 = (x * 0.5 - 0.25).contiguous()
+    with torch.no_grad():
+        ref1 = M.mcaq_hook_forward(x, a, m, q, temperature=1.0)
+        ref2 = M.mcaq_hook_forward(x2, a, m, q, temperature=1.3)
+        rec1, ws = fused.fused_scale_forward(x, a, m, q, 1.0, None)
+        rec2, ws = fused.fused_scale_forward(x2, a, m, q, 1.3, ws)     # re-armed keys
+    for ref, rec in ((ref1, rec1), (ref2, rec2)):
+        assert torch.equal(ref["complexity"], rec["complexity"])
+        assert torch.equal(ref["bit_map"], rec["bit_map"])
+        assert torch.equal(ref["features_q"], rec["features_q"])
+    if not linear:
+        assert int((rec1["bit_map"].cpu().numpy() != c["bit_map_mlp"]).sum()) == 0
+
+
+def test_fused_frozen_and_no_mask(M, W):
+    from mcaq_yolo_b200 import fused
+    c = Case("c4_v8n_smooth")
+    x = torch.from_numpy(c.x()).cuda()
+    a, m, q = M.build_fixture_modules(W, "cuda")
+    with torch.no_grad():
+        q(x, torch.from_numpy(c["bit_map_rand"]).cuda(), training=True)     # one calibration batch
+        q.freeze_calibration()
+        ref = M.mcaq_hook_forward(x * 1.1, a, m, q)
+        rec, _ = fused.fused_scale_forward(x * 1.1, a, m, q, 1.0, None)
+        assert torch.equal(ref["features_q"], rec["features_q"])
+        q2 = M.SpatialAdaptiveQuantization(smooth_transitions=False).cuda().eval()
+        ref = M.mcaq_hook_forward(x, a, m, q2)
+        rec, _ = fused.fused_scale_forward(x, a, m, q2, 1.0, None)
+        assert torch.equal(ref["features_q"], rec["features_q"]) and torch.equal(ref["bit_map"], rec["bit_map"])
+
+
+def test_fused_hot_path_streams_and_graph(M, W):
+    from mcaq_yolo_b200 import fused
+    names = ["c3_v8n_smooth", "c4_v8n_smooth", "c5_v8n_smooth"]
+    feats = [torch.from_numpy(Case(n).x()).cuda().to(torch.bfloat16) for n in names]
+    a, m, _ = M.build_fixture_modules(W, "cuda")
+    qs = [M.build_fixture_modules(W, "cuda")[2] for _ in names]
+    serial = fused.FusedHotPath(a, m, qs, streams=False)
+    multi = fused.FusedHotPath(a, m, qs, streams=True)
+    r0 = serial.run(feats)
+    r1 = multi.run(feats)
+    torch.cuda.synchronize()
+    for u, v in zip(r0, r1):
+        assert torch.equal(u["features_q"], v["features_q"]) and torch.equal(u["bit_map"], v["bit_map"])
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        r2 = multi.run(feats)
+    g.replay()
+    g.replay()
+    torch.cuda.synchronize()
+    for u, v in zip(r0, r2):
+        assert torch.equal(u["features_q"], v["features_q"]) and torch.equal(u["bit_map"], v["bit_map"])
+
+
+def test_install_registers_fused_hooks(M, W):
+    """A model-shaped object with the reference's hook protocol: install() swaps the hooks and a
+    forward produces the reference's aux records through the three-launch path."""
+    from mcaq_yolo_b200 import fused
+
+    class Backbone(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Sequential(torch.nn.Identity(), torch.nn.Identity())
+
+        def forward(self, x):
+            return self.model(x)
+
+    class FakeMcaq(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            a, m, q = M.build_fixture_modules(W, "cuda")
+            self.complexity_analyzer, self.bit_mapper = a, m
+            self.quantizers = torch.nn.ModuleDict({"1": q})
+            self.model = Backbone()
+            self.backbone_out_indices = [1]
+            self._mcaq_hooks = [self.model.model[1].register_forward_hook(lambda mod, i, o: None)]
+            self._mcaq_state = {"active": False}
+            self.normalize_complexity = False
+
+    f = FakeMcaq().eval()
+    M.install(f)
+    assert isinstance(list(f.model.model[1]._forward_hooks.values())[0], fused.FusedMcaqHook)
+    c = Case("c3_v8n_smooth")
+    x = torch.from_numpy(c.x()).cuda()
+    f._mcaq_state = {"active": True, "temperature": 1.0, "quantize": True, "aux": []}
+    with torch.no_grad():
+        y = f.model(x)
+    aux = f._mcaq_state["aux"]
+    assert len(aux) == 1 and aux[0]["layer"] == 1 and torch.equal(y, aux[0]["features_q"])
+    assert np.array_equal(aux[0]["bit_map"].cpu().numpy(), c["bit_map_mlp"])
+    np.testing.assert_allclose(y.cpu().numpy()[:, ::3, ::5, ::7], c["y_sub"], rtol=RTOL, atol=ATOL)

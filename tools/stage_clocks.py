@@ -1,30 +1,29 @@
 #!/usr/bin/env python
-"""Per-stage clock64() breakdown of the morphology kernel (debug aid)."""
+"""Per-stage clock64() breakdown of the fused morphology kernel (debug aid)."""
 import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-from mcaq_yolo_b200 import ops, _lib, constants as K
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from mcaq_yolo_b200 import ops, _lib, constants as K, modules as M
+from golden_util import weights
 lib = _lib.load()
-lib.mcaq_debug_stage_clocks.argtypes = [ctypes.c_void_p]
-lib.mcaq_debug_stage_clocks.restype = None
-names = ["S0-2 load/norm", "S3 adaptive", "zero hist", "S4 lbp+sobel", "S5 phi2/3", "S6 blur", "S7 otsu", "S8 mag",
-         "S9 nms", "S10 hyst", "S11 counts", "S11b boxes", "S12 phi"]
-B = 64
+names = ["S0-1 load/norm", "S3 adaptive", "S4 lbp+sobel", "S5 phi2/3", "S6 blur", "S7|S8 otsu|mag", "S9 nms",
+         "S10 hyst", "S11 counts", "S11b boxes", "S12 phi", "N1 complexity", "N2 mapper", "N3 softmask"]
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+a, m, q = M.build_fixture_modules(weights(), "cuda")
+cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_network(m.mapping_network), K.pack_soft_mask(q.soft_mask)
 for (C, H) in ((64, 80), (128, 40), (256, 20), (128, 160)):
     x = (torch.randn(B, C, H, H, device="cuda") * 2).to(torch.bfloat16)
-    s, a, k = ops.reduce_planes(x)
+    s, ab, k = ops.reduce_planes(x)
     clk = torch.zeros(B, 16, dtype=torch.int64, device="cuda")
     lib.mcaq_debug_stage_clocks(clk.data_ptr())
     for _ in range(3):
-        ops.morph_phi(s, C, 8, K.device_constants("cuda"))
+        ops.morph_fused(s, ab, C, 8, cm, mp, sm, 1.0)
     torch.cuda.synchronize()
-    c = clk.cpu().numpy()
-    d = (c[:, 1:13] - c[:, 0:12]).mean(0)
-    tot = (c[:, 12] - c[:, 0]).mean()
-    print(f"C={C} H={H}: total {tot:.0f} cycles")
-    for n, v in zip(names[1:], d[1:] if False else d[0:]):
-        pass
-    for i in range(12):
-        print(f"   {names[i]:16s} {d[i]:9.0f} cyc  {100 * d[i] / tot:5.1f}%")
     lib.mcaq_debug_stage_clocks(None)
+    c = clk.cpu().numpy()
+    d = (c[:, 1:15] - c[:, 0:14]).mean(0)
+    tot = (c[:, 14] - c[:, 0]).mean()
+    print(f"C={C} H={H}: total {tot:.0f} cycles = {tot / 1.965e3:.1f} us @1.965GHz")
+    for i in range(14):
+        print(f"   {names[i]:16s} {d[i]:9.0f} cyc  {100 * d[i] / tot:5.1f}%")
