@@ -98,6 +98,14 @@ __device__ __forceinline__ void sobel_at(const float* p, int r, int x, int Hc, i
   gy = fmaf(v[2][2], 1.f, c);
 }
 
+// RN(x / d) with a precomputed rinv = RN(1/d): Markstein's correction in the normal range (swept
+// against div.rn in tests/test_gpu_division.py), plain division for zero / tiny / huge numerators.
+__device__ __forceinline__ float div_exact(float x, float d, float rinv) {
+  const float ax = fabsf(x);
+  if (ax >= 1e-30f && ax < 1e27f) return div_markstein(x, d, rinv);
+  return __fdiv_rn(x, d);
+}
+
 // direction bin of the NMS (morphology.py:430-444).  Slope tests with a 1e-5 relative guard band
 // decide all but boundary cases; those take the literal atan2f path.
 __device__ __forceinline__ int nms_bin(float gx, float gy) {
@@ -132,6 +140,8 @@ morph_fused_kernel(const FusedArgs A) {
   float* bits_s = cfin + g.ntiles;                            // [ntiles] bits
   int* hist = reinterpret_cast<int*>(bits_s + g.ntiles);      // [256]
   float* red = reinterpret_cast<float*>(hist + 256);          // [64]
+  float* lutn = red + 64;                                     // [260] log(N + 1)
+  float* lutp = lutn + 260;                                   // [tile^2 + 1] log2(k / tile^2 + 1e-10)
   int* lbp_hist = reinterpret_cast<int*>(P0 + g.off_lbp);     // [ntiles][10]
   float* rowsum = P0 + g.off_rowsum;                          // [Hc][wt][4]
 
@@ -144,6 +154,11 @@ morph_fused_kernel(const FusedArgs A) {
   long long* clk = A.clk;
 #define STAGE_CLOCK(k) do { if (clk && tid == 0) clk[(long long)b * 16 + (k)] = clock64(); } while (0)
   STAGE_CLOCK(0);
+  {
+    const float* src = g.tile == 4 ? kc::LOG2P_4 : (g.tile == 8 ? kc::LOG2P_8 : (g.tile == 16 ? kc::LOG2P_16 : kc::LOG2P_32));
+    for (int i = tid; i < 257; i += NT) lutn[i] = __ldg(kc::LOGN1 + i);
+    for (int i = tid; i <= g.tile * g.tile; i += NT) lutp[i] = __ldg(src + i);
+  }
 
   // K1 -> K3 hand-off of the per-channel ranges: decode the atomics' integer keys to floats and
   // re-arm the keys for the next sweep (stream order: K1 done, K3 not started)
@@ -159,6 +174,7 @@ morph_fused_kernel(const FusedArgs A) {
   // ---- S0: gray = sum / C over the cropped plane, per-image min / max --------------------
   const float* sp = A.sum_plane + (long long)b * g.H * g.W;
   const float fC = (float)g.C;
+  const float rC = __frcp_rn(fC);
   float lmin = INFINITY, lmax = -INFINITY;
   for (int i0 = tid; i0 < NP; i0 += 4 * NT) {
     float v[4];
@@ -171,7 +187,7 @@ morph_fused_kernel(const FusedArgs A) {
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * NT;
       if (i < NP) {
-        const float q = __fdiv_rn(v[u], fC);
+        const float q = div_exact(v[u], fC, rC);
         P0[i] = q;
         lmin = fminf(lmin, q);
         lmax = fmaxf(lmax, q);
@@ -189,8 +205,9 @@ morph_fused_kernel(const FusedArgs A) {
   for (int w = 1; w < nwarps; ++w) { gmin = fminf(gmin, red[w]); gmax = fmaxf(gmax, red[32 + w]); }
   // ---- S1: normalise (morphology.py:378-383), P1 = 255 * gray ------------------------------
   const float den = __fadd_rn(__fsub_rn(gmax, gmin), 1e-8f);
+  const float rden = __frcp_rn(den);
   for (int i = tid; i < NP; i += NT) {
-    const float v = __fdiv_rn(__fsub_rn(P0[i], gmin), den);
+    const float v = div_exact(__fsub_rn(P0[i], gmin), den, rden);
     P0[i] = v;
     P1[i] = __fmul_rn(v, 255.f);
     if (A.gray_dbg) A.gray_dbg[(long long)b * NP + i] = v;
@@ -241,31 +258,43 @@ morph_fused_kernel(const FusedArgs A) {
   __syncthreads();
 
   // ---- S4: uniform-LBP histograms + Sobel(gray) tile-row sums ------------------------------
+  //      one 3x3 neighbourhood load serves both: LBP sees replicate borders, Sobel zero borders
   for (int slot = warp; slot < NW; slot += nwarps) {
     const int r = slot / WW, k = slot - r * WW;
     const int x = 32 * k + lane;
     const bool valid = x < Wc;
     float gx = 0.f, gy = 0.f;
+    int key = -1;
     if (valid) {
-      const float c = P0[r * Wc + x];
-      const int ru = clampi(r - 1, 0, Hc - 1), rd = clampi(r + 1, 0, Hc - 1);
-      const int xl = clampi(x - 1, 0, Wc - 1), xr = clampi(x + 1, 0, Wc - 1);
+      const bool up = r > 0, dn = r + 1 < Hc, lf = x > 0, rt = x + 1 < Wc;
+      const float* r0p = P0 + (up ? r - 1 : r) * Wc;
+      const float* r1p = P0 + r * Wc;
+      const float* r2p = P0 + (dn ? r + 1 : r) * Wc;
+      const int xl = lf ? x - 1 : x, xr = rt ? x + 1 : x;
+      const float v00 = r0p[xl], v01 = r0p[x], v02 = r0p[xr];
+      const float v10 = r1p[xl], c = r1p[x], v12 = r1p[xr];
+      const float v20 = r2p[xl], v21 = r2p[x], v22 = r2p[xr];
       // neighbour order (-1,-1),(-1,0),(-1,1),(0,1),(1,1),(1,0),(1,-1),(0,-1)  (morphology.py:634)
-      uint32_t code = 0;
-      code |= (P0[ru * Wc + xl] >= c) << 0;
-      code |= (P0[ru * Wc + x] >= c) << 1;
-      code |= (P0[ru * Wc + xr] >= c) << 2;
-      code |= (P0[r * Wc + xr] >= c) << 3;
-      code |= (P0[rd * Wc + xr] >= c) << 4;
-      code |= (P0[rd * Wc + x] >= c) << 5;
-      code |= (P0[rd * Wc + xl] >= c) << 6;
-      code |= (P0[r * Wc + xl] >= c) << 7;
+      uint32_t code = (uint32_t)(v00 >= c) | ((uint32_t)(v01 >= c) << 1) | ((uint32_t)(v02 >= c) << 2) |
+                      ((uint32_t)(v12 >= c) << 3) | ((uint32_t)(v22 >= c) << 4) | ((uint32_t)(v21 >= c) << 5) |
+                      ((uint32_t)(v20 >= c) << 6) | ((uint32_t)(v10 >= c) << 7);
       const uint32_t rot = ((code << 1) | (code >> 7)) & 0xffu;
-      const int trans = __popc(code ^ rot);
-      const int label = trans <= 2 ? __popc(code) : 9;
-      const int t = (r >> tshift) * wt + (x >> tshift);
-      atomicAdd(&lbp_hist[t * 10 + label], 1);
-      sobel_at<false>(P0, r, x, Hc, Wc, gx, gy);
+      const int label = __popc(code ^ rot) <= 2 ? __popc(code) : 9;
+      key = ((r >> tshift) * wt + (x >> tshift)) * 10 + label;
+      // Sobel with zero padding: FMA chain over taps in row-major order (zero taps are no-ops)
+      const float z00 = (up && lf) ? v00 : 0.f, z01 = up ? v01 : 0.f, z02 = (up && rt) ? v02 : 0.f;
+      const float z10 = lf ? v10 : 0.f, z12 = rt ? v12 : 0.f;
+      const float z20 = (dn && lf) ? v20 : 0.f, z21 = dn ? v21 : 0.f, z22 = (dn && rt) ? v22 : 0.f;
+      float a = __fmul_rn(z00, -1.f);
+      a = fmaf(z02, 1.f, a); a = fmaf(z10, -2.f, a); a = fmaf(z12, 2.f, a); a = fmaf(z20, -1.f, a);
+      gx = fmaf(z22, 1.f, a);
+      float cc = __fmul_rn(z00, -1.f);
+      cc = fmaf(z01, -2.f, cc); cc = fmaf(z02, -1.f, cc); cc = fmaf(z20, 1.f, cc); cc = fmaf(z21, 2.f, cc);
+      gy = fmaf(z22, 1.f, cc);
+    }
+    {   // warp-aggregated histogram update: one shared-memory atomic per distinct (tile, label)
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(&lbp_hist[key], __popc(peers));
     }
     // sequential left-to-right sum of each tile-row segment (leaders: lane % tile == 0)
     float s0 = gx, s1 = __fmul_rn(gx, gx), s2 = gy, s3 = __fmul_rn(gy, gy);
@@ -284,7 +313,6 @@ morph_fused_kernel(const FusedArgs A) {
 
   // ---- S5: phi2 (LBP entropy, morphology.py:648-652) and phi3 (654-670) per tile -----------
   {
-    const float* lut = tile == 4 ? kc::LOG2P_4 : (tile == 8 ? kc::LOG2P_8 : (tile == 16 ? kc::LOG2P_16 : kc::LOG2P_32));
     for (int t = tid; t < g.ntiles; t += NT) {
       const int ty = t / wt, tx = t - ty * wt;
       float ent = 0.f;
@@ -293,7 +321,7 @@ morph_fused_kernel(const FusedArgs A) {
         const int cnt = lbp_hist[t * 10 + kk];
         if (A.lbp_dbg) A.lbp_dbg[((long long)b * g.ntiles + t) * 10 + kk] = cnt;
         const float p = __fdiv_rn((float)cnt, ntile2);
-        ent = __fadd_rn(ent, __fmul_rn(p, __ldg(lut + cnt)));      // log2(p + 1e-10)
+        ent = __fadd_rn(ent, __fmul_rn(p, lutp[cnt]));             // log2(p + 1e-10)
       }
       phis[t * 5 + 1] = __fdiv_rn(-ent, kc::LOG2_10);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -342,16 +370,18 @@ morph_fused_kernel(const FusedArgs A) {
         }
       }
     }
-    if (valid) {
 #pragma unroll
-      for (int j = 0; j < RT; ++j) {
+    for (int j = 0; j < RT; ++j) {
+      int bin = -1;
+      if (valid) {
         P1[(r0 + j) * Wc + x] = acc[j];
         if (acc[j] >= 0.f && acc[j] <= 1.f) {          // torch.histc(bins=256, min=0, max=1)
-          int bin = (int)__fmul_rn(acc[j], 256.f);
+          bin = (int)__fmul_rn(acc[j], 256.f);
           if (bin == 256) bin = 255;
-          atomicAdd(&hist[bin], 1);
         }
       }
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);     // smooth images: many equal bins
+      if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
     }
   }
   __syncthreads();
@@ -410,12 +440,21 @@ morph_fused_kernel(const FusedArgs A) {
       red[1] = __int_as_float(best_i);
     }
   } else {
-    // ---- S8: L1 gradient magnitude of Sobel(255 * blur) -> P0 (morphology.py:496-497) ------
-    for (int i = tid - 32; i < NP; i += NT - 32) {
-      const int r = i / Wc, x = i - r * Wc;
-      float gx, gy;
-      sobel_at<true>(P1, r, x, Hc, Wc, gx, gy);
-      P0[i] = __fadd_rn(fabsf(gx), fabsf(gy));
+    // ---- S8: L1 gradient magnitude of Sobel(255 * blur) -> P0 (morphology.py:496-497) and the
+    //      NMS direction bin (2 bits per pixel, parked in the not-yet-used STRONG/WEAK planes)
+    for (int slot = warp - 1; slot < NW; slot += nwarps - 1) {
+      const int r = slot / WW, k = slot - r * WW;
+      const int x = 32 * k + lane;
+      int bin = 0;
+      if (x < Wc) {
+        float gx, gy;
+        sobel_at<true>(P1, r, x, Hc, Wc, gx, gy);
+        P0[r * Wc + x] = __fadd_rn(fabsf(gx), fabsf(gy));
+        bin = nms_bin(gx, gy);
+      }
+      const uint32_t d0 = __ballot_sync(0xffffffffu, bin & 1);
+      const uint32_t d1 = __ballot_sync(0xffffffffu, bin & 2);
+      if (lane == 0) { STRONG[slot] = d0; WEAK[slot] = d1; }
     }
   }
   __syncthreads();
@@ -428,13 +467,12 @@ morph_fused_kernel(const FusedArgs A) {
   for (int slot = warp; slot < NW; slot += nwarps) {
     const int r = slot / WW, k = slot - r * WW;
     const int x = 32 * k + lane;
+    const uint32_t d0 = STRONG[slot], d1 = WEAK[slot];     // direction bits of this slot (same warp rewrites it)
     bool st = false, wk = false;
     if (x < Wc) {
       const float mag = P0[r * Wc + x];
       if (mag > thr_lo) {                           // below the weak threshold the pixel is irrelevant
-        float gx, gy;
-        sobel_at<true>(P1, r, x, Hc, Wc, gx, gy);
-        const int bin = nms_bin(gx, gy);
+        const int bin = ((d0 >> lane) & 1) | (((d1 >> lane) & 1) << 1);
         const int dy1 = bin == 0 ? 0 : -1;
         const int dx1 = bin == 0 ? 1 : (bin == 1 ? 1 : (bin == 2 ? 0 : -1));
         const float n1 = P0[clampi(r + dy1, 0, Hc - 1) * Wc + clampi(x + dx1, 0, Wc - 1)];
@@ -444,6 +482,7 @@ morph_fused_kernel(const FusedArgs A) {
         wk = nms > thr_lo;
       }
     }
+    __syncwarp();
     const uint32_t ws = __ballot_sync(0xffffffffu, st);
     const uint32_t ww = __ballot_sync(0xffffffffu, wk);
     if (lane == 0) { STRONG[slot] = ws; WEAK[slot] = ww; }
@@ -552,7 +591,7 @@ morph_fused_kernel(const FusedArgs A) {
     const int* a = acc + t * 9;
     const int S = g.S;
     float y[5];
-    for (int i = 0; i < S; ++i) y[i] = __ldg(kc::LOGN1 + a[4 + i]);            // log(N_s + 1)
+    for (int i = 0; i < S; ++i) y[i] = lutn[a[4 + i]];                         // log(N_s + 1)
     float w_sum = 0.f, sx = 0.f, sy = 0.f;
     for (int i = 0; i < S; ++i) {
       w_sum = __fadd_rn(w_sum, kc::FW[i]);
@@ -607,11 +646,11 @@ morph_fused_kernel(const FusedArgs A) {
   float* scratch = P0;
   {
     float* w = scratch;
-    float* wbuf = w + CMLP_SMEM_FLOATS;
-    float* craw = wbuf + nwarps * 96;
+    float* act = w + CMLP_SMEM_FLOATS;
+    float* craw = scratch + cpx_scratch_floats(g.ntiles);
     complexity_load_weights(A.cmlp, w);
     __syncthreads();
-    complexity_block(phi8, g.ht, g.wt, w, wbuf, craw, cfin,
+    complexity_block(phi8, g.ht, g.wt, w, act, craw, cfin,
                      A.complexity_raw ? A.complexity_raw + (long long)b * g.ntiles : nullptr,
                      A.complexity ? A.complexity + (long long)b * g.ntiles : nullptr);
   }
@@ -626,11 +665,10 @@ morph_fused_kernel(const FusedArgs A) {
                         A.eps_spread, bits_s, bout);
   } else {
     float* w = scratch;
-    float* wbuf = w + MAPPER_SMEM_FLOATS;
-    float* zbuf = wbuf + nwarps * 128;
+    float* act = w + MAPPER_SMEM_FLOATS;
     mapper_load_weights(A.mapper, w);
     __syncthreads();
-    mapper_mlp_block(cfin, g.ntiles, w, wbuf, zbuf, A.temperature, A.use_t, A.continuous, A.lo, A.hi, bits_s, bout);
+    mapper_mlp_block(cfin, g.ntiles, w, act, A.temperature, A.use_t, A.continuous, A.lo, A.hi, bits_s, bout);
   }
   STAGE_CLOCK(13);
   if (!A.softmask || !A.abs_plane) return;
@@ -674,17 +712,18 @@ static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size, b
     tail += (lbp_w + 3) & ~3LL;
   }
   if (nets) {
-    const int nw = threads / 32;
+    (void)threads;
     int npow2 = 1;
     while (npow2 < g.ntiles) npow2 <<= 1;
-    long long need = CMLP_SMEM_FLOATS + nw * 96 + g.ntiles;
-    need = max_i((int)need, MAPPER_SMEM_FLOATS + nw * 128 + g.ntiles);
+    long long need = CMLP_SMEM_FLOATS + max_i(CPX_ACT_FLOATS, 25 * g.ntiles) + g.ntiles;
+    need = max_i((int)need, MAPPER_SMEM_FLOATS + MAP_ACT_FLOATS);
     need = max_i((int)need, npow2);
     need = max_i((int)need, 196 + 3 * g.ntiles + H * g.wt + 32);
     if (tail < need) tail = (need + 3) & ~3LL;
   }
   g.off_tail = (int)tail;
-  const long long words = tail + 3 * NW + (long long)g.ntiles * (5 + 8 + 1 + 1) + 256 + 64;
+  const long long words = tail + 3 * NW + (long long)g.ntiles * (5 + 8 + 1 + 1) + 256 + 64 + 260 +
+                          g.tile * g.tile + 4;
   return words * 4;
 }
 

@@ -13,13 +13,13 @@ complexity_kernel(const float* __restrict__ phi, int ht, int wt, const float* __
   extern __shared__ float sm[];
   const int ntiles = ht * wt;
   float* w = sm;
-  float* wbuf = w + CMLP_SMEM_FLOATS;
-  float* craw = wbuf + TN_WARPS * 96;
+  float* act = w + CMLP_SMEM_FLOATS;
+  float* craw = sm + cpx_scratch_floats(ntiles);
   float* cfin = craw + ntiles;
   const int b = blockIdx.x;
   complexity_load_weights(cmlp, w);
   __syncthreads();
-  complexity_block(phi + (long long)b * ntiles * 8, ht, wt, w, wbuf, craw, cfin,
+  complexity_block(phi + (long long)b * ntiles * 8, ht, wt, w, act, craw, cfin,
                    raw_out ? raw_out + (long long)b * ntiles : nullptr, out + (long long)b * ntiles);
 }
 
@@ -28,13 +28,12 @@ mapper_mlp_kernel(const float* __restrict__ cmap, int ntiles, const float* __res
                   int use_t, int continuous, float lo, float hi, float* __restrict__ out) {
   extern __shared__ float sm[];
   float* w = sm;
-  float* wbuf = w + MAPPER_SMEM_FLOATS;
-  float* zbuf = wbuf + TN_WARPS * 128;
-  float* bits_s = zbuf + ntiles;
+  float* act = w + MAPPER_SMEM_FLOATS;
+  float* bits_s = act + MAP_ACT_FLOATS;
   const int b = blockIdx.x;
   mapper_load_weights(mp, w);
   __syncthreads();
-  mapper_mlp_block(cmap + (long long)b * ntiles, ntiles, w, wbuf, zbuf, temperature, use_t, continuous, lo, hi,
+  mapper_mlp_block(cmap + (long long)b * ntiles, ntiles, w, act, temperature, use_t, continuous, lo, hi,
                    bits_s, out + (long long)b * ntiles);
 }
 
@@ -67,7 +66,8 @@ extern "C" int mcaq_complexity(const float* phi, int B, int ht, int wt, const fl
                                float* complexity_raw, float* complexity, void* stream) {
   (void)consts;   // the stencil constants are compiled in (mcaq_consts.cuh); kept for ABI stability
   if (!phi || !cmlp || !complexity || B <= 0 || ht <= 0 || wt <= 0) return MCAQ_EINVAL;
-  const size_t smem = (size_t)(CMLP_SMEM_FLOATS + TN_WARPS * 96 + 2 * ht * wt) * 4;
+  const int nt_ = ht * wt;
+  const size_t smem = (size_t)(CMLP_SMEM_FLOATS + (CPX_ACT_FLOATS > 25 * nt_ ? CPX_ACT_FLOATS : 25 * nt_) + 2 * nt_) * 4;
   if (smem > 200 * 1024) return MCAQ_ETOOBIG;
   if (smem > 48 * 1024) cudaFuncSetAttribute(complexity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   complexity_kernel<<<B, TN_THREADS, smem, (cudaStream_t)stream>>>(phi, ht, wt, cmlp, complexity_raw, complexity);
@@ -82,7 +82,7 @@ extern "C" int mcaq_bit_mapper(const float* complexity, int B, int ht, int wt, c
   const int ntiles = ht * wt;
   cudaStream_t st = (cudaStream_t)stream;
   if (mapper) {
-    const size_t smem = (size_t)(MAPPER_SMEM_FLOATS + TN_WARPS * 128 + 2 * ntiles) * 4;
+    const size_t smem = (size_t)(MAPPER_SMEM_FLOATS + MAP_ACT_FLOATS + ntiles) * 4;
     if (smem > 200 * 1024) return MCAQ_ETOOBIG;
     if (smem > 48 * 1024) cudaFuncSetAttribute(mapper_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     mapper_mlp_kernel<<<B, TN_THREADS, smem, st>>>(complexity, ntiles, mapper, temperature, use_temperature,

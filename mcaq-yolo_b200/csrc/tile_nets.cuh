@@ -24,9 +24,47 @@ __device__ __forceinline__ float warp_tree_sum(float v) {
   return v;
 }
 
+// out(t, m) = sum_k in[t][k] * Wt[k][m] as an FMA chain over k from 0 (nn.Linear's order), for nb
+// tiles.  A thread owns unit m for TT = 8 consecutive tiles: per 4 k it issues 8 LDS.128 of
+// activations (warp-broadcast: the 32 lanes of a warp share the tile group) and 4 conflict-free
+// weight loads for 32 FMAs.  in rows must be 16-byte aligned (in_stride % 4 == 0).
+template <int K_IN, int N_OUT, typename Epi>
+__device__ __forceinline__ void dense_tiled(const float* in, int in_stride, int nb, const float* Wt, Epi epi) {
+  constexpr int TT = 8;
+  static_assert(K_IN % 4 == 0 && N_OUT % 32 == 0, "dense_tiled shape");
+  const int ngroups = (nb + TT - 1) / TT;
+  for (int task = threadIdx.x; task < ngroups * N_OUT; task += blockDim.x) {
+    const int gi = task / N_OUT, m = task - gi * N_OUT;
+    const int tb = gi * TT;
+    float acc[TT];
+    const float4* ip[TT];
+#pragma unroll
+    for (int j = 0; j < TT; ++j) {
+      acc[j] = 0.f;
+      ip[j] = reinterpret_cast<const float4*>(in + min(tb + j, nb - 1) * in_stride);
+    }
+#pragma unroll 2
+    for (int k4 = 0; k4 < K_IN / 4; ++k4) {
+      const float w0 = Wt[(4 * k4 + 0) * N_OUT + m], w1 = Wt[(4 * k4 + 1) * N_OUT + m];
+      const float w2 = Wt[(4 * k4 + 2) * N_OUT + m], w3 = Wt[(4 * k4 + 3) * N_OUT + m];
+#pragma unroll
+      for (int j = 0; j < TT; ++j) {
+        const float4 a = ip[j][k4];
+        acc[j] = fmaf(a.x, w0, acc[j]);
+        acc[j] = fmaf(a.y, w1, acc[j]);
+        acc[j] = fmaf(a.z, w2, acc[j]);
+        acc[j] = fmaf(a.w, w3, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < TT; ++j)
+      if (tb + j < nb) epi(tb + j, m, acc[j]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // complexity MLP 8 -> 64 (LN, ReLU) -> 32 (LN, ReLU) -> 1, sigmoid; 5x5 bilateral; clamp
-// smem need: CMLP_SMEM_FLOATS + nwarps*96 + 2*ntiles
+// smem need: cpx_scratch_floats(ntiles) + 2*ntiles
 // ---------------------------------------------------------------------------------------------
 constexpr int CMLP_SMEM_FLOATS = 512 + 192 + 2048 + 96 + 36;   // W0t b0 g1 be1 | W3t b3 g4 be4 | W6 b6
 
@@ -39,8 +77,20 @@ __device__ __forceinline__ void complexity_load_weights(const float* __restrict_
   for (int i = tid; i < 33; i += NT) w[2848 + i] = __ldg(cmlp + 2848 + i);
 }
 
-// phi: [ntiles][8] (global or shared).  craw/cfin: [ntiles] shared.  Weights already loaded into w.
-__device__ __forceinline__ void complexity_block(const float* phi, int ht, int wt, const float* w, float* wbuf,
+// Tiles are processed in batches of NET_TB; within a batch every (tile, unit) output is one
+// thread's FMA chain, so the dense layers run at CTA width instead of one warp per tile.
+constexpr int NET_TB = 128;
+constexpr int ROW64 = 68, ROW32 = 36;                  // padded, 16-byte aligned activation rows
+constexpr int CPX_ACT_FLOATS = NET_TB * (ROW64 + ROW32);   // h1 [TB][68], h2 [TB][36]
+
+__device__ __forceinline__ int cpx_scratch_floats(int ntiles) {
+  const int act = CPX_ACT_FLOATS, bil = ntiles * 25;
+  return CMLP_SMEM_FLOATS + (act > bil ? act : bil);
+}
+
+// phi: [ntiles][8] (global or shared).  craw/cfin: [ntiles] shared.  Weights already loaded into w;
+// act: scratch of max(CPX_ACT_FLOATS, 25*ntiles) floats.
+__device__ __forceinline__ void complexity_block(const float* phi, int ht, int wt, const float* w, float* act,
                                                  float* craw, float* cfin, float* __restrict__ raw_out,
                                                  float* __restrict__ out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
@@ -55,57 +105,70 @@ __device__ __forceinline__ void complexity_block(const float* phi, int ht, int w
   const float* be4 = w + 2816;
   const float* W6 = w + 2848;
   const float b6 = w[2880];
-  float* h1 = wbuf + warp * 96;
-  float* h2 = h1 + 64;
-  for (int t = warp; t < ntiles; t += nwarps) {
-    float in[8];
+  float* h1 = act;                       // [TB][65]
+  float* h2 = act + NET_TB * ROW64;      // [TB][36]
+  for (int t0 = 0; t0 < ntiles; t0 += NET_TB) {
+    const int nb = min(NET_TB, ntiles - t0);
+    // layer 1: 8 -> 64
+    for (int o = tid; o < nb * 64; o += NT) {
+      const int t = o >> 6, m = o & 63;
+      const float* in = phi + (t0 + t) * 8;
+      float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) in[k] = phi[t * 8 + k];
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      a0 = fmaf(in[k], W0t[k * 64 + lane], a0);
-      a1 = fmaf(in[k], W0t[k * 64 + lane + 32], a1);
+      for (int k = 0; k < 8; ++k) acc = fmaf(in[k], W0t[k * 64 + m], acc);
+      h1[t * ROW64 + m] = __fadd_rn(acc, b0[m]);
     }
-    a0 = __fadd_rn(a0, b0[lane]);
-    a1 = __fadd_rn(a1, b0[lane + 32]);
-    // LayerNorm(64), eps 1e-5
-    float mean = __fdiv_rn(warp_tree_sum(__fadd_rn(a0, a1)), 64.f);
-    float d0 = __fsub_rn(a0, mean), d1 = __fsub_rn(a1, mean);
-    float var = __fdiv_rn(warp_tree_sum(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1))), 64.f);
-    float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
-    h1[lane] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g1[lane]), be1[lane]), 0.f);
-    h1[lane + 32] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d1, rstd), g1[lane + 32]), be1[lane + 32]), 0.f);
-    __syncwarp();
-    float acc = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < 64; ++k) acc = fmaf(h1[k], W3t[k * 32 + lane], acc);
-    acc = __fadd_rn(acc, b3[lane]);
-    mean = __fdiv_rn(warp_tree_sum(acc), 32.f);
-    d0 = __fsub_rn(acc, mean);
-    var = __fdiv_rn(warp_tree_sum(__fmul_rn(d0, d0)), 32.f);
-    rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
-    h2[lane] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g4[lane]), be4[lane]), 0.f);
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    // LayerNorm(64) + ReLU, one warp per tile
+    for (int t = warp; t < nb; t += nwarps) {
+      const float a0 = h1[t * ROW64 + lane], a1 = h1[t * ROW64 + lane + 32];
+      const float mean = __fdiv_rn(warp_tree_sum(__fadd_rn(a0, a1)), 64.f);
+      const float d0 = __fsub_rn(a0, mean), d1 = __fsub_rn(a1, mean);
+      const float var = __fdiv_rn(warp_tree_sum(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1))), 64.f);
+      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
+      h1[t * ROW64 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g1[lane]), be1[lane]), 0.f);
+      h1[t * ROW64 + lane + 32] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d1, rstd), g1[lane + 32]), be1[lane + 32]), 0.f);
+    }
+    __syncthreads();
+    // layer 2: 64 -> 32, register tiled (8 tiles x 1 unit per thread)
+    dense_tiled<64, 32>(h1, ROW64, nb, W3t, [&](int t, int m, float acc) { h2[t * ROW32 + m] = __fadd_rn(acc, b3[m]); });
+    __syncthreads();
+    // LayerNorm(32) + ReLU
+    for (int t = warp; t < nb; t += nwarps) {
+      const float a0 = h2[t * ROW32 + lane];
+      const float mean = __fdiv_rn(warp_tree_sum(a0), 32.f);
+      const float d0 = __fsub_rn(a0, mean);
+      const float var = __fdiv_rn(warp_tree_sum(__fmul_rn(d0, d0)), 32.f);
+      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
+      h2[t * ROW32 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g4[lane]), be4[lane]), 0.f);
+    }
+    __syncthreads();
+    // layer 3: 32 -> 1 and sigmoid, one thread per tile
+    for (int t = tid; t < nb; t += NT) {
       float z = 0.f;
 #pragma unroll 8
-      for (int k = 0; k < 32; ++k) z = fmaf(h2[k], W6[k], z);
-      craw[t] = __fadd_rn(z, b6);                 // pre-sigmoid; finished below, one thread per tile
+      for (int k = 0; k < 32; ++k) z = fmaf(h2[t * ROW32 + k], W6[k], z);
+      const float c = sigmoid_exact(__fadd_rn(z, b6));
+      craw[t0 + t] = c;
+      if (raw_out) raw_out[t0 + t] = c;
     }
-    __syncwarp();
+    __syncthreads();
+  }
+  // 5x5 bilateral filter, replicate padding (morphology.py:309-354): range weights for all
+  // (tile, tap) pairs in parallel, then one thread per tile accumulates its 25 taps in order
+  float* wgt = act;                      // [ntiles][25]
+  for (int o = tid; o < ntiles * 25; o += NT) {
+    const int t = o / 25, tap = o - t * 25;
+    const int y = t / wt, x = t - y * wt;
+    const int ky = tap / 5, kx = tap - ky * 5;
+    const int yy = min(max(y + ky - 2, 0), ht - 1), xx = min(max(x + kx - 2, 0), wt - 1);
+    const float d = __fsub_rn(craw[yy * wt + xx], craw[t]);
+    const float arg = __fdiv_rn(-__fmul_rn(d, d), kc::BILAT_DEN);
+    wgt[o] = __fmul_rn(kc::BILAT[tap], (float)exp((double)arg));
   }
   __syncthreads();
-  for (int t = tid; t < ntiles; t += NT) {
-    const float c = sigmoid_exact(craw[t]);
-    craw[t] = c;
-    if (raw_out) raw_out[t] = c;
-  }
-  __syncthreads();
-  // 5x5 bilateral filter, replicate padding (morphology.py:309-354), then clamp to [0,1]
   for (int t = tid; t < ntiles; t += NT) {
     const int y = t / wt, x = t - y * wt;
-    const float c = craw[t];
     float num = 0.f, den = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) {
@@ -113,13 +176,9 @@ __device__ __forceinline__ void complexity_block(const float* phi, int ht, int w
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
         const int xx = min(max(x + kx - 2, 0), wt - 1);
-        const float p = craw[yy * wt + xx];
-        const float d = __fsub_rn(p, c);
-        const float arg = __fdiv_rn(-__fmul_rn(d, d), kc::BILAT_DEN);
-        const float rw = (float)exp((double)arg);
-        const float wgt = __fmul_rn(kc::BILAT[ky * 5 + kx], rw);
-        num = __fadd_rn(num, __fmul_rn(wgt, p));
-        den = __fadd_rn(den, wgt);
+        const float wg = wgt[t * 25 + ky * 5 + kx];
+        num = __fadd_rn(num, __fmul_rn(wg, craw[yy * wt + xx]));
+        den = __fadd_rn(den, wg);
       }
     }
     const float r = fminf(fmaxf(__fdiv_rn(num, __fadd_rn(den, 1e-8f)), 0.f), 1.f);
@@ -153,12 +212,13 @@ __device__ __forceinline__ void mapper_load_weights(const float* __restrict__ mp
   for (int i = tid; i < 33; i += NT) w[4576 + i] = __ldg(mp + 4576 + i);
 }
 
-// cmap: [ntiles] (global or shared); zbuf: [ntiles] shared scratch; bits_s: [ntiles] shared result
-// wbuf: nwarps*128 floats
-__device__ __forceinline__ void mapper_mlp_block(const float* cmap, int ntiles, const float* w, float* wbuf,
-                                                 float* zbuf, float temperature, int use_t, int continuous,
+constexpr int MAP_ACT_FLOATS = NET_TB * (4 + ROW32 + ROW64 + ROW32);   // zin [TB][4], g0 [TB][36], g1 [TB][68], g2 [TB][36]
+
+// cmap: [ntiles] (global or shared); act: MAP_ACT_FLOATS scratch; bits_s: [ntiles] shared result
+__device__ __forceinline__ void mapper_mlp_block(const float* cmap, int ntiles, const float* w, float* act,
+                                                 float temperature, int use_t, int continuous,
                                                  float lo, float hi, float* bits_s, float* __restrict__ out) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
+  const int tid = threadIdx.x, NT = blockDim.x;
   const float* W0 = w;
   const float* v0 = w + 96;
   const float* W3t = w + 192;
@@ -166,64 +226,50 @@ __device__ __forceinline__ void mapper_mlp_block(const float* cmap, int ntiles, 
   const float* W6t = w + 2432;
   const float* v6 = w + 4480;
   const float* W9 = w + 4576;
-  // z0 = [c, c^2, log1p(c)] per tile, one thread per tile (fp64 log1p)
-  for (int t = tid; t < ntiles; t += NT) {
-    const float c = fminf(fmaxf(cmap[t], 0.f), 1.f);
-    zbuf[t] = (float)log1p((double)c);
-  }
-  __syncthreads();
-  float* h0 = wbuf + warp * 128;
-  float* h1 = h0 + 32;
-  float* h2 = h1 + 64;
-  for (int t = warp; t < ntiles; t += nwarps) {
-    const float c = fminf(fmaxf(cmap[t], 0.f), 1.f);
-    const float z1 = __fmul_rn(c, c), z2 = zbuf[t];
-    {
-      float acc = __fmul_rn(c, W0[lane * 3 + 0]);
-      acc = fmaf(z1, W0[lane * 3 + 1], acc);
-      acc = fmaf(z2, W0[lane * 3 + 2], acc);
-      const float x = __fadd_rn(acc, v0[lane]);
-      h0[lane] = fmaxf(__fadd_rn(__fmul_rn(x, v0[32 + lane]), v0[64 + lane]), 0.f);
+  float* zin = act;                      // [TB][4]
+  float* g0 = zin + NET_TB * 4;          // [TB][32]
+  float* g1 = g0 + NET_TB * ROW32;       // [TB][68]
+  float* g2 = g1 + NET_TB * ROW64;       // [TB][36]
+  for (int t0 = 0; t0 < ntiles; t0 += NET_TB) {
+    const int nb = min(NET_TB, ntiles - t0);
+    for (int t = tid; t < nb; t += NT) {          // z0 = [c, c^2, log1p(c)]  (Eq.13)
+      const float c = fminf(fmaxf(cmap[t0 + t], 0.f), 1.f);
+      zin[t * 4 + 0] = c;
+      zin[t * 4 + 1] = __fmul_rn(c, c);
+      zin[t * 4 + 2] = (float)log1p((double)c);
     }
-    __syncwarp();
-    {
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) {
-        const float hv = h0[k];
-        a0 = fmaf(hv, W3t[k * 64 + lane], a0);
-        a1 = fmaf(hv, W3t[k * 64 + lane + 32], a1);
-      }
-      const float x0 = __fadd_rn(a0, v3[lane]), x1 = __fadd_rn(a1, v3[lane + 32]);
-      h1[lane] = fmaxf(__fadd_rn(__fmul_rn(x0, v3[64 + lane]), v3[128 + lane]), 0.f);
-      h1[lane + 32] = fmaxf(__fadd_rn(__fmul_rn(x1, v3[96 + lane]), v3[160 + lane]), 0.f);
+    __syncthreads();
+    for (int o = tid; o < nb * 32; o += NT) {     // 3 -> 32, BN, ReLU
+      const int t = o >> 5, m = o & 31;
+      float acc = __fmul_rn(zin[t * 4 + 0], W0[m * 3 + 0]);
+      acc = fmaf(zin[t * 4 + 1], W0[m * 3 + 1], acc);
+      acc = fmaf(zin[t * 4 + 2], W0[m * 3 + 2], acc);
+      const float x = __fadd_rn(acc, v0[m]);
+      g0[t * ROW32 + m] = fmaxf(__fadd_rn(__fmul_rn(x, v0[32 + m]), v0[64 + m]), 0.f);
     }
-    __syncwarp();
-    {
+    __syncthreads();
+    dense_tiled<32, 64>(g0, ROW32, nb, W3t, [&](int t, int m, float acc) {      // 32 -> 64, BN, ReLU
+      const float x = __fadd_rn(acc, v3[m]);
+      g1[t * ROW64 + m] = fmaxf(__fadd_rn(__fmul_rn(x, v3[64 + m]), v3[128 + m]), 0.f);
+    });
+    __syncthreads();
+    dense_tiled<64, 32>(g1, ROW64, nb, W6t, [&](int t, int m, float acc) {      // 64 -> 32, BN, ReLU
+      const float x = __fadd_rn(acc, v6[m]);
+      g2[t * ROW32 + m] = fmaxf(__fadd_rn(__fmul_rn(x, v6[32 + m]), v6[64 + m]), 0.f);
+    });
+    __syncthreads();
+    for (int t = tid; t < nb; t += NT) {          // 32 -> 1, sigmoid, Eq.17, temperature / STE
       float acc = 0.f;
 #pragma unroll 8
-      for (int k = 0; k < 64; ++k) acc = fmaf(h1[k], W6t[k * 32 + lane], acc);
-      const float x = __fadd_rn(acc, v6[lane]);
-      h2[lane] = fmaxf(__fadd_rn(__fmul_rn(x, v6[32 + lane]), v6[64 + lane]), 0.f);
+      for (int k = 0; k < 32; ++k) acc = fmaf(g2[t * ROW32 + k], W9[k], acc);
+      const float s = sigmoid_exact(__fadd_rn(acc, W9[32]));
+      const float bits = finish_bits(__fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), s)), temperature, use_t,
+                                     continuous, lo, hi);
+      bits_s[t0 + t] = bits;
+      if (out) out[t0 + t] = bits;
     }
-    __syncwarp();
-    if (lane == 0) {
-      float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) acc = fmaf(h2[k], W9[k], acc);
-      bits_s[t] = __fadd_rn(acc, W9[32]);          // logit; finished below
-    }
-    __syncwarp();
+    __syncthreads();
   }
-  __syncthreads();
-  for (int t = tid; t < ntiles; t += NT) {
-    const float s = sigmoid_exact(bits_s[t]);
-    const float bits = finish_bits(__fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), s)), temperature, use_t,
-                                   continuous, lo, hi);
-    bits_s[t] = bits;
-    if (out) out[t] = bits;
-  }
-  __syncthreads();
 }
 
 // torch.quantile(q, 'linear') on a sorted row: fp32 rank, torch.lerp formula
@@ -293,11 +339,23 @@ __device__ __forceinline__ void soft_mask_block(const float* bits /*[Ht*Wt], glo
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
   for (int i = tid; i < 195; i += NT) P[i] = __ldg(prm + i);
   const float fC = (float)C;
+  const float rC = __frcp_rn(fC);
   for (int i = tid; i < H * Wt; i += NT) {
     const int y = i / Wt, j = i - y * Wt;
     const int xs = (j * W) / Wt, xe = ((j + 1) * W + Wt - 1) / Wt;
     float s = 0.f;
-    for (int x = xs; x < xe; ++x) s = __fadd_rn(s, __fdiv_rn(__ldg(ap + y * W + x), fC));
+    for (int x0 = xs; x0 < xe; x0 += 8) {          // 8 independent loads, then the ordered sum
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (x0 + u < xe) ? __ldg(ap + y * W + x0 + u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (x0 + u < xe) {
+          const float av = fabsf(v[u]);
+          const float q = (av >= 1e-30f && av < 1e27f) ? div_markstein(v[u], fC, rC) : __fdiv_rn(v[u], fC);
+          s = __fadd_rn(s, q);
+        }
+    }
     rows[i] = s;
   }
   __syncthreads();
