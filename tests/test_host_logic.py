@@ -1,0 +1,171 @@
+"""CPU tests of the host side: interface parity with the reference modules (state_dict keys,
+constructor signatures), the generated constants header, batch sharding and the world-size-2
+range merge over gloo.  No kernel is launched here."""
+import inspect
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+from mcaq_yolo_b200 import constants as K
+from mcaq_yolo_b200 import modules as M
+import mcaq_oracle as o
+
+
+def _reference():
+    from ref_loader import load_reference, reference_root
+    if reference_root() is None:
+        pytest.skip("reference tree not mounted (GPU box): interface parity is pinned in the build container")
+    return load_reference()
+
+
+def test_state_dict_keys_match_reference():
+    """reference checkpoints must load -- same keys and shapes (incl. lazily created
+    running_min/max, quantization.py:297-312)."""
+    morph, ba, qz = _reference()
+    pairs = [
+        (morph.MorphologicalComplexityAnalyzer(device="cpu"), M.MorphologicalComplexityAnalyzer(device="cpu")),
+        (ba.ComplexityToBitMappingNetwork(), M.ComplexityToBitMappingNetwork()),
+        (qz.SpatialAdaptiveQuantization(), M.SpatialAdaptiveQuantization()),
+        (qz.LearnedSoftMask(), M.LearnedSoftMask()),
+    ]
+    for ref, mine in pairs:
+        rs, ms = ref.state_dict(), mine.state_dict()
+        assert list(rs.keys()) == list(ms.keys()), type(ref).__name__
+        for k in rs:
+            assert rs[k].shape == ms[k].shape and rs[k].dtype == ms[k].dtype, k
+        mine.load_state_dict(rs, strict=True)
+    # a calibrated reference quantizer (running stats present) loads strictly into a fresh native one
+    q = qz.SpatialAdaptiveQuantization()
+    q.train()
+    q(torch.randn(2, 4, 16, 16), torch.full((2, 4, 4), 4.0), training=True)
+    q.freeze_calibration()
+    mine = M.SpatialAdaptiveQuantization()
+    mine.load_state_dict(q.state_dict(), strict=True)
+    assert torch.equal(mine.running_min, q.running_min) and mine._is_frozen()
+    # soft-mask smoothing buffer and init are identical
+    assert torch.equal(qz.LearnedSoftMask().smooth_kernel, M.LearnedSoftMask().smooth_kernel)
+
+
+def test_constructor_and_forward_signatures_match_reference():
+    morph, ba, qz = _reference()
+    for ref, mine in ((morph.MorphologicalComplexityAnalyzer, M.MorphologicalComplexityAnalyzer),
+                      (ba.ComplexityToBitMappingNetwork, M.ComplexityToBitMappingNetwork),
+                      (ba.LinearBitMapper, M.LinearBitMapper),
+                      (qz.LearnedSoftMask, M.LearnedSoftMask)):
+        assert list(inspect.signature(ref.__init__).parameters) == list(inspect.signature(mine.__init__).parameters)
+        assert list(inspect.signature(ref.forward).parameters) == list(inspect.signature(mine.forward).parameters)
+    ref_q = list(inspect.signature(qz.SpatialAdaptiveQuantization.__init__).parameters)
+    my_q = list(inspect.signature(M.SpatialAdaptiveQuantization.__init__).parameters)
+    assert my_q[:len(ref_q)] == ref_q          # extra trailing kwargs: process_group, sync_ranges
+    for name in ("freeze_calibration", "update_running_stats", "enforce_weight_constraints", "score_image",
+                 "compute_phi_tiles", "_tile_size", "bilateral_filter", "create_augmented_features"):
+        assert any(hasattr(c, name) for c in (M.MorphologicalComplexityAnalyzer, M.ComplexityToBitMappingNetwork,
+                                              M.SpatialAdaptiveQuantization))
+
+
+def test_unsupported_variants_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        M.MorphologicalComplexityAnalyzer(device="cpu", metric_backend="cv2")
+    with pytest.raises(NotImplementedError):
+        M.SpatialAdaptiveQuantization(calibration_mode="percentile")
+    a = M.MorphologicalComplexityAnalyzer(device="cpu")
+    with pytest.raises(RuntimeError):
+        a(torch.rand(1, 3, 32, 32))              # CPU tensor: no fallback
+
+
+def test_tile_size_rule():
+    a = M.MorphologicalComplexityAnalyzer(device="cpu", grid_size=8)
+    for H in (640, 160, 80, 50, 40, 20, 7):
+        assert a._tile_size(H) == o.tile_size(H, 8)
+    assert [M.MorphologicalComplexityAnalyzer(device="cpu", grid_size=g)._tile_size(160) for g in (4, 8, 16)] == [32, 16, 8]
+
+
+def test_constant_block_and_packers_match_oracle():
+    c = K.constant_block()
+    assert np.array_equal(c[0:25], o.CANNY_BLUR.ravel()) and np.array_equal(c[25:146], o.ADAPT_BLUR.ravel())
+    assert np.array_equal(c[146:171], o.BILATERAL_SPATIAL.ravel())
+    _, x, w = o.fractal_tables(32)
+    assert np.array_equal(c[171:176], x) and np.array_equal(c[176:181], w)
+    assert c[181] == o.RAD2DEG and c[182] == o.FOUR_PI and c[183] == o.LOG2_10 and c[184] == o.BILATERAL_RANGE_DEN
+    m = M.ComplexityToBitMappingNetwork()
+    m.train()
+    m(torch.rand(4, 6, 6))                       # non-trivial BN running stats
+    m.eval()
+    packed = K.pack_mapping_network(m.mapping_network).numpy()
+    sd = {k: v.numpy() for k, v in m.state_dict().items()}
+    # BN fold equals the oracle's batch_norm_eval affine
+    x = np.linspace(-1, 1, 32, dtype=np.float32)[None, :]
+    ref = o.batch_norm_eval(x, sd["mapping_network.1.weight"], sd["mapping_network.1.bias"],
+                            sd["mapping_network.1.running_mean"], sd["mapping_network.1.running_var"])
+    alpha, beta = packed[128:160], packed[160:192]
+    assert np.array_equal((x * alpha).astype(np.float32) + beta, ref)
+    assert packed.size == K.MAPPER_FLOATS
+    assert K.pack_mapping_network(m.mapping_network) is K.pack_mapping_network(m.mapping_network)   # cached
+    with torch.no_grad():
+        m.mapping_network[0].weight.add_(1.0)
+    assert not np.array_equal(K.pack_mapping_network(m.mapping_network).numpy(), packed)             # invalidated
+
+
+def test_generated_consts_header_is_current():
+    import gen_consts_header
+    path = os.path.join(ROOT, "mcaq-yolo_b200", "csrc", "mcaq_consts.cuh")
+    assert open(path).read() == gen_consts_header.generate(), "run tools/gen_consts_header.py"
+
+
+def test_shard_batch_partitions():
+    for n, world in ((256, 8), (64, 3), (5, 8), (128, 2)):
+        spans = [M.shard_batch(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        from inputs import feature_map
+        x = feature_map("smooth", 6, 16, 24, 24, seed=3)
+        s, e = M.shard_batch(x.shape[0], rank, world)
+        mn, mx = o.channel_minmax(x[s:e])                     # this rank's shard
+        packed = torch.from_numpy(np.concatenate([mn, -mx]).astype(np.float32))
+        M.allreduce_ranges(packed)                            # the path's only collective
+        gmn, gmx = o.channel_minmax(x)
+        ok = np.array_equal(packed[:16].numpy(), gmn) and np.array_equal(-packed[16:].numpy(), gmx)
+        # per-image quantities need no exchange: a shard's phi equals the same rows of the full batch
+        phi_full = o.phi_tiles(x, 8)
+        ok = ok and np.array_equal(o.phi_tiles(x[s:e], 8), phi_full[s:e])
+        # with merged ranges the shard's codes equal the unsharded batch's codes
+        bm = np.full((x.shape[0], 6, 6), 5.0, np.float32)
+        _, codes_full = o.quantize_eval(x, bm, gmn, gmx, None)
+        _, codes_shard = o.quantize_eval(x[s:e], bm[s:e], packed[:16].numpy(), -packed[16:].numpy(), None)
+        ok = ok and np.array_equal(codes_shard, codes_full[s:e])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_range_merge_world_size_2_gloo():
+    """Batch sharded over 2 ranks: one MIN all-reduce of [min, -max] reproduces the unsharded
+    per-channel ranges, hence bit-identical codes (quantization.py:650-654 semantics kept)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
