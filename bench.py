@@ -174,7 +174,9 @@ def run_native(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the native arm)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    out_fd = os.dup(1)
     if world > 1:
+        os.dup2(2, 1)            # NCCL prints its version banner on stdout: keep stdout for the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     from mcaq_yolo_b200 import modules as M
     from mcaq_yolo_b200 import ops
@@ -208,9 +210,17 @@ def run_native(args):
     from mcaq_yolo_b200.fused import FusedHotPath
     hot = FusedHotPath(analyzer, mapper, quantizers, temperature=1.0, streams=not args.no_streams)
 
+    sharded = None
+    if world > 1 and not args.unfused:
+        # multi-rank: the range all-reduce is kept out of the captured graphs (fused.ShardedHotPath)
+        from mcaq_yolo_b200.fused import ShardedHotPath
+        sharded = ShardedHotPath(analyzer, mapper, quantizers, shapes, dev, 1.0)
+
     def step(feats):
         if args.unfused:
             return [M.mcaq_hook_forward(x, analyzer, mapper, q, temperature=1.0) for x, q in zip(feats, quantizers)]
+        if sharded is not None:
+            return sharded.run(feats)
         return hot.run(feats)
 
     def barrier():
@@ -227,7 +237,20 @@ def run_native(args):
         step(sets[0])
         launches_per_step = ops.LAUNCHES
         graphs = None
-        if not args.no_graph:
+        if sharded is not None:
+            seg = []
+            if not args.no_graph:
+                for s_ in sets:
+                    gA, gB1, gB2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gA):
+                        planes = sharded.sweep(s_)
+                    with torch.cuda.graph(gB1):
+                        nets_out = sharded.nets(s_, planes)
+                    with torch.cuda.graph(gB2):
+                        recs = sharded.quantize(s_, nets_out)
+                    seg.append((gA, gB1, gB2, planes, nets_out, recs))
+                graphs = seg
+        elif not args.no_graph:
             try:
                 graphs, keep = [], []
                 for s in sets:
@@ -238,13 +261,23 @@ def run_native(args):
                 for g in graphs:
                     g.replay()
                 torch.cuda.synchronize()
-            except Exception as e:       # capture unsupported (e.g. NCCL in graph): time eager launches
+            except Exception as e:       # capture unsupported: time eager launches
                 sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager\n")
                 graphs = None
                 torch.cuda.synchronize()
 
         def run_step(i):
-            if graphs is not None:
+            if sharded is not None:
+                if graphs is None:
+                    sharded.run(sets[i % INPUT_SETS])
+                    return
+                gA, gB1, gB2 = graphs[i % INPUT_SETS][:3]
+                gA.replay()
+                done = sharded.exchange()
+                gB1.replay()
+                torch.cuda.current_stream().wait_event(done)
+                gB2.replay()
+            elif graphs is not None:
                 graphs[i % INPUT_SETS].replay()
             else:
                 step(sets[i % INPUT_SETS])
@@ -394,7 +427,8 @@ def run_native(args):
                    "l2": "%d rotating input sets (%.0f MB) > 126 MB L2, no flush" % (INPUT_SETS, INPUT_SETS * esize * elems * B / 1e6),
                    "launch": ("cuda-graph replay" if graphs is not None else "eager")
                    + (", module-by-module" if args.unfused else ", fused K1/K2/K3 per scale")
-                   + ("" if args.no_streams or args.unfused else ", one stream per scale")},
+                   + ("" if args.no_streams or args.unfused or world > 1 else ", one stream per scale")
+                   + (", ranges all-reduce (NCCL, eager, side stream) between graph segments" if world > 1 else "")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": nsteps_e2e, "api": "FusedHotPath.run(feats) (the hook bodies install() registers), pinned host buffers"},
@@ -407,7 +441,8 @@ def run_native(args):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{nimg} images (2-image fp32 batches, same shapes), {dt:.1f} s, numpy oracle"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -16,6 +16,46 @@ from . import modules as M
 from . import ops
 
 
+def run_forked(tasks, side_streams):
+    """Run independent callables concurrently: task 0 on the current stream, task i on
+    side_streams[i-1], fork/join with events (works eagerly and under CUDA-graph capture).
+    Returns the list of results."""
+    n = len(tasks)
+    if n == 1 or not side_streams:
+        return [t() for t in tasks]
+    cur = torch.cuda.current_stream()
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    out = [None] * n
+    joins = []
+    for i in range(1, n):
+        st = side_streams[i - 1]
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            out[i] = tasks[i]()
+            ev = torch.cuda.Event()
+            ev.record(st)
+            joins.append(ev)
+    out[0] = tasks[0]()
+    for ev in joins:
+        cur.wait_event(ev)
+    return out
+
+
+def _record_on(cur, obj):
+    """Tensors produced on a side stream and consumed on `cur`: tell the allocator (eager mode)."""
+    if torch.cuda.is_current_stream_capturing():
+        return
+    if torch.is_tensor(obj):
+        obj.record_stream(cur)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_on(cur, v)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_on(cur, v)
+
+
 class ScaleWorkspace:
     """Per-scale persistent state of the fused path: the range keys K1 accumulates into.  They are
     armed once here; afterwards K2's first CTA decodes and re-arms them every step."""
@@ -148,3 +188,102 @@ class FusedHotPath:
                 for k in ("complexity", "bit_map", "features_q"):
                     rec[k].record_stream(cur)
         return out
+
+
+class ShardedHotPath:
+    """Batch-sharded variant for world_size > 1 (one process per GPU, images split by rank).
+
+    The only exchange the inference path needs is the per-channel range merge.  It is
+    kept OUT of the captured graphs and issued as one eager NCCL all-reduce(MIN) over a single
+    buffer holding all scales' packed ranges, on a side stream, overlapped with K2:
+
+        graph A : K1 + decode + re-arm keys, all scales          (ranges of this rank's shard)
+        eager   : side stream waits for A, all_reduce(MIN) of sum_s 2*C_s floats
+        graph B1: K2 for all scales (does not need the ranges)    <- overlaps the collective
+        eager   : main stream waits for the all-reduce
+        graph B2: K3 for all scales with the merged ranges
+    """
+
+    def __init__(self, analyzer, mapper, quantizers, shapes, device, temperature: float = 1.0, group=None):
+        self.analyzer, self.mapper, self.quantizers = analyzer, mapper, list(quantizers)
+        self.temperature, self.group = temperature, group
+        self.C = [c for c, _, _ in shapes]
+        self.off = [0]
+        for c in self.C:
+            self.off.append(self.off[-1] + 2 * c)
+        self.packed_all = torch.empty((self.off[-1],), device=device, dtype=torch.float32)
+        self.ws = [ScaleWorkspace(c, device) for c in self.C]
+        self.comm_stream = torch.cuda.Stream(device=device)
+        self.side = [torch.cuda.Stream(device=device) for _ in range(len(self.C) - 1)]
+
+    def packed(self, i):
+        return self.packed_all[self.off[i]:self.off[i + 1]]
+
+    @torch.no_grad()
+    def sweep(self, feats):
+        """Phase A: K1 per scale (one stream each), ranges decoded into the shared buffer, keys re-armed."""
+        def one(i, x):
+            B, C, H, W = x.shape
+            s = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
+            a = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
+            keys = self.ws[i].keys
+            ops._call("mcaq_reduce_planes", x.data_ptr(), ops._dtype_code(x), B, C, H, W, s.data_ptr(),
+                      a.data_ptr(), keys.data_ptr(), ops._stream())
+            ops._call("mcaq_ranges_decode", keys.data_ptr(), C, self.packed(i).data_ptr(), ops._stream())
+            ops._call("mcaq_ranges_reset", keys.data_ptr(), C, ops._stream())
+            return (s, a)
+        planes = run_forked([lambda i=i, x=x: one(i, x) for i, x in enumerate(feats)], self.side)
+        _record_on(torch.cuda.current_stream(), planes[1:])
+        return planes
+
+    def exchange(self):
+        """Eager collective on the side stream; returns the event the quantize phase must wait for."""
+        import torch.distributed as dist
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.comm_stream.wait_event(ready)
+        with torch.cuda.stream(self.comm_stream):
+            if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                dist.all_reduce(self.packed_all, op=dist.ReduceOp.MIN, group=self.group)
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        return done
+
+    @torch.no_grad()
+    def nets(self, feats, planes):
+        """Phase B1: K2 per scale (bit maps, masks); independent of the ranges."""
+        linear = isinstance(self.mapper, M.LinearBitMapper)
+
+        def one(i, x, s, a):
+            q = self.quantizers[i]
+            sm = q.soft_mask if q.smooth_transitions else None
+            return ops.morph_fused(s, a if sm is not None else None, x.shape[1], self.analyzer.grid_size,
+                                   K.pack_complexity_mlp(self.analyzer.complexity_mlp),
+                                   None if linear else K.pack_mapping_network(self.mapper.mapping_network),
+                                   None if sm is None else K.pack_soft_mask(sm), self.temperature, False, None,
+                                   self.mapper.min_bits, self.mapper.max_bits,
+                                   getattr(self.mapper, "eps_spread", 1e-3))
+        out = run_forked([lambda i=i, x=x, p=p: one(i, x, p[0], p[1])
+                          for i, (x, p) in enumerate(zip(feats, planes))], self.side)
+        _record_on(torch.cuda.current_stream(), out[1:])
+        return out
+
+    @torch.no_grad()
+    def quantize(self, feats, nets_out):
+        """Phase B2: K3 per scale with the merged ranges."""
+        def one(i, x, r):
+            y = ops.tile_quantize_ranges(x, r["bit_map"], self.packed(i), None, None, r["mask"])
+            return {"layer": i, "complexity": r["complexity"], "bit_map": r["bit_map"], "features_q": y}
+        recs = run_forked([lambda i=i, x=x, r=r: one(i, x, r)
+                           for i, (x, r) in enumerate(zip(feats, nets_out))], self.side)
+        _record_on(torch.cuda.current_stream(), recs[1:])
+        return recs
+
+    def run(self, feats):
+        """Eager composition of the four phases (graphs: see bench.py)."""
+        planes = self.sweep(feats)
+        done = self.exchange()
+        nets_out = self.nets(feats, planes)
+        torch.cuda.current_stream().wait_event(done)
+        return self.quantize(feats, nets_out)

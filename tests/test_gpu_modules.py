@@ -275,3 +275,37 @@ def test_install_registers_fused_hooks(M, W):
     assert len(aux) == 1 and aux[0]["layer"] == 1 and torch.equal(y, aux[0]["features_q"])
     assert np.array_equal(aux[0]["bit_map"].cpu().numpy(), c["bit_map_mlp"])
     np.testing.assert_allclose(y.cpu().numpy()[:, ::3, ::5, ::7], c["y_sub"], rtol=RTOL, atol=ATOL)
+
+
+def test_sharded_hot_path_single_rank_equals_fused(M, W):
+    """The multi-rank phase split (K1+decode | all-reduce | K2 | K3) with world_size 1 reproduces the
+    fused path bit for bit, eagerly and as three captured graphs."""
+    from mcaq_yolo_b200 import fused
+    names = ["c3_v8n_smooth", "c4_v8n_smooth", "c5_v8n_smooth"]
+    cases = [Case(n) for n in names]
+    feats = [torch.from_numpy(c.x()).cuda() for c in cases]
+    a, m, _ = M.build_fixture_modules(W, "cuda")
+    qs = [M.build_fixture_modules(W, "cuda")[2] for _ in names]
+    ref = fused.FusedHotPath(a, m, qs, streams=False).run(feats)
+    sh = fused.ShardedHotPath(a, m, qs, [(c.C, c.H, c.W) for c in cases], torch.device("cuda"))
+    out = sh.run(feats)
+    torch.cuda.synchronize()
+    for u, v in zip(ref, out):
+        assert torch.equal(u["features_q"], v["features_q"]) and torch.equal(u["bit_map"], v["bit_map"])
+    gA, gB1, gB2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.no_grad():
+        with torch.cuda.graph(gA):
+            planes = sh.sweep(feats)
+        with torch.cuda.graph(gB1):
+            nets_out = sh.nets(feats, planes)
+        with torch.cuda.graph(gB2):
+            recs = sh.quantize(feats, nets_out)
+    for _ in range(2):
+        gA.replay()
+        done = sh.exchange()
+        gB1.replay()
+        torch.cuda.current_stream().wait_event(done)
+        gB2.replay()
+    torch.cuda.synchronize()
+    for u, v in zip(ref, recs):
+        assert torch.equal(u["features_q"], v["features_q"]) and torch.equal(u["bit_map"], v["bit_map"])
