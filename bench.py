@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-streams", action="store_true", help="run the three scales on one stream")
     ap.add_argument("--unfused", action="store_true", help="module-by-module path (9 launches per scale)")
+    ap.add_argument("--nccl-in-graph", action="store_true", help="capture the range all-reduce inside one graph per step")
+    ap.add_argument("--sharded", action="store_true", help="use the multi-rank phase split even at world size 1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -211,7 +213,7 @@ def run_native(args):
     hot = FusedHotPath(analyzer, mapper, quantizers, temperature=1.0, streams=not args.no_streams)
 
     sharded = None
-    if world > 1 and not args.unfused:
+    if (world > 1 or args.sharded) and not args.unfused:
         # multi-rank: the range all-reduce is kept out of the captured graphs (fused.ShardedHotPath)
         from mcaq_yolo_b200.fused import ShardedHotPath
         sharded = ShardedHotPath(analyzer, mapper, quantizers, shapes, dev, 1.0)
@@ -237,7 +239,15 @@ def run_native(args):
         step(sets[0])
         launches_per_step = ops.LAUNCHES
         graphs = None
-        if sharded is not None:
+        if sharded is not None and args.nccl_in_graph and not args.no_graph:
+            graphs = []
+            keep = []
+            for s_ in sets:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    keep.append(sharded.run(s_))
+                graphs.append((g,))
+        elif sharded is not None:
             seg = []
             if not args.no_graph:
                 for s_ in sets:
@@ -270,6 +280,9 @@ def run_native(args):
             if sharded is not None:
                 if graphs is None:
                     sharded.run(sets[i % INPUT_SETS])
+                    return
+                if len(graphs[i % INPUT_SETS]) == 1:
+                    graphs[i % INPUT_SETS][0].replay()
                     return
                 gA, gB1, gB2 = graphs[i % INPUT_SETS][:3]
                 gA.replay()

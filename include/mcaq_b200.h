@@ -170,6 +170,10 @@ MCAQ_API int mcaq_selftest_division(const float* scales, int nscales, unsigned f
 /* debug: device buffer of 16 clock64() stamps per image written by mcaq_morph_phi (NULL disables) */
 MCAQ_API void mcaq_debug_stage_clocks(long long* dev_buf);
 
+/* debug / tuning: force the number of CTAs (cluster size 1, 2 or 4) an image is split over in the
+ * morphology kernel; 0 = automatic */
+MCAQ_API void mcaq_debug_cluster_split(int ns);
+
 /* tile size rule of the analyzer (morphology.py:359-376) */
 MCAQ_API int mcaq_tile_size(int H, int grid_size);
 

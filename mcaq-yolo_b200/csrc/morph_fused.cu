@@ -20,7 +20,11 @@
 // rows) with the taps as FFMA immediates (mcaq_consts.cuh), accumulation order per output =
 // row-major FMA chain from 0, exactly the oracle's.  Arithmetic is otherwise separately rounded
 // fp32; log tables are fp64-rounded literals; Otsu sums are exact in fp64.
+#include <cooperative_groups.h>
+
 #include "tile_nets.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mcaq {
 
@@ -32,7 +36,8 @@ struct MorphGeom {
   // shared-memory layout, offsets in 4-byte words
   int off_lbp;      // 10 ints per tile (inside P1 when it fits next to rowsum, else separate)
   int off_rowsum;   // Hc*wt float4, inside P1
-  int off_tail;     // BIN, STRONG, WEAK, phis5, phi8, cfin, bits, hist, red
+  int off_tail;     // BIN, STRONG, WEAK, phis5, phi8, cfin, bits, craw, act, mt, hist, hloc, red, mmx, luts
+  int ns;           // CTAs per image (thread-block cluster size): the image's tile rows are split
 };
 
 struct FusedArgs {
@@ -138,21 +143,41 @@ morph_fused_kernel(const FusedArgs A) {
   float* phi8 = phis + g.ntiles * 5;                          // [ntiles][8]
   float* cfin = phi8 + g.ntiles * 8;                          // [ntiles] complexity
   float* bits_s = cfin + g.ntiles;                            // [ntiles] bits
-  int* hist = reinterpret_cast<int*>(bits_s + g.ntiles);      // [256]
-  float* red = reinterpret_cast<float*>(hist + 256);          // [64]
-  float* lutn = red + 64;                                     // [260] log(N + 1)
+  float* craw_s = bits_s + g.ntiles;                          // [ntiles] complexity before the bilateral
+  float* act_s = craw_s + g.ntiles;                           // [ntiles] tile activity (soft mask)
+  float* mt_s = act_s + g.ntiles;                             // [ntiles] tile mask
+  int* hist = reinterpret_cast<int*>(mt_s + g.ntiles);        // [256] whole-image Otsu histogram
+  int* hloc = hist + 256;                                     // [256] this CTA's band
+  float* red = reinterpret_cast<float*>(hloc + 256);          // [64]
+  float* mmx = red + 64;                                      // [16] per-rank min/max | per-rank act max
+  float* lutn = mmx + 16;                                     // [260] log(N + 1)
   float* lutp = lutn + 260;                                   // [tile^2 + 1] log2(k / tile^2 + 1e-10)
   int* lbp_hist = reinterpret_cast<int*>(P0 + g.off_lbp);     // [ntiles][10]
   float* rowsum = P0 + g.off_rowsum;                          // [Hc][wt][4]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NT = blockDim.x, nwarps = NT >> 5;
-  const int b = blockIdx.x;
   const int tile = g.tile, Hc = g.Hc, Wc = g.Wc, WW = g.WW, wt = g.wt;
+  // an image is split over the ns CTAs of a thread-block cluster by tile rows; every CTA keeps
+  // full-size planes and all-gathers the bands the others produced through DSMEM
+  cg::cluster_group cl = cg::this_cluster();
+  const int ns = g.ns;
+  const int rank = ns > 1 ? (int)cl.block_rank() : 0;
+  const int b = blockIdx.x / ns;
+  const int tr0 = (g.ht * rank) / ns, tr1 = (g.ht * (rank + 1)) / ns;   // own tile rows
+  const int r_lo = tr0 * tile, r_hi = tr1 * tile;                       // own pixel rows
+  const int t_lo = tr0 * wt, t_hi = tr1 * wt;                           // own tiles
+  auto csync = [&]() { if (ns > 1) cl.sync(); else __syncthreads(); };
+  auto publish = [&](auto* base, int off, int n) {                      // my [off, off+n) -> every peer
+    for (int pr = 1; pr < ns; ++pr) {
+      auto* dst = cl.map_shared_rank(base, (rank + pr) % ns);
+      for (int i = tid; i < n; i += NT) dst[off + i] = base[off + i];
+    }
+  };
   const int tshift = 31 - __clz(tile);
   const float ntile2 = (float)(tile * tile);
   long long* clk = A.clk;
-#define STAGE_CLOCK(k) do { if (clk && tid == 0) clk[(long long)b * 16 + (k)] = clock64(); } while (0)
+#define STAGE_CLOCK(k) do { if (clk && tid == 0 && rank == 0) clk[(long long)b * 16 + (k)] = clock64(); } while (0)
   STAGE_CLOCK(0);
   {
     const float* src = g.tile == 4 ? kc::LOG2P_4 : (g.tile == 8 ? kc::LOG2P_8 : (g.tile == 16 ? kc::LOG2P_16 : kc::LOG2P_32));
@@ -162,7 +187,7 @@ morph_fused_kernel(const FusedArgs A) {
 
   // K1 -> K3 hand-off of the per-channel ranges: decode the atomics' integer keys to floats and
   // re-arm the keys for the next sweep (stream order: K1 done, K3 not started)
-  if (A.keys && b == 0) {
+  if (A.keys && blockIdx.x == 0) {
     for (int c = tid; c < g.C; c += NT) {
       A.packed[c] = key_float(A.keys[c]);
       A.packed[g.C + c] = -key_float(A.keys[g.C + c]);
@@ -176,17 +201,20 @@ morph_fused_kernel(const FusedArgs A) {
   const float fC = (float)g.C;
   const float rC = __frcp_rn(fC);
   float lmin = INFINITY, lmax = -INFINITY;
-  for (int i0 = tid; i0 < NP; i0 += 4 * NT) {
+  for (int i = tid; i < 512; i += NT) hist[i] = 0;               // hist + hloc
+  if (ns > 1) cl.sync();      // every CTA of the cluster is resident before the first DSMEM store
+  const int band_lo = r_lo * Wc, band_hi = r_hi * Wc;
+  for (int i0 = band_lo + tid; i0 < band_hi; i0 += 4 * NT) {
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * NT;
-      if (i < NP) { const int r = i / Wc, x = i - r * Wc; v[u] = __ldg(sp + r * g.W + x); }
+      if (i < band_hi) { const int r = i / Wc, x = i - r * Wc; v[u] = __ldg(sp + r * g.W + x); }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * NT;
-      if (i < NP) {
+      if (i < band_hi) {
         const float q = div_exact(v[u], fC, rC);
         P0[i] = q;
         lmin = fminf(lmin, q);
@@ -203,6 +231,18 @@ morph_fused_kernel(const FusedArgs A) {
   __syncthreads();
   float gmin = red[0], gmax = red[32];
   for (int w = 1; w < nwarps; ++w) { gmin = fminf(gmin, red[w]); gmax = fmaxf(gmax, red[32 + w]); }
+  if (ns > 1) {                                                   // all-gather raw gray bands and band min/max
+    if (tid == 0)
+      for (int pr = 0; pr < ns; ++pr) {
+        float* m = cl.map_shared_rank(mmx, pr);
+        m[2 * rank] = gmin;
+        m[2 * rank + 1] = gmax;
+      }
+    publish(P0, band_lo, band_hi - band_lo);
+    cl.sync();
+    gmin = mmx[0]; gmax = mmx[1];
+    for (int pr = 1; pr < ns; ++pr) { gmin = fminf(gmin, mmx[2 * pr]); gmax = fmaxf(gmax, mmx[2 * pr + 1]); }
+  }
   // ---- S1: normalise (morphology.py:378-383), P1 = 255 * gray ------------------------------
   const float den = __fadd_rn(__fsub_rn(gmax, gmin), 1e-8f);
   const float rden = __frcp_rn(den);
@@ -210,18 +250,17 @@ morph_fused_kernel(const FusedArgs A) {
     const float v = div_exact(__fsub_rn(P0[i], gmin), den, rden);
     P0[i] = v;
     P1[i] = __fmul_rn(v, 255.f);
-    if (A.gray_dbg) A.gray_dbg[(long long)b * NP + i] = v;
+    if (A.gray_dbg && rank == 0) A.gray_dbg[(long long)b * NP + i] = v;
   }
-  for (int i = tid; i < 256; i += NT) hist[i] = 0;
   __syncthreads();
   STAGE_CLOCK(1);
 
   // ---- S3: adaptive threshold, 11x11 Gaussian mean, replicate borders (morphology.py:550-573)
   //      register tile: RT output rows share their 14 input rows; taps are immediates
-  const int nrg = Hc / RT;                                       // Hc % 4 == 0 (tile >= 4)
+  const int nrg = (r_hi - r_lo) / RT;                            // band rows % 4 == 0 (tile >= 4)
   for (int task = warp; task < nrg * WW; task += nwarps) {
     const int rg = task / WW, k = task - rg * WW;
-    const int r0 = rg * RT;
+    const int r0 = r_lo + rg * RT;
     const int x = 32 * k + lane;
     const bool valid = x < Wc;
     int xc[11];
@@ -253,14 +292,16 @@ morph_fused_kernel(const FusedArgs A) {
     }
   }
   __syncthreads();
+  if (ns > 1) publish(BIN, r_lo * WW, (r_hi - r_lo) * WW);        // visible to the peers after the next cluster sync
   STAGE_CLOCK(2);
   for (int i = tid; i < g.ntiles * 10; i += NT) lbp_hist[i] = 0;
   __syncthreads();
 
   // ---- S4: uniform-LBP histograms + Sobel(gray) tile-row sums ------------------------------
   //      one 3x3 neighbourhood load serves both: LBP sees replicate borders, Sobel zero borders
-  for (int slot = warp; slot < NW; slot += nwarps) {
-    const int r = slot / WW, k = slot - r * WW;
+  const int nslot_b = (r_hi - r_lo) * WW;
+  for (int slot = warp; slot < nslot_b; slot += nwarps) {
+    const int r = r_lo + slot / WW, k = slot % WW;
     const int x = 32 * k + lane;
     const bool valid = x < Wc;
     float gx = 0.f, gy = 0.f;
@@ -313,7 +354,7 @@ morph_fused_kernel(const FusedArgs A) {
 
   // ---- S5: phi2 (LBP entropy, morphology.py:648-652) and phi3 (654-670) per tile -----------
   {
-    for (int t = tid; t < g.ntiles; t += NT) {
+    for (int t = t_lo + tid; t < t_hi; t += NT) {
       const int ty = t / wt, tx = t - ty * wt;
       float ent = 0.f;
 #pragma unroll
@@ -337,13 +378,19 @@ morph_fused_kernel(const FusedArgs A) {
       phis[t * 5 + 2] = __fdiv_rn(v, __fadd_rn(v, 1.0f));
     }
   }
-  __syncthreads();
+  csync();           // every CTA is done with P1 = 255*gray; BIN bands have landed
   STAGE_CLOCK(4);
 
   // ---- S6: 5x5 Gaussian blur (zero padding) -> P1, Otsu histogram (morphology.py:485-493) --
+  float* P1r[3] = {P1, P1, P1};
+  float* P0r[3] = {P0, P0, P0};
+  for (int pr = 1; pr < ns; ++pr) {
+    P1r[pr - 1] = cl.map_shared_rank(P1, (rank + pr) % ns);
+    P0r[pr - 1] = cl.map_shared_rank(P0, (rank + pr) % ns);
+  }
   for (int task = warp; task < nrg * WW; task += nwarps) {
     const int rg = task / WW, k = task - rg * WW;
-    const int r0 = rg * RT;
+    const int r0 = r_lo + rg * RT;
     const int x = 32 * k + lane;
     const bool valid = x < Wc;
     int xc[5];
@@ -375,16 +422,23 @@ morph_fused_kernel(const FusedArgs A) {
       int bin = -1;
       if (valid) {
         P1[(r0 + j) * Wc + x] = acc[j];
+        for (int pr = 1; pr < ns; ++pr) P1r[pr - 1][(r0 + j) * Wc + x] = acc[j];
         if (acc[j] >= 0.f && acc[j] <= 1.f) {          // torch.histc(bins=256, min=0, max=1)
           bin = (int)__fmul_rn(acc[j], 256.f);
           if (bin == 256) bin = 255;
         }
       }
       const unsigned peers = __match_any_sync(0xffffffffu, bin);     // smooth images: many equal bins
-      if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+      if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hloc[bin], __popc(peers));
     }
   }
   __syncthreads();
+  for (int pr = 0; pr < ns; ++pr) {                               // integer counts: order-free, exact
+    int* hp = ns > 1 ? cl.map_shared_rank(hist, pr) : hist;
+    for (int i = tid; i < 256; i += NT)
+      if (hloc[i]) atomicAdd(&hp[i], hloc[i]);
+  }
+  csync();           // blurred bands and the whole-image histogram are complete everywhere
   STAGE_CLOCK(5);
 
   // ---- S7 (warp 0): Otsu threshold (morphology.py:397-418)  ||  S8 (other warps): magnitude ---
@@ -442,30 +496,33 @@ morph_fused_kernel(const FusedArgs A) {
   } else {
     // ---- S8: L1 gradient magnitude of Sobel(255 * blur) -> P0 (morphology.py:496-497) and the
     //      NMS direction bin (2 bits per pixel, parked in the not-yet-used STRONG/WEAK planes)
-    for (int slot = warp - 1; slot < NW; slot += nwarps - 1) {
-      const int r = slot / WW, k = slot - r * WW;
+    for (int slot = warp - 1; slot < nslot_b; slot += nwarps - 1) {
+      const int r = r_lo + slot / WW, k = slot % WW;
       const int x = 32 * k + lane;
       int bin = 0;
       if (x < Wc) {
         float gx, gy;
         sobel_at<true>(P1, r, x, Hc, Wc, gx, gy);
-        P0[r * Wc + x] = __fadd_rn(fabsf(gx), fabsf(gy));
+        const float mg = __fadd_rn(fabsf(gx), fabsf(gy));
+        P0[r * Wc + x] = mg;
+        for (int pr = 1; pr < ns; ++pr) P0r[pr - 1][r * Wc + x] = mg;
         bin = nms_bin(gx, gy);
       }
       const uint32_t d0 = __ballot_sync(0xffffffffu, bin & 1);
       const uint32_t d1 = __ballot_sync(0xffffffffu, bin & 2);
-      if (lane == 0) { STRONG[slot] = d0; WEAK[slot] = d1; }
+      if (lane == 0) { STRONG[r * WW + k] = d0; WEAK[r * WW + k] = d1; }
     }
   }
-  __syncthreads();
+  csync();           // magnitude bands have landed everywhere
   STAGE_CLOCK(6);
   const float thr255 = red[0];
   const int otsu_bin = __float_as_int(red[1]);
   const float thr_lo = __fmul_rn(0.5f, thr255);
 
   // ---- S9: non-maximum suppression + double threshold (morphology.py:426-449, 500-502) ----
-  for (int slot = warp; slot < NW; slot += nwarps) {
-    const int r = slot / WW, k = slot - r * WW;
+  for (int bslot = warp; bslot < nslot_b; bslot += nwarps) {
+    const int r = r_lo + bslot / WW, k = bslot % WW;
+    const int slot = r * WW + k;
     const int x = 32 * k + lane;
     const uint32_t d0 = STRONG[slot], d1 = WEAK[slot];     // direction bits of this slot (same warp rewrites it)
     bool st = false, wk = false;
@@ -488,6 +545,11 @@ morph_fused_kernel(const FusedArgs A) {
     if (lane == 0) { STRONG[slot] = ws; WEAK[slot] = ww; }
   }
   __syncthreads();
+  if (ns > 1) {
+    publish(STRONG, r_lo * WW, (r_hi - r_lo) * WW);
+    publish(WEAK, r_lo * WW, (r_hi - r_lo) * WW);
+    cl.sync();       // full strong / weak planes everywhere; hysteresis then runs redundantly per CTA
+  }
   STAGE_CLOCK(7);
 
   // ---- S10: hysteresis = 8 constrained 3x3 dilations (morphology.py:504-509) ---------------
@@ -519,7 +581,7 @@ morph_fused_kernel(const FusedArgs A) {
   __syncthreads();
   const int segs = 32 >> tshift;
   const uint32_t segmask = tile == 32 ? 0xffffffffu : ((1u << tile) - 1u);
-  for (int i = tid; i < NW; i += NT) {
+  for (int i = r_lo * WW + tid; i < r_hi * WW; i += NT) {
     const int r = i / WW, k = i - r * WW;
     const int nbits = min(32, Wc - 32 * k);
     const uint32_t vmask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
@@ -567,7 +629,7 @@ morph_fused_kernel(const FusedArgs A) {
   }
   STAGE_CLOCK(9);
   // dyadic box counts (morphology.py:595-601): one thread per (tile, scale)
-  for (int ts = tid; ts < g.ntiles * g.S; ts += NT) {
+  for (int ts = t_lo * g.S + tid; ts < t_hi * g.S; ts += NT) {
     const int t = ts / g.S, sidx = ts - t * g.S;
     const int s = 2 << sidx;
     const int ty = t / wt, tx = t - ty * wt;
@@ -587,7 +649,7 @@ morph_fused_kernel(const FusedArgs A) {
   STAGE_CLOCK(10);
 
   // ---- S12: phi1, phi4, phi5, interactions (morphology.py:852-864) --------------------------
-  for (int t = tid; t < g.ntiles; t += NT) {
+  for (int t = t_lo + tid; t < t_hi; t += NT) {
     const int* a = acc + t * 9;
     const int S = g.S;
     float y[5];
@@ -634,48 +696,72 @@ morph_fused_kernel(const FusedArgs A) {
       c[9] = otsu_bin; c[10] = 0; c[11] = 0;
     }
   }
-  if (A.edge_dbg)
+  if (A.edge_dbg && rank == 0)
     for (int i = tid; i < NW; i += NT) A.edge_dbg[(long long)b * NW + i] = EDGE[i];
-  if (A.bin_dbg)
+  if (A.bin_dbg && rank == 0)
     for (int i = tid; i < NW; i += NT) A.bin_dbg[(long long)b * NW + i] = BIN[i];
   __syncthreads();
   STAGE_CLOCK(11);
-  if (!A.cmlp) return;
+  if (!A.cmlp) return;                       // last remote access was before the strong/weak sync
 
-  // ---- N1: complexity MLP + bilateral (scratch aliases the dead planes) ---------------------
-  float* scratch = P0;
+  // ---- N1: complexity MLP (own tiles) -> all-gather -> bilateral (own tiles) -> all-gather ----
+  float* scratch = P0;                       // the planes are dead from here on
+  const int nt = g.ntiles;
   {
     float* w = scratch;
     float* act = w + CMLP_SMEM_FLOATS;
-    float* craw = scratch + cpx_scratch_floats(g.ntiles);
     complexity_load_weights(A.cmlp, w);
     __syncthreads();
-    complexity_block(phi8, g.ht, g.wt, w, act, craw, cfin,
-                     A.complexity_raw ? A.complexity_raw + (long long)b * g.ntiles : nullptr,
-                     A.complexity ? A.complexity + (long long)b * g.ntiles : nullptr);
+    complexity_mlp_range(phi8, t_lo, t_hi, w, act, craw_s,
+                         A.complexity_raw ? A.complexity_raw + (long long)b * nt : nullptr);
+    if (ns > 1) { publish(craw_s, t_lo, t_hi - t_lo); cl.sync(); }
+    bilateral_range(craw_s, g.ht, g.wt, t_lo, t_hi, act, cfin, A.complexity ? A.complexity + (long long)b * nt : nullptr);
+    if (ns > 1) { publish(cfin, t_lo, t_hi - t_lo); cl.sync(); }
   }
   STAGE_CLOCK(12);
   if (!A.run_mapper) return;
-  // ---- N2: bit mapper ----------------------------------------------------------------------
-  float* bout = A.bit_map ? A.bit_map + (long long)b * g.ntiles : nullptr;
+  // ---- N2: bit mapper (own tiles) --------------------------------------------------------------
+  float* bout = A.bit_map ? A.bit_map + (long long)b * nt : nullptr;
   if (A.linear_mapper) {
     int npow2 = 1;
-    while (npow2 < g.ntiles) npow2 <<= 1;
-    mapper_linear_block(cfin, g.ntiles, npow2, scratch, A.temperature, A.use_t, A.continuous, A.lo, A.hi,
+    while (npow2 < nt) npow2 <<= 1;
+    mapper_linear_range(cfin, nt, npow2, scratch, t_lo, t_hi, A.temperature, A.use_t, A.continuous, A.lo, A.hi,
                         A.eps_spread, bits_s, bout);
   } else {
     float* w = scratch;
     float* act = w + MAPPER_SMEM_FLOATS;
     mapper_load_weights(A.mapper, w);
     __syncthreads();
-    mapper_mlp_block(cfin, g.ntiles, w, act, A.temperature, A.use_t, A.continuous, A.lo, A.hi, bits_s, bout);
+    mapper_mlp_range(cfin, t_lo, t_hi, w, act, A.temperature, A.use_t, A.continuous, A.lo, A.hi, bits_s, bout);
   }
   STAGE_CLOCK(13);
-  if (!A.softmask || !A.abs_plane) return;
-  // ---- N3: soft mask (quantization.py:213-239): tile head + nearest upsample + 5x5 smoothing --
-  soft_mask_block(bits_s, g.ht, g.wt, A.abs_plane + (long long)b * g.H * g.W, g.C, g.H, g.W, A.softmask, scratch,
-                  A.mask_tiles ? A.mask_tiles + (long long)b * g.ntiles : nullptr,
-                  A.mask + (long long)b * g.H * g.W);
+  if (!A.softmask || !A.abs_plane) {
+    if (ns > 1) cl.sync();                   // nobody leaves while a peer may still write into it
+    return;
+  }
+  // ---- N3: soft mask (quantization.py:213-239): tile head (own tiles) + m rows (own band) ------
+  {
+    float* rows = scratch;                   // [H*wt]
+    float* P = rows + g.H * g.wt;            // 196
+    float* bn = P + 196;                     // [nt]
+    float* an = bn + nt;                     // [nt]
+    float amax = softmask_act_range(A.abs_plane + (long long)b * g.H * g.W, g.C, g.H, g.W, g.ht, g.wt, tr0, tr1,
+                                    rows, red, act_s);
+    if (ns > 1) {
+      if (tid == 0)
+        for (int pr = 0; pr < ns; ++pr) cl.map_shared_rank(mmx, pr)[8 + rank] = amax;
+      publish(bits_s, t_lo, t_hi - t_lo);
+      publish(act_s, t_lo, t_hi - t_lo);
+      cl.sync();
+      amax = mmx[8];
+      for (int pr = 1; pr < ns; ++pr) amax = fmaxf(amax, mmx[8 + pr]);
+    }
+    softmask_head_range(bits_s, act_s, amax, g.ht, g.wt, t_lo, t_hi, A.softmask, P, bn, an, mt_s,
+                        A.mask_tiles ? A.mask_tiles + (long long)b * nt : nullptr);
+    if (ns > 1) { publish(mt_s, t_lo, t_hi - t_lo); cl.sync(); }
+    softmask_plane_rows(mt_s, P, g.H, g.W, g.ht, g.wt, (g.H * rank) / ns, (g.H * (rank + 1)) / ns,
+                        A.mask + (long long)b * g.H * g.W);
+  }
   STAGE_CLOCK(14);
 }
 
@@ -688,6 +774,19 @@ extern "C" void mcaq_debug_stage_clocks(long long* dev_buf) { g_stage_clk = dev_
 
 static int max_i(int a, int b) { return a > b ? a : b; }
 
+static int g_force_split = 0;
+// debug / tuning: force the number of CTAs per image (0 = automatic)
+extern "C" void mcaq_debug_cluster_split(int ns) { g_force_split = ns; }
+
+// CTAs per image: tile rows are split over a thread-block cluster (portable size <= 8)
+static int pick_split(int ht) {
+  int ns = ht >= 4 ? 4 : (ht >= 2 ? 2 : 1);
+  if (g_force_split == 1 || g_force_split == 2 || g_force_split == 4) ns = g_force_split;
+  while (ns > ht) ns >>= 1;
+  return ns < 1 ? 1 : ns;
+}
+
+
 // geometry + shared-memory layout; returns bytes of dynamic smem or a negative error
 static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size, bool nets, int threads) {
   g.B = B; g.C = C; g.H = H; g.W = W;
@@ -699,6 +798,7 @@ static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size, b
   g.ntiles = g.ht * g.wt;
   g.S = 0;
   for (int s = 2; s <= g.tile; s <<= 1) g.S++;
+  g.ns = pick_split(g.ht);
   const long long NP = (long long)g.Hc * g.Wc, NW = (long long)g.Hc * g.WW;
   const long long rowsum_w = (long long)g.Hc * g.wt * 4, lbp_w = (long long)g.ntiles * 10;
   long long np1 = NP < rowsum_w ? rowsum_w : NP;
@@ -715,19 +815,23 @@ static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size, b
     (void)threads;
     int npow2 = 1;
     while (npow2 < g.ntiles) npow2 <<= 1;
-    long long need = CMLP_SMEM_FLOATS + max_i(CPX_ACT_FLOATS, 25 * g.ntiles) + g.ntiles;
+    long long need = CMLP_SMEM_FLOATS + max_i(CPX_ACT_FLOATS, 25 * g.ntiles);
     need = max_i((int)need, MAPPER_SMEM_FLOATS + MAP_ACT_FLOATS);
     need = max_i((int)need, npow2);
-    need = max_i((int)need, 196 + 3 * g.ntiles + H * g.wt + 32);
+    need = max_i((int)need, H * g.wt + 196 + 2 * g.ntiles);
     if (tail < need) tail = (need + 3) & ~3LL;
   }
   g.off_tail = (int)tail;
-  const long long words = tail + 3 * NW + (long long)g.ntiles * (5 + 8 + 1 + 1) + 256 + 64 + 260 +
+  const long long words = tail + 3 * NW + (long long)g.ntiles * (5 + 8 + 5) + 512 + 64 + 16 + 260 +
                           g.tile * g.tile + 4;
   return words * 4;
 }
 
-static int pick_threads(long long NP) { return NP <= 1024 ? 128 : (NP <= 4096 ? 256 : MORPH_THREADS); }
+// threads per CTA from the pixels of the largest band
+static int pick_threads(const MorphGeom& g) {
+  const long long band = (long long)((g.ht + g.ns - 1) / g.ns) * g.tile * g.Wc;
+  return band <= 640 ? 128 : (band <= 4096 ? 256 : MORPH_THREADS);
+}
 
 static int launch_fused(FusedArgs& A, long long smem, int threads, cudaStream_t st) {
   if (smem > 227 * 1024) return MCAQ_ETOOBIG;
@@ -737,7 +841,20 @@ static int launch_fused(FusedArgs& A, long long smem, int threads, cudaStream_t 
     attr_set = true;
   }
   A.clk = g_stage_clk;
-  morph_fused_kernel<<<A.g.B, threads, (size_t)smem, st>>>(A);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(A.g.B * A.g.ns));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)A.g.ns;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, morph_fused_kernel, A);
+  if (e != cudaSuccess) return (int)e;
   MCAQ_LAUNCH_CHECK();
   return 0;
 }
@@ -748,10 +865,9 @@ extern "C" int mcaq_morph_phi(const float* sum_plane, int B, int C, int H, int W
   (void)consts;   // compiled in (mcaq_consts.cuh); argument kept for ABI stability
   if (!sum_plane || !phi || B <= 0 || C <= 0 || H <= 0 || W <= 0 || grid_size <= 0) return MCAQ_EINVAL;
   FusedArgs A = {};
-  const int tile = mcaq_tile_size(H, grid_size);
-  const int threads = pick_threads((long long)(H / tile) * tile * (W / tile) * tile);
-  const long long smem = plan(A.g, B, C, H, W, grid_size, false, threads);
+  const long long smem = plan(A.g, B, C, H, W, grid_size, false, 0);
   if (smem < 0) return (int)smem;
+  const int threads = pick_threads(A.g);
   A.sum_plane = sum_plane;
   A.phi = phi;
   A.gray_dbg = gray_dbg; A.edge_dbg = edge_bits_dbg; A.bin_dbg = bin_bits_dbg;
@@ -771,10 +887,9 @@ extern "C" int mcaq_morph_fused(const float* sum_plane, const float* abs_plane, 
   if (softmask && (!abs_plane || !mask)) return MCAQ_EINVAL;
   if (keys && !packed_ranges) return MCAQ_EINVAL;
   FusedArgs A = {};
-  const int tile = mcaq_tile_size(H, grid_size);
-  const int threads = pick_threads((long long)(H / tile) * tile * (W / tile) * tile);
-  const long long smem = plan(A.g, B, C, H, W, grid_size, true, threads);
+  const long long smem = plan(A.g, B, C, H, W, grid_size, true, 0);
   if (smem < 0) return (int)smem;
+  const int threads = pick_threads(A.g);
   A.sum_plane = sum_plane; A.abs_plane = abs_plane;
   A.keys = keys; A.packed = packed_ranges;
   A.cmlp = cmlp; A.mapper = mapper; A.softmask = softmask;

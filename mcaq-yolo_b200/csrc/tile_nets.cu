@@ -19,8 +19,9 @@ complexity_kernel(const float* __restrict__ phi, int ht, int wt, const float* __
   const int b = blockIdx.x;
   complexity_load_weights(cmlp, w);
   __syncthreads();
-  complexity_block(phi + (long long)b * ntiles * 8, ht, wt, w, act, craw, cfin,
-                   raw_out ? raw_out + (long long)b * ntiles : nullptr, out + (long long)b * ntiles);
+  complexity_mlp_range(phi + (long long)b * ntiles * 8, 0, ntiles, w, act, craw,
+                       raw_out ? raw_out + (long long)b * ntiles : nullptr);
+  bilateral_range(craw, ht, wt, 0, ntiles, act, cfin, out + (long long)b * ntiles);
 }
 
 __global__ void __launch_bounds__(TN_THREADS)
@@ -33,7 +34,7 @@ mapper_mlp_kernel(const float* __restrict__ cmap, int ntiles, const float* __res
   const int b = blockIdx.x;
   mapper_load_weights(mp, w);
   __syncthreads();
-  mapper_mlp_block(cmap + (long long)b * ntiles, ntiles, w, act, temperature, use_t, continuous, lo, hi,
+  mapper_mlp_range(cmap + (long long)b * ntiles, 0, ntiles, w, act, temperature, use_t, continuous, lo, hi,
                    bits_s, out + (long long)b * ntiles);
 }
 
@@ -44,8 +45,8 @@ mapper_linear_kernel(const float* __restrict__ cmap, int ntiles, int npow2, floa
   float* srt = sm;
   float* bits_s = srt + npow2;
   const int b = blockIdx.x;
-  mapper_linear_block(cmap + (long long)b * ntiles, ntiles, npow2, srt, temperature, use_t, continuous, lo, hi,
-                      eps_spread, bits_s, out + (long long)b * ntiles);
+  mapper_linear_range(cmap + (long long)b * ntiles, ntiles, npow2, srt, 0, ntiles, temperature, use_t, continuous,
+                      lo, hi, eps_spread, bits_s, out + (long long)b * ntiles);
 }
 
 __global__ void __launch_bounds__(TN_THREADS)
@@ -54,8 +55,19 @@ soft_mask_kernel(const float* __restrict__ bit_map, int Ht, int Wt, const float*
                  float* __restrict__ mask) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, nt = Ht * Wt;
-  soft_mask_block(bit_map + (long long)b * nt, Ht, Wt, abs_plane + (long long)b * H * W, C, H, W, prm, sm,
-                  tiles_out ? tiles_out + (long long)b * nt : nullptr, mask + (long long)b * H * W);
+  float* P = sm;                         // 196
+  float* act = P + 196;                  // [nt]
+  float* bn = act + nt;
+  float* an = bn + nt;
+  float* mt = an + nt;
+  float* bits = mt + nt;                 // [nt] staged copy of the bit map
+  float* rows = bits + nt;               // [H*Wt]
+  float* red = rows + H * Wt;            // [32]
+  for (int t = threadIdx.x; t < nt; t += blockDim.x) bits[t] = bit_map[(long long)b * nt + t];
+  const float amax = softmask_act_range(abs_plane + (long long)b * H * W, C, H, W, Ht, Wt, 0, Ht, rows, red, act);
+  softmask_head_range(bits, act, amax, Ht, Wt, 0, nt, prm, P, bn, an, mt,
+                      tiles_out ? tiles_out + (long long)b * nt : nullptr);
+  softmask_plane_rows(mt, P, H, W, Ht, Wt, 0, H, mask + (long long)b * H * W);
 }
 
 }  // namespace mcaq
@@ -105,7 +117,7 @@ extern "C" int mcaq_soft_mask(const float* bit_map, int Ht, int Wt, const float*
                               int W, const float* softmask, float* mask_tiles, float* mask, void* stream) {
   if (!bit_map || !abs_plane || !softmask || !mask || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0)
     return MCAQ_EINVAL;
-  const size_t smem = (size_t)(196 + 3 * Ht * Wt + H * Wt + 32) * 4;
+  const size_t smem = (size_t)(196 + 5 * Ht * Wt + H * Wt + 32) * 4;
   if (smem > 200 * 1024) return MCAQ_ETOOBIG;
   if (smem > 48 * 1024) cudaFuncSetAttribute(soft_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   soft_mask_kernel<<<B, TN_THREADS, smem, (cudaStream_t)stream>>>(bit_map, Ht, Wt, abs_plane, C, H, W, softmask,

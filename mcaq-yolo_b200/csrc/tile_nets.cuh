@@ -79,22 +79,22 @@ __device__ __forceinline__ void complexity_load_weights(const float* __restrict_
 
 // Tiles are processed in batches of NET_TB; within a batch every (tile, unit) output is one
 // thread's FMA chain, so the dense layers run at CTA width instead of one warp per tile.
+// All functions take a tile range [t_lo, t_hi): the fused kernel splits an image's tiles over the
+// CTAs of a cluster and all-gathers the results through distributed shared memory.
 constexpr int NET_TB = 128;
 constexpr int ROW64 = 68, ROW32 = 36;                  // padded, 16-byte aligned activation rows
 constexpr int CPX_ACT_FLOATS = NET_TB * (ROW64 + ROW32);   // h1 [TB][68], h2 [TB][36]
 
-__device__ __forceinline__ int cpx_scratch_floats(int ntiles) {
+__host__ __device__ __forceinline__ int cpx_scratch_floats(int ntiles) {
   const int act = CPX_ACT_FLOATS, bil = ntiles * 25;
   return CMLP_SMEM_FLOATS + (act > bil ? act : bil);
 }
 
-// phi: [ntiles][8] (global or shared).  craw/cfin: [ntiles] shared.  Weights already loaded into w;
-// act: scratch of max(CPX_ACT_FLOATS, 25*ntiles) floats.
-__device__ __forceinline__ void complexity_block(const float* phi, int ht, int wt, const float* w, float* act,
-                                                 float* craw, float* cfin, float* __restrict__ raw_out,
-                                                 float* __restrict__ out) {
+// craw[t] = sigmoid(MLP(phi[t])) for t in [t_lo, t_hi).  phi: [ntiles][8] (global or shared),
+// weights already in w, act: CPX_ACT_FLOATS scratch.
+__device__ __forceinline__ void complexity_mlp_range(const float* phi, int t_lo, int t_hi, const float* w,
+                                                     float* act, float* craw, float* __restrict__ raw_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
-  const int ntiles = ht * wt;
   const float* W0t = w;
   const float* b0 = w + 512;
   const float* g1 = w + 576;
@@ -105,12 +105,11 @@ __device__ __forceinline__ void complexity_block(const float* phi, int ht, int w
   const float* be4 = w + 2816;
   const float* W6 = w + 2848;
   const float b6 = w[2880];
-  float* h1 = act;                       // [TB][65]
+  float* h1 = act;                       // [TB][68]
   float* h2 = act + NET_TB * ROW64;      // [TB][36]
-  for (int t0 = 0; t0 < ntiles; t0 += NET_TB) {
-    const int nb = min(NET_TB, ntiles - t0);
-    // layer 1: 8 -> 64
-    for (int o = tid; o < nb * 64; o += NT) {
+  for (int t0 = t_lo; t0 < t_hi; t0 += NET_TB) {
+    const int nb = min(NET_TB, t_hi - t0);
+    for (int o = tid; o < nb * 64; o += NT) {     // layer 1: 8 -> 64
       const int t = o >> 6, m = o & 63;
       const float* in = phi + (t0 + t) * 8;
       float acc = 0.f;
@@ -119,8 +118,7 @@ __device__ __forceinline__ void complexity_block(const float* phi, int ht, int w
       h1[t * ROW64 + m] = __fadd_rn(acc, b0[m]);
     }
     __syncthreads();
-    // LayerNorm(64) + ReLU, one warp per tile
-    for (int t = warp; t < nb; t += nwarps) {
+    for (int t = warp; t < nb; t += nwarps) {     // LayerNorm(64) + ReLU, one warp per tile
       const float a0 = h1[t * ROW64 + lane], a1 = h1[t * ROW64 + lane + 32];
       const float mean = __fdiv_rn(warp_tree_sum(__fadd_rn(a0, a1)), 64.f);
       const float d0 = __fsub_rn(a0, mean), d1 = __fsub_rn(a1, mean);
@@ -133,8 +131,7 @@ __device__ __forceinline__ void complexity_block(const float* phi, int ht, int w
     // layer 2: 64 -> 32, register tiled (8 tiles x 1 unit per thread)
     dense_tiled<64, 32>(h1, ROW64, nb, W3t, [&](int t, int m, float acc) { h2[t * ROW32 + m] = __fadd_rn(acc, b3[m]); });
     __syncthreads();
-    // LayerNorm(32) + ReLU
-    for (int t = warp; t < nb; t += nwarps) {
+    for (int t = warp; t < nb; t += nwarps) {     // LayerNorm(32) + ReLU
       const float a0 = h2[t * ROW32 + lane];
       const float mean = __fdiv_rn(warp_tree_sum(a0), 32.f);
       const float d0 = __fsub_rn(a0, mean);
@@ -143,8 +140,7 @@ __device__ __forceinline__ void complexity_block(const float* phi, int ht, int w
       h2[t * ROW32 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g4[lane]), be4[lane]), 0.f);
     }
     __syncthreads();
-    // layer 3: 32 -> 1 and sigmoid, one thread per tile
-    for (int t = tid; t < nb; t += NT) {
+    for (int t = tid; t < nb; t += NT) {          // layer 3: 32 -> 1 and sigmoid, one thread per tile
       float z = 0.f;
 #pragma unroll 8
       for (int k = 0; k < 32; ++k) z = fmaf(h2[t * ROW32 + k], W6[k], z);
@@ -154,11 +150,17 @@ __device__ __forceinline__ void complexity_block(const float* phi, int ht, int w
     }
     __syncthreads();
   }
-  // 5x5 bilateral filter, replicate padding (morphology.py:309-354): range weights for all
-  // (tile, tap) pairs in parallel, then one thread per tile accumulates its 25 taps in order
-  float* wgt = act;                      // [ntiles][25]
-  for (int o = tid; o < ntiles * 25; o += NT) {
-    const int t = o / 25, tap = o - t * 25;
+}
+
+// 5x5 bilateral filter with replicate padding (morphology.py:309-354) and clamp, for tiles
+// [t_lo, t_hi); craw must hold ALL tiles of the image.  wgt: 25*(t_hi-t_lo) floats of scratch.
+__device__ __forceinline__ void bilateral_range(const float* craw, int ht, int wt, int t_lo, int t_hi, float* wgt,
+                                                float* cfin, float* __restrict__ out) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int n = t_hi - t_lo;
+  for (int o = tid; o < n * 25; o += NT) {        // range weights for all (tile, tap) pairs in parallel
+    const int tl = o / 25, tap = o - tl * 25;
+    const int t = t_lo + tl;
     const int y = t / wt, x = t - y * wt;
     const int ky = tap / 5, kx = tap - ky * 5;
     const int yy = min(max(y + ky - 2, 0), ht - 1), xx = min(max(x + kx - 2, 0), wt - 1);
@@ -167,7 +169,8 @@ __device__ __forceinline__ void complexity_block(const float* phi, int ht, int w
     wgt[o] = __fmul_rn(kc::BILAT[tap], (float)exp((double)arg));
   }
   __syncthreads();
-  for (int t = tid; t < ntiles; t += NT) {
+  for (int tl = tid; tl < n; tl += NT) {          // ordered accumulation of the 25 taps
+    const int t = t_lo + tl;
     const int y = t / wt, x = t - y * wt;
     float num = 0.f, den = 0.f;
 #pragma unroll
@@ -176,7 +179,7 @@ __device__ __forceinline__ void complexity_block(const float* phi, int ht, int w
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
         const int xx = min(max(x + kx - 2, 0), wt - 1);
-        const float wg = wgt[t * 25 + ky * 5 + kx];
+        const float wg = wgt[tl * 25 + ky * 5 + kx];
         num = __fadd_rn(num, __fmul_rn(wg, craw[yy * wt + xx]));
         den = __fadd_rn(den, wg);
       }
@@ -214,8 +217,8 @@ __device__ __forceinline__ void mapper_load_weights(const float* __restrict__ mp
 
 constexpr int MAP_ACT_FLOATS = NET_TB * (4 + ROW32 + ROW64 + ROW32);   // zin [TB][4], g0 [TB][36], g1 [TB][68], g2 [TB][36]
 
-// cmap: [ntiles] (global or shared); act: MAP_ACT_FLOATS scratch; bits_s: [ntiles] shared result
-__device__ __forceinline__ void mapper_mlp_block(const float* cmap, int ntiles, const float* w, float* act,
+// bits_s[t] for t in [t_lo, t_hi); cmap indexed by absolute tile
+__device__ __forceinline__ void mapper_mlp_range(const float* cmap, int t_lo, int t_hi, const float* w, float* act,
                                                  float temperature, int use_t, int continuous,
                                                  float lo, float hi, float* bits_s, float* __restrict__ out) {
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -227,11 +230,11 @@ __device__ __forceinline__ void mapper_mlp_block(const float* cmap, int ntiles, 
   const float* v6 = w + 4480;
   const float* W9 = w + 4576;
   float* zin = act;                      // [TB][4]
-  float* g0 = zin + NET_TB * 4;          // [TB][32]
+  float* g0 = zin + NET_TB * 4;          // [TB][36]
   float* g1 = g0 + NET_TB * ROW32;       // [TB][68]
   float* g2 = g1 + NET_TB * ROW64;       // [TB][36]
-  for (int t0 = 0; t0 < ntiles; t0 += NET_TB) {
-    const int nb = min(NET_TB, ntiles - t0);
+  for (int t0 = t_lo; t0 < t_hi; t0 += NET_TB) {
+    const int nb = min(NET_TB, t_hi - t0);
     for (int t = tid; t < nb; t += NT) {          // z0 = [c, c^2, log1p(c)]  (Eq.13)
       const float c = fminf(fmaxf(cmap[t0 + t], 0.f), 1.f);
       zin[t * 4 + 0] = c;
@@ -283,11 +286,12 @@ __device__ __forceinline__ float quantile_sorted(const float* srt, int n, float 
   return __fsub_rn(bb, __fmul_rn(diff, __fsub_rn(1.0f, w)));
 }
 
-// cmap: [ntiles]; srt: [npow2] shared scratch; bits_s: [ntiles] shared
-__device__ __forceinline__ void mapper_linear_block(const float* cmap, int ntiles, int npow2, float* srt,
-                                                    float temperature, int use_t, int continuous, float lo,
-                                                    float hi, float eps_spread, float* bits_s,
-                                                    float* __restrict__ out) {
+// LinearBitMapper: quantiles over ALL tiles of the image (cmap: [ntiles]); writes bits for
+// [t_lo, t_hi).  srt: npow2 floats of scratch.
+__device__ __forceinline__ void mapper_linear_range(const float* cmap, int ntiles, int npow2, float* srt,
+                                                    int t_lo, int t_hi, float temperature, int use_t,
+                                                    int continuous, float lo, float hi, float eps_spread,
+                                                    float* bits_s, float* __restrict__ out) {
   const int tid = threadIdx.x, NT = blockDim.x;
   for (int i = tid; i < npow2; i += NT) srt[i] = i < ntiles ? cmap[i] : INFINITY;
   __syncthreads();
@@ -307,7 +311,7 @@ __device__ __forceinline__ void mapper_linear_block(const float* cmap, int ntile
   const float qlo = quantile_sorted(srt, ntiles, 0.02f);
   const float qhi = quantile_sorted(srt, ntiles, 0.98f);
   const float spread = __fsub_rn(qhi, qlo);
-  for (int t = tid; t < ntiles; t += NT) {
+  for (int t = t_lo + tid; t < t_hi; t += NT) {
     const float v = cmap[t];
     float rel = __fdiv_rn(__fsub_rn(v, qlo), __fadd_rn(spread, 1e-8f));
     rel = fminf(fmaxf(rel, 0.f), 1.f);
@@ -321,26 +325,19 @@ __device__ __forceinline__ void mapper_linear_block(const float* cmap, int ntile
 }
 
 // ---------------------------------------------------------------------------------------------
-// learned soft mask (quantization.py:213-239)
+// learned soft mask (quantization.py:213-239), in three range-aware steps
 // packed params: W0[8][2][3][3] b0[8] W2[2][8] b2[2] smooth[5][5]  (195 floats)
-// smem need: 196 + 3*Ht*Wt + H*Wt + 32
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void soft_mask_block(const float* bits /*[Ht*Wt], global or shared*/, int Ht, int Wt,
-                                                const float* __restrict__ ap /*[H*W] sum_c|x| of this image*/,
-                                                int C, int H, int W, const float* __restrict__ prm, float* sm,
-                                                float* __restrict__ tiles_out, float* __restrict__ mo) {
-  float* P = sm;                         // 196
-  const int nt = Ht * Wt;
-  float* act = P + 196;                  // [nt]
-  float* bn = act + nt;                  // [nt]
-  float* mt = bn + nt;                   // [nt]
-  float* rows = mt + nt;                 // [H*Wt]
-  float* red = rows + H * Wt;            // [32]
+// (a) act[t] = mean over the tile's adaptive window of sum_c|x| / C, for tile rows [ty_lo, ty_hi);
+//     returns the maximum over those tiles (every thread gets it).  rows: H*Wt floats, red: 32.
+__device__ __forceinline__ float softmask_act_range(const float* __restrict__ ap, int C, int H, int W, int Ht,
+                                                    int Wt, int ty_lo, int ty_hi, float* rows, float* red,
+                                                    float* act) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
-  for (int i = tid; i < 195; i += NT) P[i] = __ldg(prm + i);
   const float fC = (float)C;
   const float rC = __frcp_rn(fC);
-  for (int i = tid; i < H * Wt; i += NT) {
+  const int y_lo = (ty_lo * H) / Ht, y_hi = (ty_hi * H + Ht - 1) / Ht;
+  for (int i = y_lo * Wt + tid; i < y_hi * Wt; i += NT) {
     const int y = i / Wt, j = i - y * Wt;
     const int xs = (j * W) / Wt, xe = ((j + 1) * W + Wt - 1) / Wt;
     float s = 0.f;
@@ -360,7 +357,7 @@ __device__ __forceinline__ void soft_mask_block(const float* bits /*[Ht*Wt], glo
   }
   __syncthreads();
   float lmax = -INFINITY;
-  for (int t = tid; t < nt; t += NT) {
+  for (int t = ty_lo * Wt + tid; t < ty_hi * Wt; t += NT) {
     const int i = t / Wt, j = t - i * Wt;
     const int ys = (i * H) / Ht, ye = ((i + 1) * H + Ht - 1) / Ht;
     const int xs = (j * W) / Wt, xe = ((j + 1) * W + Wt - 1) / Wt;
@@ -369,7 +366,6 @@ __device__ __forceinline__ void soft_mask_block(const float* bits /*[Ht*Wt], glo
     const float a = __fdiv_rn(s, (float)((ye - ys) * (xe - xs)));
     act[t] = a;
     lmax = fmaxf(lmax, a);
-    bn[t] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bits[t], 2.0f), 6.0f), 0.f), 1.f);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
@@ -377,15 +373,30 @@ __device__ __forceinline__ void soft_mask_block(const float* bits /*[Ht*Wt], glo
   __syncthreads();
   float amax = red[0];
   for (int w = 1; w < nwarps; ++w) amax = fmaxf(amax, red[w]);
-  const float aden = __fadd_rn(amax, 1e-8f);
   __syncthreads();
-  for (int t = tid; t < nt; t += NT) act[t] = __fdiv_rn(act[t], aden);
+  return amax;
+}
+
+// (b) tile head for tiles [t_lo, t_hi): act / (amax + 1e-8), bits -> [0,1], conv3x3(2->8)+ReLU,
+//     conv1x1(8->2), softmax channel 0.  bits/act hold ALL tiles; P: 196 floats (params loaded
+//     here), bn/an: nt floats each of scratch.
+__device__ __forceinline__ void softmask_head_range(const float* bits, const float* act, float amax, int Ht, int Wt,
+                                                    int t_lo, int t_hi, const float* __restrict__ prm, float* P,
+                                                    float* bn, float* an, float* mt, float* __restrict__ tiles_out) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int nt = Ht * Wt;
+  for (int i = tid; i < 195; i += NT) P[i] = __ldg(prm + i);
+  const float aden = __fadd_rn(amax, 1e-8f);
+  for (int t = tid; t < nt; t += NT) {
+    an[t] = __fdiv_rn(act[t], aden);
+    bn[t] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bits[t], 2.0f), 6.0f), 0.f), 1.f);
+  }
   __syncthreads();
   const float* W0 = P;
   const float* b0 = P + 144;
   const float* W2 = P + 152;
   const float* b2 = P + 168;
-  for (int t = tid; t < nt; t += NT) {
+  for (int t = t_lo + tid; t < t_hi; t += NT) {
     const int i = t / Wt, j = t - i * Wt;
     float hid[8];
 #pragma unroll
@@ -393,7 +404,7 @@ __device__ __forceinline__ void soft_mask_block(const float* bits /*[Ht*Wt], glo
       float acc = 0.f;
 #pragma unroll
       for (int ic = 0; ic < 2; ++ic) {
-        const float* src = ic == 0 ? bn : act;
+        const float* src = ic == 0 ? bn : an;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const int yy = i + ky - 1;
@@ -423,9 +434,16 @@ __device__ __forceinline__ void soft_mask_block(const float* bits /*[Ht*Wt], glo
     if (tiles_out) tiles_out[t] = m;
   }
   __syncthreads();
+}
+
+// (c) rows [h_lo, h_hi) of m = smooth5x5(nearest_upsample(mt)), replicate padding, FMA chain over
+//     taps in row-major order.  mt holds ALL tiles; P holds the params (smooth kernel at +170).
+__device__ __forceinline__ void softmask_plane_rows(const float* mt, const float* P, int H, int W, int Ht, int Wt,
+                                                    int h_lo, int h_hi, float* __restrict__ mo) {
+  const int tid = threadIdx.x, NT = blockDim.x;
   const float* ks = P + 170;
   const float sy = (float)Ht / (float)H, sx = (float)Wt / (float)W;
-  for (int p = tid; p < H * W; p += NT) {
+  for (int p = h_lo * W + tid; p < h_hi * W; p += NT) {
     const int h = p / W, w = p - h * W;
     int ix[5];
 #pragma unroll
@@ -439,7 +457,6 @@ __device__ __forceinline__ void soft_mask_block(const float* bits /*[Ht*Wt], glo
     }
     mo[p] = acc;
   }
-  __syncthreads();
 }
 
 }  // namespace mcaq

@@ -309,3 +309,34 @@ def test_sharded_hot_path_single_rank_equals_fused(M, W):
     torch.cuda.synchronize()
     for u, v in zip(ref, recs):
         assert torch.equal(u["features_q"], v["features_q"]) and torch.equal(u["bit_map"], v["bit_map"])
+
+
+# ------------------------------------------------------------------------------ K2 cluster split
+@pytest.mark.parametrize("name", CASES + ["c3_v8s1280_smooth", "small_noise"])
+@pytest.mark.parametrize("linear", [False, True])
+def test_cluster_split_is_bit_identical(name, linear, M, W):
+    """The morphology kernel splits an image's tile rows over a 1/2/4-CTA cluster (DSMEM
+    all-gathers); every split must give the same phi / complexity / bit map / mask bit for bit."""
+    from mcaq_yolo_b200 import _lib, constants as K, ops
+    lib = _lib.load()
+    c = Case(name)
+    a, m, q = M.build_fixture_modules(W, "cuda", grid_size=c.grid, linear_mapper=linear)
+    cm = K.pack_complexity_mlp(a.complexity_mlp)
+    mp = None if linear else K.pack_mapping_network(m.mapping_network)
+    sm = K.pack_soft_mask(q.soft_mask)
+    x = torch.from_numpy(c.x()).cuda()
+    s, ab, _ = ops.reduce_planes(x)
+    outs = []
+    try:
+        for ns in (1, 2, 4, 0):
+            lib.mcaq_debug_cluster_split(ns)
+            r = ops.morph_fused(s, ab, c.C, c.grid, cm, mp, sm, 1.0, want_phi=True)
+            torch.cuda.synchronize()
+            outs.append(r)
+    finally:
+        lib.mcaq_debug_cluster_split(0)
+    for r in outs[1:]:
+        for k in ("phi", "complexity", "bit_map", "mask"):
+            assert torch.equal(outs[0][k], r[k]), f"{k} differs between cluster splits"
+    if not linear:
+        assert int((outs[0]["bit_map"].cpu().numpy() != c["bit_map_mlp"]).sum()) == 0
