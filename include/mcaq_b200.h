@@ -45,9 +45,9 @@ extern "C" {
 /* number of floats in the constant block expected by the morphology kernels, and the
  * packed-parameter block sizes of the three small networks (see mcaq_b200/constants.py) */
 #define MCAQ_CONSTS_FLOATS     192
-#define MCAQ_CMLP_FLOATS       2881   /* complexity_mlp: 8-64-LN-32-LN-1            */
-#define MCAQ_MAPPER_FLOATS     4609   /* mapping_network with BN folded to (alpha,beta) */
-#define MCAQ_SOFTMASK_FLOATS   195    /* conv3x3(2->8)+b, conv1x1(8->2)+b, 5x5 smooth  */
+#define MCAQ_CMLP_FLOATS       2884   /* complexity_mlp 8-64-LN-32-LN-1: W0^T[8][64] b0 g1 be1 W3^T[64][32] b3 g4 be4 W6[32] b6 pad3 */
+#define MCAQ_MAPPER_FLOATS     4612   /* mapping_network, BN folded: W0^T[3][32] (b,alpha,beta)[32] W3^T[32][64] (..)[64] W6^T[64][32] (..)[32] W9[32] b9 pad3 */
+#define MCAQ_SOFTMASK_FLOATS   196    /* conv3x3(2->8)+b, conv1x1(8->2)+b, 5x5 smooth, pad1; all three blocks 16-byte aligned */
 
 MCAQ_API int mcaq_abi_version(void);
 MCAQ_API const char* mcaq_error_string(int code);

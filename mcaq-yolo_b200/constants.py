@@ -13,9 +13,9 @@ import numpy as np
 import torch
 
 CONSTS_FLOATS = 192
-CMLP_FLOATS = 2881
-MAPPER_FLOATS = 4609
-SOFTMASK_FLOATS = 195
+CMLP_FLOATS = 2884
+MAPPER_FLOATS = 4612
+SOFTMASK_FLOATS = 196
 
 _CANNY_TAPS = ['0x1.be5f10p-5', '0x1.f41fd8p-3', '0x1.9c4868p-2', '0x1.f41fd8p-3', '0x1.be5f10p-5']
 _ADAPT_TAPS = ['0x1.20c256p-7', '0x1.bcb868p-6', '0x1.0ab508p-4', '0x1.f2464cp-4', '0x1.6a7e1cp-3',
@@ -83,7 +83,10 @@ def pack_complexity_mlp(seq) -> torch.Tensor:
           seq[4].weight, seq[4].bias, seq[6].weight, seq[6].bias]
 
     def build():
-        out = _flat(*ts)
+        # layout the kernels stage into shared memory as is: first / second layer weights transposed
+        # to [k][unit] (conflict-free per-lane reads), three pad floats (16-byte copies)
+        out = _flat(seq[0].weight.t(), seq[0].bias, seq[1].weight, seq[1].bias, seq[3].weight.t(), seq[3].bias,
+                    seq[4].weight, seq[4].bias, seq[6].weight, seq[6].bias, seq[6].bias.new_zeros(3))
         assert out.numel() == CMLP_FLOATS, out.numel()
         return out
     return _cached(seq, "cmlp", ts, build)
@@ -110,8 +113,8 @@ def pack_mapping_network(seq) -> torch.Tensor:
         parts = []
         for li, bi in ((0, 1), (3, 4), (6, 7)):
             a, b = fold_batchnorm(seq[bi])
-            parts += [seq[li].weight, seq[li].bias, a, b]
-        parts += [seq[9].weight, seq[9].bias]
+            parts += [seq[li].weight.t(), seq[li].bias, a, b]          # weights as [k][unit]
+        parts += [seq[9].weight, seq[9].bias, seq[9].bias.new_zeros(3)]
         out = _flat(*parts)
         assert out.numel() == MAPPER_FLOATS, out.numel()
         return out
@@ -124,7 +127,7 @@ def pack_soft_mask(soft_mask) -> torch.Tensor:
           soft_mask.net[2].bias, soft_mask.smooth_kernel]
 
     def build():
-        out = _flat(*ts)
+        out = _flat(*ts, soft_mask.smooth_kernel.new_zeros(1))
         assert out.numel() == SOFTMASK_FLOATS, out.numel()
         return out
     return _cached(soft_mask, "softmask", ts, build)

@@ -2,24 +2,36 @@
 // the same launch by the complexity MLP + bilateral filter, the bit mapper and the soft mask
 // (the whole "between the two HBM sweeps" part of the hook in one kernel).
 //
-// One CTA per image.  The cropped gray plane (Hc x Wc fp32) lives in shared memory with one
-// scratch plane; binary maps (adaptive mask, Canny strong/weak/edge) are 1-bit planes (32 pixels
-// per word, built with warp ballots) so hysteresis, erosion, Euler quads and box counting are
-// word-parallel bit operations.  Stages (CTA barrier between each):
+// An image is split by tile rows over the `ns` CTAs of a thread-block cluster.  Each CTA keeps only
+// its band of the float planes (plus the stencil halos, recomputed locally) in shared memory:
+//   G   normalised gray, rows [r_lo-5, r_hi+5), two zero columns each side (zero rows outside the image)
+//   BL  255 * blur5x5(G), rows [r_lo-2, r_hi+2), one zero column each side
+//   MAG |Sobel(BL)| (L1),  rows [r_lo-1, r_hi+1)
+// Binary maps (adaptive mask, NMS direction, Canny strong / weak / edge) are 1-bit planes (32 pixels
+// per word, built with warp ballots) indexed by image row; the strong / weak / adaptive planes are
+// all-gathered through distributed shared memory, so hysteresis, erosion, Euler quads and box
+// counting are word-parallel bit operations on whole-image planes.
 //
-//   S0  gray = sum/C, per-image min/max            S7  Otsu (fp64 warp scan, first argmax) on warp 0
-//   S1  normalise to [0,1], P1 = 255*gray              while the other warps do S8
-//   S3  11x11 adaptive threshold -> BIN bits       S8  |Sobel(255*blur)| -> P0
-//   S4  LBP histograms, Sobel(gray) row sums       S9  NMS + double threshold -> strong/weak bits
-//   S5  phi2 (entropy), phi3 (gradient variance)   S10 8 constrained dilations (hysteresis)
-//   S6  5x5 blur -> P1, 256-bin histogram          S11 tile counts: edge, area, perimeter, Euler, boxes
-//                                                  S12 phi1, phi4, phi5, interactions
-//   N1  complexity MLP + bilateral   N2  bit mapper   N3  soft mask tiles + full-resolution m
+// Every pixel stage is organised as "one thread owns a column, a warp owns 32 adjacent columns and
+// walks a run of rows": stencil inputs slide through registers, there is no per-pixel index
+// arithmetic, and tile statistics are accumulated down the column in registers and combined across
+// the tile's lanes once per tile.  Stages between two barriers (blur + Otsu histogram, adaptive
+// threshold, LBP + gradient variance, soft-mask activity) are independent warp tasks.
 //
-// The 11x11 and 5x5 stencils are register-tiled (4 output rows per thread share their input
-// rows) with the taps as FFMA immediates (mcaq_consts.cuh), accumulation order per output =
-// row-major FMA chain from 0, exactly the oracle's.  Arithmetic is otherwise separately rounded
-// fp32; log tables are fp64-rounded literals; Otsu sums are exact in fp64.
+//   L   gray = sum / C (band + halo), band min / max      -> cluster exchange of min / max
+//   N   normalise in place (morphology.py:378-383)
+//   T1  tasks: 5x5 blur -> BL + histogram | 11x11 adaptive threshold -> BIN | LBP + Sobel(G) -> phi2, phi3
+//              | tile activity of sum_c|x| (soft mask)
+//   T2  |Sobel(BL)| -> MAG, NMS direction bits         -> cluster sync (histogram complete)
+//   T3  Otsu (every warp, fp64 scan), NMS + double threshold -> STRONG / WEAK  -> cluster sync
+//   T4  hysteresis: 8 constrained dilations held in registers (lane = row) -> EDGE
+//   T5  integer tile counts (edge, area, perimeter, Euler, boxes) -> phi1, phi4, phi5, interactions
+//   N1  complexity MLP -> gather -> bilateral   N2  bit mapper   N3  soft-mask head -> gather -> m
+//
+// Arithmetic contract = oracle/mcaq_oracle.py: stencils are FMA chains over the taps in row-major
+// order from 0 (taps are FFMA immediates from mcaq_consts.cuh), everything else separately rounded
+// fp32; float tile sums are column sums top-to-bottom added left-to-right; log tables are
+// fp64-rounded literals; Otsu sums are exact in fp64.
 #include <cooperative_groups.h>
 
 #include "tile_nets.cuh"
@@ -28,16 +40,17 @@ namespace cg = cooperative_groups;
 
 namespace mcaq {
 
-constexpr int MORPH_THREADS = 512;
-constexpr int RT = 4;    // output rows per thread in the stencil stages
+constexpr int MORPH_MAX_THREADS = 256;
 
 struct MorphGeom {
   int B, C, H, W, tile, ht, wt, Hc, Wc, WW, ntiles, S;
+  int ns;             // CTAs per image (thread-block cluster size)
+  int band_max;       // largest band (rows) of a CTA
+  int gs, bs;         // row strides of G (Wc + 4) and BL (Wc + 2)
+  int aligned;        // H == Hc && W == Wc: soft-mask windows are the analyzer's tiles
   // shared-memory layout, offsets in 4-byte words
-  int off_lbp;      // 10 ints per tile (inside P1 when it fits next to rowsum, else separate)
-  int off_rowsum;   // Hc*wt float4, inside P1
-  int off_tail;     // BIN, STRONG, WEAK, phis5, phi8, cfin, bits, craw, act, mt, hist, hloc, red, mmx, luts
-  int ns;           // CTAs per image (thread-block cluster size): the image's tile rows are split
+  int off_bl, off_mag, off_bits, off_tiles, off_w, words;
+  int max_own;        // most tiles a CTA owns
 };
 
 struct FusedArgs {
@@ -67,42 +80,6 @@ struct FusedArgs {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-__device__ __forceinline__ uint32_t bp_get(const uint32_t* bp, int r, int k, int Hc, int WW) {
-  return (r < 0 || r >= Hc || k < 0 || k >= WW) ? 0u : bp[r * WW + k];
-}
-
-// Sobel responses at (r, x) with zero padding; FMA chain over the 3x3 taps in row-major order.
-template <bool SCALED>
-__device__ __forceinline__ void sobel_at(const float* p, int r, int x, int Hc, int Wc, float& gx, float& gy) {
-  float v[3][3];
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int rr = r + dy - 1;
-    const bool rok = rr >= 0 && rr < Hc;
-    const float* row = p + clampi(rr, 0, Hc - 1) * Wc;
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      if (dy == 1 && dx == 1) { v[1][1] = 0.f; continue; }
-      const int xx = x + dx - 1;
-      float t = row[clampi(xx, 0, Wc - 1)];
-      if (SCALED) t = __fmul_rn(t, 255.f);
-      v[dy][dx] = (rok && xx >= 0 && xx < Wc) ? t : 0.f;
-    }
-  }
-  float a = __fmul_rn(v[0][0], -1.f);
-  a = fmaf(v[0][2], 1.f, a);
-  a = fmaf(v[1][0], -2.f, a);
-  a = fmaf(v[1][2], 2.f, a);
-  a = fmaf(v[2][0], -1.f, a);
-  gx = fmaf(v[2][2], 1.f, a);
-  float c = __fmul_rn(v[0][0], -1.f);
-  c = fmaf(v[0][1], -2.f, c);
-  c = fmaf(v[0][2], -1.f, c);
-  c = fmaf(v[2][0], 1.f, c);
-  c = fmaf(v[2][1], 2.f, c);
-  gy = fmaf(v[2][2], 1.f, c);
-}
-
 // RN(x / d) with a precomputed rinv = RN(1/d): Markstein's correction in the normal range (swept
 // against div.rn in tests/test_gpu_division.py), plain division for zero / tiny / huge numerators.
 __device__ __forceinline__ float div_exact(float x, float d, float rinv) {
@@ -128,38 +105,427 @@ __device__ __forceinline__ int nms_bin(float gx, float gy) {
   return 3;
 }
 
-__global__ void __launch_bounds__(MORPH_THREADS, 1)
+// Sobel responses from a 3x3 window of zero-padded values: FMA chain over the taps in row-major
+// order (morphology.py:385-395); the centre tap is zero in both kernels.
+__device__ __forceinline__ void sobel3(float z00, float z01, float z02, float z10, float z12, float z20, float z21,
+                                       float z22, float& gx, float& gy) {
+  float a = __fmul_rn(z00, -1.f);
+  a = fmaf(z02, 1.f, a); a = fmaf(z10, -2.f, a); a = fmaf(z12, 2.f, a); a = fmaf(z20, -1.f, a);
+  gx = fmaf(z22, 1.f, a);
+  float c = __fmul_rn(z00, -1.f);
+  c = fmaf(z01, -2.f, c); c = fmaf(z02, -1.f, c); c = fmaf(z20, 1.f, c); c = fmaf(z21, 2.f, c);
+  gy = fmaf(z22, 1.f, c);
+}
+
+struct Ctx {
+  // planes (biased so that [r * stride + x] works with image coordinates)
+  const float* Gp; int gs;
+  float* BLp; int bs;
+  float* MAGp;
+  uint32_t *BIN, *DIR0, *DIR1, *STRONG, *WEAK, *EDGE;
+  int Hc, Wc, WW, tile, tshift, wt;
+  int r_lo, r_hi;
+  int ns, rank;
+};
+
+// ---- T1a: 5x5 Gaussian blur (zero padding) of rows [r0, r0+RT) -> BL = 255 * blur; Otsu histogram
+//      of the blurred value for band rows (morphology.py:485-493).  Equal bins of vertically adjacent
+//      pixels are merged before the shared-memory atomic.
+template <int RT>
+__device__ __forceinline__ void task_blur(const Ctx& c, int r0, int rend, int k, int lane, int* hloc) {
+  const int x = 32 * k + lane;
+  const bool valid = x < c.Wc;
+  const int xr = valid ? x : c.Wc - 1;
+  const float* base = c.Gp + (r0 - 2) * c.gs + xr - 2;
+  float acc[RT];
+#pragma unroll
+  for (int j = 0; j < RT; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int rr = 0; rr < RT + 4; ++rr) {
+    float v[5];
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx) v[kx] = base[rr * c.gs + kx];
+#pragma unroll
+    for (int j = 0; j < RT; ++j) {
+      const int ky = rr - j;
+      if (ky >= 0 && ky < 5) {
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) acc[j] = fmaf(v[kx], kc::CANNY[ky * 5 + kx], acc[j]);
+      }
+    }
+  }
+  int cur = -1, cnt = 0;
+#pragma unroll
+  for (int j = 0; j < RT; ++j) {
+    const int r = r0 + j;
+    if (valid && r < rend) {
+      c.BLp[r * c.bs + x] = __fmul_rn(acc[j], 255.f);
+      if (r >= c.r_lo && r < c.r_hi && acc[j] >= 0.f && acc[j] <= 1.f) {   // torch.histc(bins=256, min=0, max=1)
+        int bin = (int)__fmul_rn(acc[j], 256.f);
+        bin = min(bin, 255);
+        if (bin == cur) {
+          ++cnt;
+        } else {
+          if (cnt) atomicAdd(&hloc[cur], cnt);
+          cur = bin;
+          cnt = 1;
+        }
+      }
+    }
+  }
+  if (cnt) atomicAdd(&hloc[cur], cnt);
+}
+
+// ---- T1b: adaptive threshold, 11x11 Gaussian mean of 255*G with replicate borders, rows [r0, r0+RT)
+//      (morphology.py:550-573) -> BIN words (own plane and every peer's).
+template <int RT>
+__device__ __forceinline__ void task_adaptive(const Ctx& c, cg::cluster_group& cl, int r0, int k, int lane) {
+  const int x = 32 * k + lane;
+  const bool valid = x < c.Wc;
+  int xc[11];
+#pragma unroll
+  for (int j = 0; j < 11; ++j) xc[j] = clampi(x + j - 5, 0, c.Wc - 1);
+  float acc[RT], ctr[RT];
+#pragma unroll
+  for (int j = 0; j < RT; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int rr = 0; rr < RT + 10; ++rr) {
+    const float* row = c.Gp + clampi(r0 - 5 + rr, 0, c.Hc - 1) * c.gs;
+    float v[11];
+#pragma unroll
+    for (int kx = 0; kx < 11; ++kx) v[kx] = __fmul_rn(row[xc[kx]], 255.f);
+    if (rr >= 5 && rr < RT + 5) ctr[rr - 5] = v[5];
+#pragma unroll
+    for (int j = 0; j < RT; ++j) {
+      const int ky = rr - j;
+      if (ky >= 0 && ky < 11) {
+#pragma unroll
+        for (int kx = 0; kx < 11; ++kx) acc[j] = fmaf(v[kx], kc::ADAPT[ky * 11 + kx], acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RT; ++j) {
+    const bool bit = valid && (ctr[j] > __fsub_rn(acc[j], 2.0f));
+    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+    if (lane < c.ns) {
+      uint32_t* dst = lane == 0 ? c.BIN : cl.map_shared_rank(c.BIN, (c.rank + lane) % c.ns);
+      dst[(r0 + j) * c.WW + k] = word;
+    }
+  }
+}
+
+// ---- T1c: uniform-LBP histogram (morphology.py:623-652) and Sobel(G) statistics (654-670) of the
+//      tiles of tile row ty under word k -> phi2, phi3.
+__device__ __forceinline__ void task_lbp_var(const Ctx& c, int ty, int k, int lane, const float* lutp, float* phis,
+                                             int* __restrict__ lbp_dbg) {
+  const int x = 32 * k + lane;
+  const bool valid = x < c.Wc;
+  const int xr = valid ? x : c.Wc - 1;
+  const bool x0 = xr == 0, xN = xr == c.Wc - 1;
+  const int tile = c.tile;
+  const int r0 = ty * tile;
+  const float* p = c.Gp + (r0 - 1) * c.gs + xr;
+  // window rows: a = above, m = current, b = below; L / R zero padded, Lr / Rr replicate padded
+  float aL = p[-1], aC = p[0], aR = p[1];
+  p += c.gs;
+  float mL = p[-1], mC = p[0], mR = p[1];
+  float aLr = x0 ? aC : aL, aRr = xN ? aC : aR;
+  float mLr = x0 ? mC : mL, mRr = xN ? mC : mR;
+  const bool top = r0 == 0, bot = r0 + tile == c.Hc;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  unsigned long long cnt = 0ull;                          // ten 6-bit counters (a column has <= 32 pixels)
+  for (int j = 0; j < tile; ++j) {
+    p += c.gs;
+    const float bL = p[-1], bC = p[0], bR = p[1];
+    const float bLr = x0 ? bC : bL, bRr = xN ? bC : bR;
+    // replicate padding in y: the row above row 0 is row 0, the row below the last row is the last row
+    const bool rt = top && j == 0, rb = bot && j == tile - 1;
+    const float uL = rt ? mLr : aLr, uC = rt ? mC : aC, uR = rt ? mRr : aRr;
+    const float dL = rb ? mLr : bLr, dC = rb ? mC : bC, dR = rb ? mRr : bRr;
+    // neighbour order (-1,-1),(-1,0),(-1,1),(0,1),(1,1),(1,0),(1,-1),(0,-1)  (morphology.py:634)
+    const uint32_t code = (uint32_t)(uL >= mC) | ((uint32_t)(uC >= mC) << 1) | ((uint32_t)(uR >= mC) << 2) |
+                          ((uint32_t)(mRr >= mC) << 3) | ((uint32_t)(dR >= mC) << 4) | ((uint32_t)(dC >= mC) << 5) |
+                          ((uint32_t)(dL >= mC) << 6) | ((uint32_t)(mLr >= mC) << 7);
+    const uint32_t rot = ((code << 1) | (code >> 7)) & 0xffu;
+    const int label = __popc(code ^ rot) <= 2 ? __popc(code) : 9;
+    cnt += 1ull << (6 * label);
+    float gx, gy;
+    sobel3(aL, aC, aR, mL, mR, bL, bC, bR, gx, gy);
+    s0 = __fadd_rn(s0, gx);
+    s1 = __fadd_rn(s1, __fmul_rn(gx, gx));
+    s2 = __fadd_rn(s2, gy);
+    s3 = __fadd_rn(s3, __fmul_rn(gy, gy));
+    aL = mL; aC = mC; aR = mR; aLr = mLr; aRr = mRr;
+    mL = bL; mC = bC; mR = bR; mLr = bLr; mRr = bRr;
+  }
+  // column sums left-to-right over the tile's lanes (leader = first lane of the tile)
+  const float q0 = s0, q1 = s1, q2 = s2, q3 = s3;
+  for (int j = 1; j < tile; ++j) {
+    s0 = __fadd_rn(s0, __shfl_down_sync(0xffffffffu, q0, j));
+    s1 = __fadd_rn(s1, __shfl_down_sync(0xffffffffu, q1, j));
+    s2 = __fadd_rn(s2, __shfl_down_sync(0xffffffffu, q2, j));
+    s3 = __fadd_rn(s3, __shfl_down_sync(0xffffffffu, q3, j));
+  }
+  // label counts: five registers of two 16-bit counters, butterfly over the tile's lanes
+  uint32_t h[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    h[i] = (uint32_t)((cnt >> (12 * i)) & 63ull) | ((uint32_t)((cnt >> (12 * i + 6)) & 63ull) << 16);
+  if (!valid) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) h[i] = 0;
+  }
+  for (int o = tile >> 1; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) h[i] += __shfl_xor_sync(0xffffffffu, h[i], o);
+  }
+  if (valid && (lane & (tile - 1)) == 0) {
+    const int t = ty * c.wt + (x >> c.tshift);
+    const float ntile2 = (float)(tile * tile);
+    float ent = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 10; ++kk) {
+      const int n = (h[kk >> 1] >> (16 * (kk & 1))) & 0xffff;
+      if (lbp_dbg) lbp_dbg[t * 10 + kk] = n;
+      const float pr = __fdiv_rn((float)n, ntile2);
+      ent = __fadd_rn(ent, __fmul_rn(pr, lutp[n]));                // log2(p + 1e-10)
+    }
+    phis[t * 2 + 0] = __fdiv_rn(-ent, kc::LOG2_10);
+    const float mx_ = __fdiv_rn(s0, ntile2), mx2 = __fdiv_rn(s1, ntile2);
+    const float my_ = __fdiv_rn(s2, ntile2), my2 = __fdiv_rn(s3, ntile2);
+    const float vx = fmaxf(__fsub_rn(mx2, __fmul_rn(mx_, mx_)), 0.f);
+    const float vy = fmaxf(__fsub_rn(my2, __fmul_rn(my_, my_)), 0.f);
+    const float v = __fadd_rn(vx, vy);
+    phis[t * 2 + 1] = __fdiv_rn(v, __fadd_rn(v, 1.0f));
+  }
+}
+
+// ---- T1d: tile activity of the soft mask (quantization.py:224-226) for tile row ty under word k when
+//      the adaptive-pool windows are the analyzer's tiles: mean over the tile of sum_c|x| / C.
+__device__ __forceinline__ void task_act(const Ctx& c, const float* __restrict__ ap, int W, float fC, float rC,
+                                         int ty, int k, int lane, float* act) {
+  const int x = 32 * k + lane;
+  const bool valid = x < c.Wc;
+  const int xr = valid ? x : c.Wc - 1;
+  const int tile = c.tile;
+  const float* p = ap + (long long)(ty * tile) * W + xr;
+  float s = 0.f;
+  for (int j0 = 0; j0 < tile; j0 += 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (j0 + u) * W);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s = __fadd_rn(s, div_exact(v[u], fC, rC));
+  }
+  const float q = s;
+  for (int j = 1; j < tile; ++j) s = __fadd_rn(s, __shfl_down_sync(0xffffffffu, q, j));
+  if (valid && (lane & (tile - 1)) == 0)
+    act[ty * c.wt + (x >> c.tshift)] = __fdiv_rn(s, (float)(tile * tile));
+}
+
+// ---- T2: L1 magnitude of Sobel(BL) (morphology.py:496-497) for rows [r0, min(r0+RT, rend)) -> MAG and
+//      the NMS direction bin as two bit planes.
+template <int RT>
+__device__ __forceinline__ void task_mag(const Ctx& c, int r0, int rend, int k, int lane) {
+  const int x = 32 * k + lane;
+  const bool valid = x < c.Wc;
+  const int xr = valid ? x : c.Wc - 1;
+  const float* p = c.BLp + (r0 - 1) * c.bs + xr;
+  float aL = p[-1], aC = p[0], aR = p[1];
+  p += c.bs;
+  float mL = p[-1], mC = p[0], mR = p[1];
+#pragma unroll
+  for (int j = 0; j < RT; ++j) {
+    const int r = r0 + j;
+    if (r < rend) {                                   // warp-uniform
+      p += c.bs;
+      const float bL = p[-1], bC = p[0], bR = p[1];
+      float gx, gy;
+      sobel3(aL, aC, aR, mL, mR, bL, bC, bR, gx, gy);
+      int bin = 0;
+      if (valid) {
+        c.MAGp[r * c.Wc + x] = __fadd_rn(fabsf(gx), fabsf(gy));
+        bin = nms_bin(gx, gy);
+      }
+      const uint32_t d0 = __ballot_sync(0xffffffffu, bin & 1);
+      const uint32_t d1 = __ballot_sync(0xffffffffu, bin & 2);
+      if (lane == 0) { c.DIR0[r * c.WW + k] = d0; c.DIR1[r * c.WW + k] = d1; }
+      aL = mL; aC = mC; aR = mR;
+      mL = bL; mC = bC; mR = bR;
+      (void)mC;
+    }
+  }
+}
+
+// ---- T3: non-maximum suppression + double threshold (morphology.py:426-449, 500-502) for band rows
+//      [r0, r0+RT) -> STRONG / WEAK words (own planes and every peer's).
+template <int RT>
+__device__ __forceinline__ void task_nms(const Ctx& c, cg::cluster_group& cl, int r0, int k, int lane, float thr_hi,
+                                         float thr_lo) {
+  const int x = 32 * k + lane;
+  const bool valid = x < c.Wc;
+  const int xr = valid ? x : c.Wc - 1;
+  const int xl = max(xr - 1, 0), xg = min(xr + 1, c.Wc - 1);
+  const float* ra = c.MAGp + max(r0 - 1, 0) * c.Wc;
+  float aL = ra[xl], aC = ra[xr], aR = ra[xg];
+  const float* rm = c.MAGp + r0 * c.Wc;
+  float mL = rm[xl], mC = rm[xr], mR = rm[xg];
+#pragma unroll
+  for (int j = 0; j < RT; ++j) {
+    const int r = r0 + j;
+    const float* rb = c.MAGp + min(r + 1, c.Hc - 1) * c.Wc;
+    const float bL = rb[xl], bC = rb[xr], bR = rb[xg];
+    const uint32_t d0 = (c.DIR0[r * c.WW + k] >> lane) & 1u, d1 = (c.DIR1[r * c.WW + k] >> lane) & 1u;
+    // bin 0: (0,+1)/(0,-1)   1: (-1,+1)/(+1,-1)   2: (-1,0)/(+1,0)   3: (-1,-1)/(+1,+1)
+    const float n1 = d1 ? (d0 ? aL : aC) : (d0 ? aR : mR);
+    const float n2 = d1 ? (d0 ? bR : bC) : (d0 ? bL : mL);
+    const float nms = (mC >= n1 && mC >= n2) ? mC : 0.f;
+    const uint32_t ws = __ballot_sync(0xffffffffu, valid && nms > thr_hi);
+    const uint32_t ww = __ballot_sync(0xffffffffu, valid && nms > thr_lo);
+    if (lane < c.ns) {
+      const int pr = (c.rank + lane) % c.ns;
+      uint32_t* ds = lane == 0 ? c.STRONG : cl.map_shared_rank(c.STRONG, pr);
+      uint32_t* dw = lane == 0 ? c.WEAK : cl.map_shared_rank(c.WEAK, pr);
+      ds[r * c.WW + k] = ws;
+      dw[r * c.WW + k] = ww;
+    }
+    aL = mL; aC = mC; aR = mR;
+    mL = bL; mC = bC; mR = bR;
+  }
+}
+
+// Otsu threshold from the whole-image histogram (morphology.py:397-418), computed by one warp; every
+// lane returns the same values.  fp64 prefix sums of fp32 terms are exact.
+__device__ __forceinline__ void otsu_warp(const int* hist, int lane, float& thr255, int& otsu_bin) {
+  int cnt[8];
+  int tot_i = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { cnt[j] = hist[lane * 8 + j]; tot_i += cnt[j]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot_i += __shfl_xor_sync(0xffffffffu, tot_i, o);
+  const float tot = fmaxf((float)tot_i, 1.0f);
+  float p[8], pc[8];
+  double so = 0.0, sm = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    p[j] = __fdiv_rn((float)cnt[j], tot);
+    const float center = (float)(2 * (lane * 8 + j) + 1) * 0.001953125f;   // (i + 0.5) / 256, exact
+    pc[j] = __fmul_rn(p[j], center);
+    so += (double)p[j];
+    sm += (double)pc[j];
+  }
+  double io = so, im = sm;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double to = __shfl_up_sync(0xffffffffu, io, o);
+    const double tm = __shfl_up_sync(0xffffffffu, im, o);
+    if (lane >= o) { io += to; im += tm; }
+  }
+  const float mu_t = (float)__shfl_sync(0xffffffffu, im, 31);
+  double ro = io - so, rm = im - sm;
+  float best = -INFINITY;
+  int best_i = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ro += (double)p[j];
+    rm += (double)pc[j];
+    const float omega = (float)ro, mu = (float)rm;
+    float num = __fsub_rn(__fmul_rn(mu_t, omega), mu);
+    num = __fmul_rn(num, num);
+    const float dn = __fadd_rn(__fmul_rn(omega, __fsub_rn(1.0f, omega)), 1e-12f);
+    const float sig = __fdiv_rn(num, dn);
+    if (sig > best) { best = sig; best_i = lane * 8 + j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  const float thr = (float)(2 * best_i + 1) * 0.001953125f;
+  thr255 = __fmul_rn(thr, 255.f);
+  otsu_bin = best_i;
+}
+
+// ---- T4: hysteresis = 8 constrained 3x3 dilations (morphology.py:504-509) of a block of 32 rows held
+//      in registers (lane = row R0 + lane, up to 5 words per row); after 8 steps the 16 middle rows are
+//      exact, so blocks advance by 16 rows.
+__device__ __forceinline__ void task_hysteresis(const Ctx& c, int R0, int lane) {
+  const int row = R0 + lane;
+  const bool rok = row >= 0 && row < c.Hc;
+  uint32_t e[5], w[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const bool ok = rok && k < c.WW;
+    e[k] = ok ? c.STRONG[row * c.WW + k] : 0u;
+    w[k] = ok ? c.WEAK[row * c.WW + k] : 0u;
+  }
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    uint32_t h[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const uint32_t cc = e[k];
+      const uint32_t l = k > 0 ? e[k - 1] : 0u;
+      const uint32_t rn = k < 4 ? e[k + 1] : 0u;
+      h[k] = cc | (cc << 1) | (l >> 31) | (cc >> 1) | (rn << 31);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if (k < c.WW) {                                   // warp-uniform
+        uint32_t up = __shfl_up_sync(0xffffffffu, h[k], 1);
+        uint32_t dn = __shfl_down_sync(0xffffffffu, h[k], 1);
+        if (lane == 0) up = 0u;
+        if (lane == 31) dn = 0u;
+        e[k] |= w[k] & (h[k] | up | dn);
+      }
+    }
+  }
+  if (lane >= 8 && lane < 24 && row >= c.r_lo && row < c.r_hi) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (k < c.WW) c.EDGE[row * c.WW + k] = e[k];
+  }
+}
+
+__global__ void __launch_bounds__(MORPH_MAX_THREADS, 2)
 morph_fused_kernel(const FusedArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const MorphGeom& g = A.g;
-  const int NP = g.Hc * g.Wc;
+  float* S = reinterpret_cast<float*>(smem_raw);
   const int NW = g.Hc * g.WW;
-  float* P0 = reinterpret_cast<float*>(smem_raw);
-  float* P1 = P0 + NP;
-  uint32_t* BIN = reinterpret_cast<uint32_t*>(P0 + g.off_tail);
-  uint32_t* STRONG = BIN + NW;
+  float* G = S;
+  float* BL = S + g.off_bl;
+  float* MAG = S + g.off_mag;
+  uint32_t* BIN = reinterpret_cast<uint32_t*>(S + g.off_bits);
+  uint32_t* DIR0 = BIN + NW;
+  uint32_t* DIR1 = DIR0 + NW;
+  uint32_t* STRONG = DIR1 + NW;
   uint32_t* WEAK = STRONG + NW;
-  float* phis = reinterpret_cast<float*>(WEAK + NW);          // [ntiles][5]  (phi2, phi3 parked here)
-  float* phi8 = phis + g.ntiles * 5;                          // [ntiles][8]
-  float* cfin = phi8 + g.ntiles * 8;                          // [ntiles] complexity
-  float* bits_s = cfin + g.ntiles;                            // [ntiles] bits
-  float* craw_s = bits_s + g.ntiles;                          // [ntiles] complexity before the bilateral
-  float* act_s = craw_s + g.ntiles;                           // [ntiles] tile activity (soft mask)
-  float* mt_s = act_s + g.ntiles;                             // [ntiles] tile mask
-  int* hist = reinterpret_cast<int*>(mt_s + g.ntiles);        // [256] whole-image Otsu histogram
-  int* hloc = hist + 256;                                     // [256] this CTA's band
-  float* red = reinterpret_cast<float*>(hloc + 256);          // [64]
-  float* mmx = red + 64;                                      // [16] per-rank min/max | per-rank act max
-  float* lutn = mmx + 16;                                     // [260] log(N + 1)
-  float* lutp = lutn + 260;                                   // [tile^2 + 1] log2(k / tile^2 + 1e-10)
-  int* lbp_hist = reinterpret_cast<int*>(P0 + g.off_lbp);     // [ntiles][10]
-  float* rowsum = P0 + g.off_rowsum;                          // [Hc][wt][4]
+  uint32_t* EDGE = WEAK + NW;
+  float* phi8 = S + g.off_tiles;                               // [ntiles][8]  (16-byte aligned rows)
+  float* phis = phi8 + g.ntiles * 8;                           // [ntiles][2]  phi2, phi3
+  float* craw_s = phis + g.ntiles * 2;                         // [ntiles] complexity before the bilateral
+  float* cfin = craw_s + g.ntiles;                             // [ntiles] complexity
+  float* bits_s = cfin + g.ntiles;                             // [ntiles] bits
+  float* act_s = bits_s + g.ntiles;                            // [ntiles] tile activity (soft mask)
+  float* mt_s = act_s + g.ntiles;                              // [ntiles] tile mask
+  int* acc = reinterpret_cast<int*>(mt_s + g.ntiles);          // [ntiles][9] integer tile counts
+  int* hist = acc + g.ntiles * 9;                              // [256] whole-image Otsu histogram
+  int* hloc = hist + 256;                                      // [256] this CTA's band
+  float* red = reinterpret_cast<float*>(hloc + 256);           // [64]
+  float* mmx = red + 64;                                       // [16] per-rank min / max
+  float* lutn = mmx + 16;                                      // [260] log(N + 1)
+  float* lutp = lutn + 260;                                    // [tile^2 + 1 (+pad)] log2(k / tile^2 + 1e-10)
+  float* wts = S + g.off_w;                                    // CMLP | MAPPER | SOFTMASK parameter blocks
+  float* w_cmlp = wts;
+  float* w_map = wts + CMLP_SMEM_FLOATS;
+  float* w_sm = w_map + MAPPER_SMEM_FLOATS;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NT = blockDim.x, nwarps = NT >> 5;
   const int tile = g.tile, Hc = g.Hc, Wc = g.Wc, WW = g.WW, wt = g.wt;
-  // an image is split over the ns CTAs of a thread-block cluster by tile rows; every CTA keeps
-  // full-size planes and all-gathers the bands the others produced through DSMEM
   cg::cluster_group cl = cg::this_cluster();
   const int ns = g.ns;
   const int rank = ns > 1 ? (int)cl.block_rank() : 0;
@@ -167,58 +533,78 @@ morph_fused_kernel(const FusedArgs A) {
   const int tr0 = (g.ht * rank) / ns, tr1 = (g.ht * (rank + 1)) / ns;   // own tile rows
   const int r_lo = tr0 * tile, r_hi = tr1 * tile;                       // own pixel rows
   const int t_lo = tr0 * wt, t_hi = tr1 * wt;                           // own tiles
-  auto csync = [&]() { if (ns > 1) cl.sync(); else __syncthreads(); };
-  auto publish = [&](auto* base, int off, int n) {                      // my [off, off+n) -> every peer
-    for (int pr = 1; pr < ns; ++pr) {
-      auto* dst = cl.map_shared_rank(base, (rank + pr) % ns);
-      for (int i = tid; i < n; i += NT) dst[off + i] = base[off + i];
-    }
-  };
   const int tshift = 31 - __clz(tile);
   const float ntile2 = (float)(tile * tile);
   long long* clk = A.clk;
 #define STAGE_CLOCK(k) do { if (clk && tid == 0 && rank == 0) clk[(long long)b * 16 + (k)] = clock64(); } while (0)
   STAGE_CLOCK(0);
-  {
-    const float* src = g.tile == 4 ? kc::LOG2P_4 : (g.tile == 8 ? kc::LOG2P_8 : (g.tile == 16 ? kc::LOG2P_16 : kc::LOG2P_32));
-    for (int i = tid; i < 257; i += NT) lutn[i] = __ldg(kc::LOGN1 + i);
-    for (int i = tid; i <= g.tile * g.tile; i += NT) lutp[i] = __ldg(src + i);
-  }
+  if (ns > 1) cl.barrier_arrive();      // paired with the wait before the first DSMEM store
 
+  // parameter blocks: asynchronous 16-byte copies, consumed after the pixel stages
+  if (A.cmlp) {
+    copy_params_async(A.cmlp, w_cmlp, CMLP_SMEM_FLOATS);
+    if (A.mapper) copy_params_async(A.mapper, w_map, MAPPER_SMEM_FLOATS);
+    if (A.softmask) copy_params_async(A.softmask, w_sm, SOFTMASK_SMEM_FLOATS);
+  }
+  {
+    const float* src = tile == 4 ? kc::LOG2P_4 : (tile == 8 ? kc::LOG2P_8 : (tile == 16 ? kc::LOG2P_16 : kc::LOG2P_32));
+    for (int i = tid; i < 257; i += NT) lutn[i] = __ldg(kc::LOGN1 + i);
+    for (int i = tid; i <= tile * tile; i += NT) lutp[i] = __ldg(src + i);
+  }
   // K1 -> K3 hand-off of the per-channel ranges: decode the atomics' integer keys to floats and
   // re-arm the keys for the next sweep (stream order: K1 done, K3 not started)
   if (A.keys && blockIdx.x == 0) {
-    for (int c = tid; c < g.C; c += NT) {
-      A.packed[c] = key_float(A.keys[c]);
-      A.packed[g.C + c] = -key_float(A.keys[g.C + c]);
-      A.keys[c] = MCAQ_KEY_POS_INF;
-      A.keys[g.C + c] = MCAQ_KEY_NEG_INF;
+    for (int ch = tid; ch < g.C; ch += NT) {
+      A.packed[ch] = key_float(A.keys[ch]);
+      A.packed[g.C + ch] = -key_float(A.keys[g.C + ch]);
+      A.keys[ch] = MCAQ_KEY_POS_INF;
+      A.keys[g.C + ch] = MCAQ_KEY_NEG_INF;
     }
   }
 
-  // ---- S0: gray = sum / C over the cropped plane, per-image min / max --------------------
+  Ctx c;
+  c.gs = g.gs; c.bs = g.bs;
+  c.Gp = G + (5 - r_lo) * g.gs + 2;
+  c.BLp = BL + (2 - r_lo) * g.bs + 1;
+  c.MAGp = MAG + (1 - r_lo) * Wc;
+  c.BIN = BIN; c.DIR0 = DIR0; c.DIR1 = DIR1; c.STRONG = STRONG; c.WEAK = WEAK; c.EDGE = EDGE;
+  c.Hc = Hc; c.Wc = Wc; c.WW = WW; c.tile = tile; c.tshift = tshift; c.wt = wt;
+  c.r_lo = r_lo; c.r_hi = r_hi; c.ns = ns; c.rank = rank;
+  float* Gw = G + (5 - r_lo) * g.gs + 2;                   // writable alias of c.Gp
+
+  // ---- L: gray = sum / C for rows [r_lo-5, r_hi+5) (zero outside the image and in the pad
+  //      columns), min / max over the band; BL and the histograms start as zeros -------------------
   const float* sp = A.sum_plane + (long long)b * g.H * g.W;
   const float fC = (float)g.C;
   const float rC = __frcp_rn(fC);
   float lmin = INFINITY, lmax = -INFINITY;
   for (int i = tid; i < 512; i += NT) hist[i] = 0;               // hist + hloc
-  if (ns > 1) cl.sync();      // every CTA of the cluster is resident before the first DSMEM store
-  const int band_lo = r_lo * Wc, band_hi = r_hi * Wc;
-  for (int i0 = band_lo + tid; i0 < band_hi; i0 += 4 * NT) {
-    float v[4];
+  {
+    const int nbl = (r_hi - r_lo + 4) * g.bs;
+    for (int i = tid; i < nbl; i += NT) BL[i] = 0.f;
+  }
+  {
+    const int nrows = r_hi - r_lo + 10;
+    for (int lr0 = warp * 4; lr0 < nrows; lr0 += nwarps * 4) {
+      for (int c0 = lane; c0 < g.gs; c0 += 32) {
+        const int x = c0 - 2;
+        const bool xok = x >= 0 && x < Wc;
+        float v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * NT;
-      if (i < band_hi) { const int r = i / Wc, x = i - r * Wc; v[u] = __ldg(sp + r * g.W + x); }
-    }
+        for (int u = 0; u < 4; ++u) {
+          const int r = r_lo - 5 + lr0 + u;
+          v[u] = (xok && lr0 + u < nrows && r >= 0 && r < Hc) ? __ldg(sp + r * g.W + x) : 0.f;
+        }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * NT;
-      if (i < band_hi) {
-        const float q = div_exact(v[u], fC, rC);
-        P0[i] = q;
-        lmin = fminf(lmin, q);
-        lmax = fmaxf(lmax, q);
+        for (int u = 0; u < 4; ++u) {
+          const int r = r_lo - 5 + lr0 + u;
+          if (lr0 + u < nrows) {
+            const bool in = xok && r >= 0 && r < Hc;
+            const float q = in ? div_exact(v[u], fC, rC) : 0.f;
+            G[(lr0 + u) * g.gs + c0] = q;
+            if (in && r >= r_lo && r < r_hi) { lmin = fminf(lmin, q); lmax = fmaxf(lmax, q); }
+          }
+        }
       }
     }
   }
@@ -231,206 +617,68 @@ morph_fused_kernel(const FusedArgs A) {
   __syncthreads();
   float gmin = red[0], gmax = red[32];
   for (int w = 1; w < nwarps; ++w) { gmin = fminf(gmin, red[w]); gmax = fmaxf(gmax, red[32 + w]); }
-  if (ns > 1) {                                                   // all-gather raw gray bands and band min/max
-    if (tid == 0)
-      for (int pr = 0; pr < ns; ++pr) {
-        float* m = cl.map_shared_rank(mmx, pr);
-        m[2 * rank] = gmin;
-        m[2 * rank + 1] = gmax;
-      }
-    publish(P0, band_lo, band_hi - band_lo);
+  if (ns > 1) {                                                   // all-gather the band min / max
+    cl.barrier_wait();                                            // every CTA of the cluster is resident
+    if (tid < ns) {
+      float* m = cl.map_shared_rank(mmx, tid);
+      m[2 * rank] = gmin;
+      m[2 * rank + 1] = gmax;
+    }
     cl.sync();
     gmin = mmx[0]; gmax = mmx[1];
     for (int pr = 1; pr < ns; ++pr) { gmin = fminf(gmin, mmx[2 * pr]); gmax = fmaxf(gmax, mmx[2 * pr + 1]); }
   }
-  // ---- S1: normalise (morphology.py:378-383), P1 = 255 * gray ------------------------------
-  const float den = __fadd_rn(__fsub_rn(gmax, gmin), 1e-8f);
-  const float rden = __frcp_rn(den);
-  for (int i = tid; i < NP; i += NT) {
-    const float v = div_exact(__fsub_rn(P0[i], gmin), den, rden);
-    P0[i] = v;
-    P1[i] = __fmul_rn(v, 255.f);
-    if (A.gray_dbg && rank == 0) A.gray_dbg[(long long)b * NP + i] = v;
-  }
-  __syncthreads();
   STAGE_CLOCK(1);
-
-  // ---- S3: adaptive threshold, 11x11 Gaussian mean, replicate borders (morphology.py:550-573)
-  //      register tile: RT output rows share their 14 input rows; taps are immediates
-  const int nrg = (r_hi - r_lo) / RT;                            // band rows % 4 == 0 (tile >= 4)
-  for (int task = warp; task < nrg * WW; task += nwarps) {
-    const int rg = task / WW, k = task - rg * WW;
-    const int r0 = r_lo + rg * RT;
-    const int x = 32 * k + lane;
-    const bool valid = x < Wc;
-    int xc[11];
-#pragma unroll
-    for (int j = 0; j < 11; ++j) xc[j] = clampi(x + j - 5, 0, Wc - 1);
-    float acc[RT];
-#pragma unroll
-    for (int j = 0; j < RT; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int rr = 0; rr < RT + 10; ++rr) {
-      const float* row = P1 + clampi(r0 - 5 + rr, 0, Hc - 1) * Wc;
-      float v[11];
-#pragma unroll
-      for (int kx = 0; kx < 11; ++kx) v[kx] = row[xc[kx]];
-#pragma unroll
-      for (int j = 0; j < RT; ++j) {
-        const int ky = rr - j;
-        if (ky >= 0 && ky < 11) {
-#pragma unroll
-          for (int kx = 0; kx < 11; ++kx) acc[j] = fmaf(v[kx], kc::ADAPT[ky * 11 + kx], acc[j]);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < RT; ++j) {
-      const bool bit = valid && (P1[(r0 + j) * Wc + min(x, Wc - 1)] > __fsub_rn(acc[j], 2.0f));
-      const uint32_t word = __ballot_sync(0xffffffffu, bit);
-      if (lane == 0) BIN[(r0 + j) * WW + k] = word;
-    }
-  }
-  __syncthreads();
-  if (ns > 1) publish(BIN, r_lo * WW, (r_hi - r_lo) * WW);        // visible to the peers after the next cluster sync
-  STAGE_CLOCK(2);
-  for (int i = tid; i < g.ntiles * 10; i += NT) lbp_hist[i] = 0;
-  __syncthreads();
-
-  // ---- S4: uniform-LBP histograms + Sobel(gray) tile-row sums ------------------------------
-  //      one 3x3 neighbourhood load serves both: LBP sees replicate borders, Sobel zero borders
-  const int nslot_b = (r_hi - r_lo) * WW;
-  for (int slot = warp; slot < nslot_b; slot += nwarps) {
-    const int r = r_lo + slot / WW, k = slot % WW;
-    const int x = 32 * k + lane;
-    const bool valid = x < Wc;
-    float gx = 0.f, gy = 0.f;
-    int key = -1;
-    if (valid) {
-      const bool up = r > 0, dn = r + 1 < Hc, lf = x > 0, rt = x + 1 < Wc;
-      const float* r0p = P0 + (up ? r - 1 : r) * Wc;
-      const float* r1p = P0 + r * Wc;
-      const float* r2p = P0 + (dn ? r + 1 : r) * Wc;
-      const int xl = lf ? x - 1 : x, xr = rt ? x + 1 : x;
-      const float v00 = r0p[xl], v01 = r0p[x], v02 = r0p[xr];
-      const float v10 = r1p[xl], c = r1p[x], v12 = r1p[xr];
-      const float v20 = r2p[xl], v21 = r2p[x], v22 = r2p[xr];
-      // neighbour order (-1,-1),(-1,0),(-1,1),(0,1),(1,1),(1,0),(1,-1),(0,-1)  (morphology.py:634)
-      uint32_t code = (uint32_t)(v00 >= c) | ((uint32_t)(v01 >= c) << 1) | ((uint32_t)(v02 >= c) << 2) |
-                      ((uint32_t)(v12 >= c) << 3) | ((uint32_t)(v22 >= c) << 4) | ((uint32_t)(v21 >= c) << 5) |
-                      ((uint32_t)(v20 >= c) << 6) | ((uint32_t)(v10 >= c) << 7);
-      const uint32_t rot = ((code << 1) | (code >> 7)) & 0xffu;
-      const int label = __popc(code ^ rot) <= 2 ? __popc(code) : 9;
-      key = ((r >> tshift) * wt + (x >> tshift)) * 10 + label;
-      // Sobel with zero padding: FMA chain over taps in row-major order (zero taps are no-ops)
-      const float z00 = (up && lf) ? v00 : 0.f, z01 = up ? v01 : 0.f, z02 = (up && rt) ? v02 : 0.f;
-      const float z10 = lf ? v10 : 0.f, z12 = rt ? v12 : 0.f;
-      const float z20 = (dn && lf) ? v20 : 0.f, z21 = dn ? v21 : 0.f, z22 = (dn && rt) ? v22 : 0.f;
-      float a = __fmul_rn(z00, -1.f);
-      a = fmaf(z02, 1.f, a); a = fmaf(z10, -2.f, a); a = fmaf(z12, 2.f, a); a = fmaf(z20, -1.f, a);
-      gx = fmaf(z22, 1.f, a);
-      float cc = __fmul_rn(z00, -1.f);
-      cc = fmaf(z01, -2.f, cc); cc = fmaf(z02, -1.f, cc); cc = fmaf(z20, 1.f, cc); cc = fmaf(z21, 2.f, cc);
-      gy = fmaf(z22, 1.f, cc);
-    }
-    {   // warp-aggregated histogram update: one shared-memory atomic per distinct (tile, label)
-      const unsigned peers = __match_any_sync(0xffffffffu, key);
-      if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(&lbp_hist[key], __popc(peers));
-    }
-    // sequential left-to-right sum of each tile-row segment (leaders: lane % tile == 0)
-    float s0 = gx, s1 = __fmul_rn(gx, gx), s2 = gy, s3 = __fmul_rn(gy, gy);
-    const float q0 = s0, q1 = s1, q2 = s2, q3 = s3;
-    for (int j = 1; j < tile; ++j) {
-      s0 = __fadd_rn(s0, __shfl_down_sync(0xffffffffu, q0, j));
-      s1 = __fadd_rn(s1, __shfl_down_sync(0xffffffffu, q1, j));
-      s2 = __fadd_rn(s2, __shfl_down_sync(0xffffffffu, q2, j));
-      s3 = __fadd_rn(s3, __shfl_down_sync(0xffffffffu, q3, j));
-    }
-    if (valid && (lane & (tile - 1)) == 0)
-      reinterpret_cast<float4*>(rowsum)[r * wt + (x >> tshift)] = make_float4(s0, s1, s2, s3);
-  }
-  __syncthreads();
-  STAGE_CLOCK(3);
-
-  // ---- S5: phi2 (LBP entropy, morphology.py:648-652) and phi3 (654-670) per tile -----------
+  // ---- N: normalise in place (morphology.py:378-383); rows outside the image stay zero ---------
   {
-    for (int t = t_lo + tid; t < t_hi; t += NT) {
-      const int ty = t / wt, tx = t - ty * wt;
-      float ent = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < 10; ++kk) {
-        const int cnt = lbp_hist[t * 10 + kk];
-        if (A.lbp_dbg) A.lbp_dbg[((long long)b * g.ntiles + t) * 10 + kk] = cnt;
-        const float p = __fdiv_rn((float)cnt, ntile2);
-        ent = __fadd_rn(ent, __fmul_rn(p, lutp[cnt]));             // log2(p + 1e-10)
+    const float den = __fadd_rn(__fsub_rn(gmax, gmin), 1e-8f);
+    const float rden = __frcp_rn(den);
+    const int ra = max(r_lo - 5, 0), rb = min(r_hi + 5, Hc);
+    for (int r = ra + warp; r < rb; r += nwarps) {
+      float* row = Gw + r * g.gs;
+      for (int x = lane; x < Wc; x += 32) {
+        const float v = div_exact(__fsub_rn(row[x], gmin), den, rden);
+        row[x] = v;
+        if (A.gray_dbg && r >= r_lo && r < r_hi) A.gray_dbg[(long long)b * Hc * Wc + r * Wc + x] = v;
       }
-      phis[t * 5 + 1] = __fdiv_rn(-ent, kc::LOG2_10);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int y = 0; y < tile; ++y) {
-        const float4 v = reinterpret_cast<const float4*>(rowsum)[(ty * tile + y) * wt + tx];
-        a0 = __fadd_rn(a0, v.x); a1 = __fadd_rn(a1, v.y); a2 = __fadd_rn(a2, v.z); a3 = __fadd_rn(a3, v.w);
-      }
-      const float mx_ = __fdiv_rn(a0, ntile2), mx2 = __fdiv_rn(a1, ntile2);
-      const float my_ = __fdiv_rn(a2, ntile2), my2 = __fdiv_rn(a3, ntile2);
-      const float vx = fmaxf(__fsub_rn(mx2, __fmul_rn(mx_, mx_)), 0.f);
-      const float vy = fmaxf(__fsub_rn(my2, __fmul_rn(my_, my_)), 0.f);
-      const float v = __fadd_rn(vx, vy);
-      phis[t * 5 + 2] = __fdiv_rn(v, __fadd_rn(v, 1.0f));
     }
   }
-  csync();           // every CTA is done with P1 = 255*gray; BIN bands have landed
-  STAGE_CLOCK(4);
+  __syncthreads();
+  STAGE_CLOCK(2);
 
-  // ---- S6: 5x5 Gaussian blur (zero padding) -> P1, Otsu histogram (morphology.py:485-493) --
-  float* P1r[3] = {P1, P1, P1};
-  float* P0r[3] = {P0, P0, P0};
-  for (int pr = 1; pr < ns; ++pr) {
-    P1r[pr - 1] = cl.map_shared_rank(P1, (rank + pr) % ns);
-    P0r[pr - 1] = cl.map_shared_rank(P0, (rank + pr) % ns);
-  }
-  for (int task = warp; task < nrg * WW; task += nwarps) {
-    const int rg = task / WW, k = task - rg * WW;
-    const int r0 = r_lo + rg * RT;
-    const int x = 32 * k + lane;
-    const bool valid = x < Wc;
-    int xc[5];
-    bool xok[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) { const int xx = x + j - 2; xok[j] = xx >= 0 && xx < Wc; xc[j] = clampi(xx, 0, Wc - 1); }
-    float acc[RT];
-#pragma unroll
-    for (int j = 0; j < RT; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int rr = 0; rr < RT + 4; ++rr) {
-      const int r = r0 - 2 + rr;
-      const bool rok = r >= 0 && r < Hc;
-      const float* row = P0 + clampi(r, 0, Hc - 1) * Wc;
-      float v[5];
-#pragma unroll
-      for (int kx = 0; kx < 5; ++kx) v[kx] = (rok && xok[kx]) ? row[xc[kx]] : 0.f;   // fma(0, w, acc) == acc
-#pragma unroll
-      for (int j = 0; j < RT; ++j) {
-        const int ky = rr - j;
-        if (ky >= 0 && ky < 5) {
-#pragma unroll
-          for (int kx = 0; kx < 5; ++kx) acc[j] = fmaf(v[kx], kc::CANNY[ky * 5 + kx], acc[j]);
-        }
+  // ---- T1: independent warp tasks on G ----------------------------------------------------------
+  {
+    const int b_lo = max(r_lo - 2, 0), b_hi = min(r_hi + 2, Hc);          // blur rows
+    const int nblur = ((b_hi - b_lo + 7) >> 3) * WW;
+    const int RTa = tile >= 8 ? 8 : 4;
+    const int nadapt = ((r_hi - r_lo) / RTa) * WW;
+    const int nlbp = (tr1 - tr0) * WW;
+    const bool fast_act = A.softmask && A.abs_plane && g.aligned;
+    const int nact = fast_act ? nlbp : 0;
+    const int ntask = nadapt + nblur + nlbp + nact;
+    const float* ap = A.abs_plane ? A.abs_plane + (long long)b * g.H * g.W : nullptr;
+    for (int task = warp; task < ntask; task += nwarps) {
+      if (task < nadapt) {
+        const int rg = task / WW, k = task - rg * WW;
+        if (RTa == 8) task_adaptive<8>(c, cl, r_lo + rg * 8, k, lane);
+        else task_adaptive<4>(c, cl, r_lo + rg * 4, k, lane);
+      } else if (task < nadapt + nblur) {
+        const int q = task - nadapt;
+        const int rg = q / WW, k = q - rg * WW;
+        task_blur<8>(c, b_lo + rg * 8, b_hi, k, lane, hloc);
+      } else if (task < nadapt + nblur + nlbp) {
+        const int q = task - nadapt - nblur;
+        const int tyl = q / WW, k = q - tyl * WW;
+        task_lbp_var(c, tr0 + tyl, k, lane, lutp, phis,
+                     A.lbp_dbg ? A.lbp_dbg + (long long)b * g.ntiles * 10 : nullptr);
+      } else {
+        const int q = task - nadapt - nblur - nlbp;
+        const int tyl = q / WW, k = q - tyl * WW;
+        task_act(c, ap, g.W, fC, rC, tr0 + tyl, k, lane, act_s);
       }
     }
-#pragma unroll
-    for (int j = 0; j < RT; ++j) {
-      int bin = -1;
-      if (valid) {
-        P1[(r0 + j) * Wc + x] = acc[j];
-        for (int pr = 1; pr < ns; ++pr) P1r[pr - 1][(r0 + j) * Wc + x] = acc[j];
-        if (acc[j] >= 0.f && acc[j] <= 1.f) {          // torch.histc(bins=256, min=0, max=1)
-          bin = (int)__fmul_rn(acc[j], 256.f);
-          if (bin == 256) bin = 255;
-        }
-      }
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);     // smooth images: many equal bins
-      if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hloc[bin], __popc(peers));
-    }
+    if (A.softmask && A.abs_plane && !g.aligned)
+      softmask_act_generic(ap, g.C, g.H, g.W, g.ht, g.wt, tr0, tr1, act_s);
   }
   __syncthreads();
   for (int pr = 0; pr < ns; ++pr) {                               // integer counts: order-free, exact
@@ -438,196 +686,98 @@ morph_fused_kernel(const FusedArgs A) {
     for (int i = tid; i < 256; i += NT)
       if (hloc[i]) atomicAdd(&hp[i], hloc[i]);
   }
-  csync();           // blurred bands and the whole-image histogram are complete everywhere
+  STAGE_CLOCK(3);
+
+  // ---- T2: gradient magnitude + direction for rows [r_lo-1, r_hi+1) ------------------------------
+  {
+    const int m_lo = max(r_lo - 1, 0), m_hi = min(r_hi + 1, Hc);
+    const int nmag = ((m_hi - m_lo + 7) >> 3) * WW;
+    for (int task = warp; task < nmag; task += nwarps) {
+      const int rg = task / WW, k = task - rg * WW;
+      task_mag<8>(c, m_lo + rg * 8, m_hi, k, lane);
+    }
+  }
+  if (ns > 1) cl.sync(); else __syncthreads();       // MAG / DIR complete, whole-image histogram complete
+  STAGE_CLOCK(4);
+
+  // ---- T3: Otsu (redundantly per warp), NMS + double threshold -----------------------------------
+  float thr255;
+  int otsu_bin;
+  otsu_warp(hist, lane, thr255, otsu_bin);
+  {
+    const float thr_lo = __fmul_rn(0.5f, thr255);
+    const int RTn = tile >= 8 ? 8 : 4;
+    const int nnms = ((r_hi - r_lo) / RTn) * WW;
+    for (int task = warp; task < nnms; task += nwarps) {
+      const int rg = task / WW, k = task - rg * WW;
+      if (RTn == 8) task_nms<8>(c, cl, r_lo + rg * 8, k, lane, thr255, thr_lo);
+      else task_nms<4>(c, cl, r_lo + rg * 4, k, lane, thr255, thr_lo);
+    }
+  }
+  if (ns > 1) cl.sync(); else __syncthreads();       // strong / weak / adaptive planes complete everywhere
   STAGE_CLOCK(5);
 
-  // ---- S7 (warp 0): Otsu threshold (morphology.py:397-418)  ||  S8 (other warps): magnitude ---
-  if (warp == 0) {
-    int cnt[8];
-    int tot_i = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { cnt[j] = hist[lane * 8 + j]; tot_i += cnt[j]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot_i += __shfl_xor_sync(0xffffffffu, tot_i, o);
-    const float tot = fmaxf((float)tot_i, 1.0f);
-    float p[8], pc[8];
-    double so = 0.0, sm = 0.0;                      // fp64 sums of these fp32 terms are exact
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      p[j] = __fdiv_rn((float)cnt[j], tot);
-      const float center = (float)(2 * (lane * 8 + j) + 1) * 0.001953125f;   // (i + 0.5) / 256, exact
-      pc[j] = __fmul_rn(p[j], center);
-      so += (double)p[j];
-      sm += (double)pc[j];
-    }
-    double io = so, im = sm;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double to = __shfl_up_sync(0xffffffffu, io, o);
-      const double tm = __shfl_up_sync(0xffffffffu, im, o);
-      if (lane >= o) { io += to; im += tm; }
-    }
-    const float mu_t = (float)__shfl_sync(0xffffffffu, im, 31);
-    double ro = io - so, rm = im - sm;
-    float best = -INFINITY;
-    int best_i = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ro += (double)p[j];
-      rm += (double)pc[j];
-      const float omega = (float)ro, mu = (float)rm;
-      float num = __fsub_rn(__fmul_rn(mu_t, omega), mu);
-      num = __fmul_rn(num, num);
-      const float dn = __fadd_rn(__fmul_rn(omega, __fsub_rn(1.0f, omega)), 1e-12f);
-      const float sig = __fdiv_rn(num, dn);
-      if (sig > best) { best = sig; best_i = lane * 8 + j; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
-    }
-    if (lane == 0) {
-      const float thr = (float)(2 * best_i + 1) * 0.001953125f;
-      red[0] = __fmul_rn(thr, 255.f);
-      red[1] = __int_as_float(best_i);
-    }
-  } else {
-    // ---- S8: L1 gradient magnitude of Sobel(255 * blur) -> P0 (morphology.py:496-497) and the
-    //      NMS direction bin (2 bits per pixel, parked in the not-yet-used STRONG/WEAK planes)
-    for (int slot = warp - 1; slot < nslot_b; slot += nwarps - 1) {
-      const int r = r_lo + slot / WW, k = slot % WW;
-      const int x = 32 * k + lane;
-      int bin = 0;
-      if (x < Wc) {
-        float gx, gy;
-        sobel_at<true>(P1, r, x, Hc, Wc, gx, gy);
-        const float mg = __fadd_rn(fabsf(gx), fabsf(gy));
-        P0[r * Wc + x] = mg;
-        for (int pr = 1; pr < ns; ++pr) P0r[pr - 1][r * Wc + x] = mg;
-        bin = nms_bin(gx, gy);
-      }
-      const uint32_t d0 = __ballot_sync(0xffffffffu, bin & 1);
-      const uint32_t d1 = __ballot_sync(0xffffffffu, bin & 2);
-      if (lane == 0) { STRONG[r * WW + k] = d0; WEAK[r * WW + k] = d1; }
-    }
+  // ---- T4: hysteresis ------------------------------------------------------------------------------
+  {
+    const int nblk = (r_hi - r_lo + 15) >> 4;
+    for (int task = warp; task < nblk; task += nwarps) task_hysteresis(c, r_lo - 8 + 16 * task, lane);
   }
-  csync();           // magnitude bands have landed everywhere
+  for (int i = t_lo * 9 + tid; i < t_hi * 9; i += NT) acc[i] = 0;
+  __syncthreads();
   STAGE_CLOCK(6);
-  const float thr255 = red[0];
-  const int otsu_bin = __float_as_int(red[1]);
-  const float thr_lo = __fmul_rn(0.5f, thr255);
 
-  // ---- S9: non-maximum suppression + double threshold (morphology.py:426-449, 500-502) ----
-  for (int bslot = warp; bslot < nslot_b; bslot += nwarps) {
-    const int r = r_lo + bslot / WW, k = bslot % WW;
-    const int slot = r * WW + k;
-    const int x = 32 * k + lane;
-    const uint32_t d0 = STRONG[slot], d1 = WEAK[slot];     // direction bits of this slot (same warp rewrites it)
-    bool st = false, wk = false;
-    if (x < Wc) {
-      const float mag = P0[r * Wc + x];
-      if (mag > thr_lo) {                           // below the weak threshold the pixel is irrelevant
-        const int bin = ((d0 >> lane) & 1) | (((d1 >> lane) & 1) << 1);
-        const int dy1 = bin == 0 ? 0 : -1;
-        const int dx1 = bin == 0 ? 1 : (bin == 1 ? 1 : (bin == 2 ? 0 : -1));
-        const float n1 = P0[clampi(r + dy1, 0, Hc - 1) * Wc + clampi(x + dx1, 0, Wc - 1)];
-        const float n2 = P0[clampi(r - dy1, 0, Hc - 1) * Wc + clampi(x - dx1, 0, Wc - 1)];
-        const float nms = (mag >= n1 && mag >= n2) ? mag : 0.f;
-        st = nms > thr255;
-        wk = nms > thr_lo;
-      }
-    }
-    __syncwarp();
-    const uint32_t ws = __ballot_sync(0xffffffffu, st);
-    const uint32_t ww = __ballot_sync(0xffffffffu, wk);
-    if (lane == 0) { STRONG[slot] = ws; WEAK[slot] = ww; }
-  }
-  __syncthreads();
-  if (ns > 1) {
-    publish(STRONG, r_lo * WW, (r_hi - r_lo) * WW);
-    publish(WEAK, r_lo * WW, (r_hi - r_lo) * WW);
-    cl.sync();       // full strong / weak planes everywhere; hysteresis then runs redundantly per CTA
-  }
-  STAGE_CLOCK(7);
-
-  // ---- S10: hysteresis = 8 constrained 3x3 dilations (morphology.py:504-509) ---------------
-  uint32_t* EA = STRONG;
-  uint32_t* EB = reinterpret_cast<uint32_t*>(P1);               // P1 is dead from here on
-  for (int it = 0; it < 8; ++it) {
-    for (int i = tid; i < NW; i += NT) {
-      const int r = i / WW, k = i - r * WW;
-      uint32_t d = 0;
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const uint32_t c = bp_get(EA, r + dy, k, Hc, WW);
-        const uint32_t l = bp_get(EA, r + dy, k - 1, Hc, WW);
-        const uint32_t rr = bp_get(EA, r + dy, k + 1, Hc, WW);
-        d |= c | (c << 1) | (l >> 31) | (c >> 1) | (rr << 31);
-      }
-      EB[i] = EA[i] | (WEAK[i] & d);
-    }
-    __syncthreads();
-    uint32_t* t = EA; EA = EB; EB = t;
-  }
-  const uint32_t* EDGE = EA;                                      // == STRONG after 8 swaps
-  STAGE_CLOCK(8);
-
-  // ---- S11: integer tile counts ------------------------------------------------------------
-  // acc[t][0..8] = edge, area, perim, euler_x4, N_2, N_4, N_8, N_16, N_32   (aliases P0)
-  int* acc = reinterpret_cast<int*>(P0);
-  for (int i = tid; i < g.ntiles * 9; i += NT) acc[i] = 0;
-  __syncthreads();
+  // ---- T5: integer tile counts -------------------------------------------------------------------
+  // acc[t][0..8] = edge, area, perim, euler_x4, N_2, N_4, N_8, N_16, N_32
   const int segs = 32 >> tshift;
   const uint32_t segmask = tile == 32 ? 0xffffffffu : ((1u << tile) - 1u);
   for (int i = r_lo * WW + tid; i < r_hi * WW; i += NT) {
-    const int r = i / WW, k = i - r * WW;
-    const int nbits = min(32, Wc - 32 * k);
-    const uint32_t vmask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
-    const uint32_t e = EDGE[i];
-    const uint32_t m = BIN[i];
-    uint32_t er = 0xffffffffu;                                    // 3x3 erosion, outside ignored
+    {
+      const int r = i / WW, k = i - r * WW;
+      const int nbits = min(32, Wc - 32 * k);
+      const uint32_t vmask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+      const uint32_t e = EDGE[i];
+      const uint32_t m = BIN[i];
+      uint32_t er = 0xffffffffu;                                    // 3x3 erosion, outside ignored
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int rr = r + dy;
-      if (rr < 0 || rr >= Hc) continue;
-      const uint32_t c = BIN[rr * WW + k];
-      const uint32_t l = k > 0 ? BIN[rr * WW + k - 1] : 0xffffffffu;
-      const uint32_t rn = k + 1 < WW ? BIN[rr * WW + k + 1] : 0xffffffffu;
-      const uint32_t left = (c << 1) | (l >> 31);
-      uint32_t right = (c >> 1) | (rn << 31);
-      if (nbits < 32) right |= (1u << (nbits - 1));
-      er &= c & left & right;
-    }
-    const uint32_t bnd = m & ~er & vmask;
-    // Euler quads (morphology.py:694-702): a=(i-1,j-1) b=(i-1,j) c=(i,j-1) d=(i,j), zero padded
-    const uint32_t U = r > 0 ? BIN[(r - 1) * WW + k] : 0u;
-    const uint32_t Up = (r > 0 && k > 0) ? BIN[(r - 1) * WW + k - 1] : 0u;
-    const uint32_t Cp = k > 0 ? BIN[r * WW + k - 1] : 0u;
-    const uint32_t qa = (U << 1) | (Up >> 31), qb = U, qc = (m << 1) | (Cp >> 31), qd = m;
-    const uint32_t x1 = qa ^ qb, c1 = qa & qb, x2 = qc ^ qd, c2 = qc & qd;
-    const uint32_t odd = x1 ^ x2, anyc = c1 | c2;
-    const uint32_t Q1 = odd & ~anyc & vmask, Q3 = odd & anyc & vmask;
-    const uint32_t QD = ((qb & qc & ~qa & ~qd) | (qa & qd & ~qb & ~qc)) & vmask;
-    const int ty = r >> tshift;
-    for (int s = 0; s < segs; ++s) {
-      const int x0 = 32 * k + s * tile;
-      if (x0 >= Wc) break;
-      const int t = ty * wt + (x0 >> tshift);
-      const int sh = s * tile;
-      const int ne = __popc((e >> sh) & segmask);
-      const int na = __popc((m >> sh) & segmask);
-      const int np = __popc((bnd >> sh) & segmask);
-      const int e4 = __popc((Q1 >> sh) & segmask) - __popc((Q3 >> sh) & segmask) -
-                     2 * __popc((QD >> sh) & segmask);
-      if (ne) atomicAdd(&acc[t * 9 + 0], ne);
-      if (na) atomicAdd(&acc[t * 9 + 1], na);
-      if (np) atomicAdd(&acc[t * 9 + 2], np);
-      if (e4) atomicAdd(&acc[t * 9 + 3], e4);
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int rr = r + dy;
+        if (rr < 0 || rr >= Hc) continue;
+        const uint32_t cc = BIN[rr * WW + k];
+        const uint32_t l = k > 0 ? BIN[rr * WW + k - 1] : 0xffffffffu;
+        const uint32_t rn = k + 1 < WW ? BIN[rr * WW + k + 1] : 0xffffffffu;
+        const uint32_t left = (cc << 1) | (l >> 31);
+        uint32_t right = (cc >> 1) | (rn << 31);
+        if (nbits < 32) right |= (1u << (nbits - 1));
+        er &= cc & left & right;
+      }
+      const uint32_t bnd = m & ~er & vmask;
+      // Euler quads (morphology.py:694-702): a=(i-1,j-1) b=(i-1,j) c=(i,j-1) d=(i,j), zero padded
+      const uint32_t U = r > 0 ? BIN[(r - 1) * WW + k] : 0u;
+      const uint32_t Up = (r > 0 && k > 0) ? BIN[(r - 1) * WW + k - 1] : 0u;
+      const uint32_t Cp = k > 0 ? BIN[r * WW + k - 1] : 0u;
+      const uint32_t qa = (U << 1) | (Up >> 31), qb = U, qc = (m << 1) | (Cp >> 31), qd = m;
+      const uint32_t x1 = qa ^ qb, c1 = qa & qb, x2 = qc ^ qd, c2 = qc & qd;
+      const uint32_t odd = x1 ^ x2, anyc = c1 | c2;
+      const uint32_t Q1 = odd & ~anyc & vmask, Q3 = odd & anyc & vmask;
+      const uint32_t QD = ((qb & qc & ~qa & ~qd) | (qa & qd & ~qb & ~qc)) & vmask;
+      const int ty = r >> tshift;
+      for (int s = 0; s < segs; ++s) {
+        const int x0 = 32 * k + s * tile;
+        if (x0 >= Wc) break;
+        const int t = ty * wt + (x0 >> tshift);
+        const int sh = s * tile;
+        const int ne = __popc((e >> sh) & segmask);
+        const int na = __popc((m >> sh) & segmask);
+        const int np = __popc((bnd >> sh) & segmask);
+        const int e4 = __popc((Q1 >> sh) & segmask) - __popc((Q3 >> sh) & segmask) -
+                       2 * __popc((QD >> sh) & segmask);
+        if (ne) atomicAdd(&acc[t * 9 + 0], ne);
+        if (na) atomicAdd(&acc[t * 9 + 1], na);
+        if (np) atomicAdd(&acc[t * 9 + 2], np);
+        if (e4) atomicAdd(&acc[t * 9 + 3], e4);
+      }
     }
   }
-  STAGE_CLOCK(9);
   // dyadic box counts (morphology.py:595-601): one thread per (tile, scale)
   for (int ts = t_lo * g.S + tid; ts < t_hi * g.S; ts += NT) {
     const int t = ts / g.S, sidx = ts - t * g.S;
@@ -646,31 +796,31 @@ morph_fused_kernel(const FusedArgs A) {
     acc[t * 9 + 4 + sidx] = n;
   }
   __syncthreads();
-  STAGE_CLOCK(10);
+  STAGE_CLOCK(7);
 
-  // ---- S12: phi1, phi4, phi5, interactions (morphology.py:852-864) --------------------------
+  // ---- phi1, phi4, phi5, interactions (morphology.py:852-864) --------------------------------------
   for (int t = t_lo + tid; t < t_hi; t += NT) {
     const int* a = acc + t * 9;
-    const int S = g.S;
+    const int Sn = g.S;
     float y[5];
-    for (int i = 0; i < S; ++i) y[i] = lutn[a[4 + i]];                         // log(N_s + 1)
+    for (int i = 0; i < Sn; ++i) y[i] = lutn[a[4 + i]];                         // log(N_s + 1)
     float w_sum = 0.f, sx = 0.f, sy = 0.f;
-    for (int i = 0; i < S; ++i) {
+    for (int i = 0; i < Sn; ++i) {
       w_sum = __fadd_rn(w_sum, kc::FW[i]);
       sx = __fadd_rn(sx, __fmul_rn(kc::FW[i], kc::FLOG[i]));
       sy = __fadd_rn(sy, __fmul_rn(kc::FW[i], y[i]));
     }
     const float x_mean = __fdiv_rn(sx, w_sum), y_mean = __fdiv_rn(sy, w_sum);
     float cov = 0.f, var = 0.f;
-    for (int i = 0; i < S; ++i) {
+    for (int i = 0; i < Sn; ++i) {
       const float dx = __fsub_rn(kc::FLOG[i], x_mean);
       cov = __fadd_rn(cov, __fmul_rn(__fmul_rn(kc::FW[i], dx), __fsub_rn(y[i], y_mean)));
       var = __fadd_rn(var, __fmul_rn(kc::FW[i], __fmul_rn(dx, dx)));
     }
     float df = -__fdiv_rn(cov, __fadd_rn(var, 1e-12f));
     df = fminf(fmaxf(df, 1.0f), 2.0f);
-    const float p1 = S < 2 ? 0.5f : __fdiv_rn(df, 2.0f);
-    const float p2 = phis[t * 5 + 1], p3 = phis[t * 5 + 2];
+    const float p1 = Sn < 2 ? 0.5f : __fdiv_rn(df, 2.0f);
+    const float p2 = phis[t * 2 + 0], p3 = phis[t * 2 + 1];
     const float p4 = __fdiv_rn((float)a[0], ntile2);
     const float area = (float)a[1], perim = (float)a[2];
     float ic = __fdiv_rn(__fmul_rn(perim, perim), __fadd_rn(__fmul_rn(kc::FOUR_PI, area), 1e-6f));
@@ -683,86 +833,86 @@ morph_fused_kernel(const FusedArgs A) {
     o[5] = __fmul_rn(p1, p2);
     o[6] = __fmul_rn(p3, p3);
     o[7] = __fsqrt_rn(__fadd_rn(__fmul_rn(p4, p5), 1e-12f));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) phi8[t * 8 + i] = o[i];
+    float4* ds = reinterpret_cast<float4*>(phi8 + t * 8);
+    ds[0] = make_float4(o[0], o[1], o[2], o[3]);
+    ds[1] = make_float4(o[4], o[5], o[6], o[7]);
     if (A.phi) {
       float4* dst = reinterpret_cast<float4*>(A.phi + ((long long)b * g.ntiles + t) * 8);
       dst[0] = make_float4(o[0], o[1], o[2], o[3]);
       dst[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
     if (A.counts_dbg) {
-      int* c = A.counts_dbg + ((long long)b * g.ntiles + t) * 12;
-      for (int i = 0; i < 9; ++i) c[i] = a[i];
-      c[9] = otsu_bin; c[10] = 0; c[11] = 0;
+      int* cd = A.counts_dbg + ((long long)b * g.ntiles + t) * 12;
+      for (int i = 0; i < 9; ++i) cd[i] = a[i];
+      cd[9] = otsu_bin; cd[10] = 0; cd[11] = 0;
     }
   }
-  if (A.edge_dbg && rank == 0)
-    for (int i = tid; i < NW; i += NT) A.edge_dbg[(long long)b * NW + i] = EDGE[i];
-  if (A.bin_dbg && rank == 0)
-    for (int i = tid; i < NW; i += NT) A.bin_dbg[(long long)b * NW + i] = BIN[i];
+  if (A.edge_dbg)
+    for (int i = r_lo * WW + tid; i < r_hi * WW; i += NT) A.edge_dbg[(long long)b * NW + i] = EDGE[i];
+  if (A.bin_dbg)
+    for (int i = r_lo * WW + tid; i < r_hi * WW; i += NT) A.bin_dbg[(long long)b * NW + i] = BIN[i];
+  if (!A.cmlp) return;                       // last remote access was before the strong / weak sync
+  cp_async_wait_all();
   __syncthreads();
-  STAGE_CLOCK(11);
-  if (!A.cmlp) return;                       // last remote access was before the strong/weak sync
+  STAGE_CLOCK(8);
 
-  // ---- N1: complexity MLP (own tiles) -> all-gather -> bilateral (own tiles) -> all-gather ----
-  float* scratch = P0;                       // the planes are dead from here on
+  // all-gather of a per-tile array: own tiles -> every peer
+  auto publish = [&](float* base) {
+    const int n = t_hi - t_lo;
+    for (int i = tid; i < n * (ns - 1); i += NT) {
+      const int pr = 1 + i / n, o = t_lo + (i - (pr - 1) * n);
+      cl.map_shared_rank(base, (rank + pr) % ns)[o] = base[o];
+    }
+  };
+
+  // ---- N1: complexity MLP (own tiles) -> all-gather -> bilateral (own tiles) -------------------------
+  float* scratch = S;                        // the float planes are dead from here on
   const int nt = g.ntiles;
-  {
-    float* w = scratch;
-    float* act = w + CMLP_SMEM_FLOATS;
-    complexity_load_weights(A.cmlp, w);
-    __syncthreads();
-    complexity_mlp_range(phi8, t_lo, t_hi, w, act, craw_s,
-                         A.complexity_raw ? A.complexity_raw + (long long)b * nt : nullptr);
-    if (ns > 1) { publish(craw_s, t_lo, t_hi - t_lo); cl.sync(); }
-    bilateral_range(craw_s, g.ht, g.wt, t_lo, t_hi, act, cfin, A.complexity ? A.complexity + (long long)b * nt : nullptr);
-    if (ns > 1) { publish(cfin, t_lo, t_hi - t_lo); cl.sync(); }
-  }
-  STAGE_CLOCK(12);
+  complexity_mlp_warps(phi8, t_lo, t_hi, w_cmlp, scratch, craw_s,
+                       A.complexity_raw ? A.complexity_raw + (long long)b * nt : nullptr);
+  if (ns > 1) { __syncthreads(); publish(craw_s); cl.sync(); } else __syncthreads();
+  STAGE_CLOCK(9);
+  bilateral_range(craw_s, g.ht, g.wt, t_lo, t_hi, scratch, cfin, A.complexity ? A.complexity + (long long)b * nt : nullptr);
+  STAGE_CLOCK(10);
   if (!A.run_mapper) return;
-  // ---- N2: bit mapper (own tiles) --------------------------------------------------------------
+  // ---- N2: bit mapper (own tiles) --------------------------------------------------------------------
   float* bout = A.bit_map ? A.bit_map + (long long)b * nt : nullptr;
   if (A.linear_mapper) {
-    int npow2 = 1;
-    while (npow2 < nt) npow2 <<= 1;
-    mapper_linear_range(cfin, nt, npow2, scratch, t_lo, t_hi, A.temperature, A.use_t, A.continuous, A.lo, A.hi,
-                        A.eps_spread, bits_s, bout);
+    if (ns > 1) { publish(cfin); cl.sync(); }
+    mapper_linear_range(cfin, nt, red, t_lo, t_hi, A.temperature, A.use_t, A.continuous, A.lo, A.hi, A.eps_spread,
+                        bits_s, bout);
   } else {
-    float* w = scratch;
-    float* act = w + MAPPER_SMEM_FLOATS;
-    mapper_load_weights(A.mapper, w);
+    mapper_mlp_warps(cfin, t_lo, t_hi, w_map, scratch, A.temperature, A.use_t, A.continuous, A.lo, A.hi, bits_s, bout);
     __syncthreads();
-    mapper_mlp_range(cfin, t_lo, t_hi, w, act, A.temperature, A.use_t, A.continuous, A.lo, A.hi, bits_s, bout);
   }
-  STAGE_CLOCK(13);
+  STAGE_CLOCK(11);
   if (!A.softmask || !A.abs_plane) {
     if (ns > 1) cl.sync();                   // nobody leaves while a peer may still write into it
     return;
   }
-  // ---- N3: soft mask (quantization.py:213-239): tile head (own tiles) + m rows (own band) ------
+  // ---- N3: soft mask (quantization.py:213-239): tile head (own tiles) + m rows (own band) -----------
   {
-    float* rows = scratch;                   // [H*wt]
-    float* P = rows + g.H * g.wt;            // 196
-    float* bn = P + 196;                     // [nt]
+    if (ns > 1) { publish(bits_s); publish(act_s); cl.sync(); }
+    float amax = -INFINITY;                                    // every warp: max over all tiles
+    for (int t = lane; t < nt; t += 32) amax = fmaxf(amax, act_s[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    float* bn = scratch;                     // [nt]
     float* an = bn + nt;                     // [nt]
-    float amax = softmask_act_range(A.abs_plane + (long long)b * g.H * g.W, g.C, g.H, g.W, g.ht, g.wt, tr0, tr1,
-                                    rows, red, act_s);
-    if (ns > 1) {
-      if (tid == 0)
-        for (int pr = 0; pr < ns; ++pr) cl.map_shared_rank(mmx, pr)[8 + rank] = amax;
-      publish(bits_s, t_lo, t_hi - t_lo);
-      publish(act_s, t_lo, t_hi - t_lo);
-      cl.sync();
-      amax = mmx[8];
-      for (int pr = 1; pr < ns; ++pr) amax = fmaxf(amax, mmx[8 + pr]);
-    }
-    softmask_head_range(bits_s, act_s, amax, g.ht, g.wt, t_lo, t_hi, A.softmask, P, bn, an, mt_s,
+    float* cls = an + nt;                    // [own tiles][25]
+    softmask_head_range(bits_s, act_s, amax, g.ht, g.wt, t_lo, t_hi, w_sm, bn, an, mt_s,
                         A.mask_tiles ? A.mask_tiles + (long long)b * nt : nullptr);
-    if (ns > 1) { publish(mt_s, t_lo, t_hi - t_lo); cl.sync(); }
-    softmask_plane_rows(mt_s, P, g.H, g.W, g.ht, g.wt, (g.H * rank) / ns, (g.H * (rank + 1)) / ns,
-                        A.mask + (long long)b * g.H * g.W);
+    if (ns > 1) { publish(mt_s); cl.sync(); }
+    float* mo = A.mask + (long long)b * g.H * g.W;
+    if (g.aligned) {
+      softmask_class_table(mt_s, w_sm, g.ht, g.wt, t_lo, t_hi, cls);
+      __syncthreads();
+      softmask_plane_from_classes(cls, g.W, g.wt, tile, tshift, t_lo, r_lo, r_hi, mo);
+    } else {
+      softmask_plane_rows(mt_s, w_sm, g.H, g.W, g.ht, g.wt, (g.H * rank) / ns, (g.H * (rank + 1)) / ns, mo);
+    }
   }
-  STAGE_CLOCK(14);
+  STAGE_CLOCK(12);
 }
 
 }  // namespace mcaq
@@ -778,59 +928,82 @@ static int g_force_split = 0;
 // debug / tuning: force the number of CTAs per image (0 = automatic)
 extern "C" void mcaq_debug_cluster_split(int ns) { g_force_split = ns; }
 
-// CTAs per image: tile rows are split over a thread-block cluster (portable size <= 8)
-static int pick_split(int ht) {
-  int ns = ht >= 4 ? 4 : (ht >= 2 ? 2 : 1);
-  if (g_force_split == 1 || g_force_split == 2 || g_force_split == 4) ns = g_force_split;
+static int g_sm_count = 0;
+
+// CTAs per image: tile rows are split over a thread-block cluster (portable size <= 8) so that the
+// launch fills the GPU (two CTAs fit an SM) without shrinking a band below one 8-row run
+static int pick_split(int B, int ht, int tile) {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
+      g_sm_count = 148;
+  }
+  int ns = 1;
+  if (g_force_split == 1 || g_force_split == 2 || g_force_split == 4 || g_force_split == 8) {
+    ns = g_force_split;
+  } else {
+    while (ns < 8 && B * ns * 2 <= 2 * g_sm_count && (ht / (ns * 2)) * tile >= 8) ns *= 2;
+  }
   while (ns > ht) ns >>= 1;
   return ns < 1 ? 1 : ns;
 }
 
+// shared-memory layout for a given split; returns bytes of dynamic smem
+static long long layout(MorphGeom& g) {
+  g.band_max = ((g.ht + g.ns - 1) / g.ns) * g.tile;
+  g.max_own = ((g.ht + g.ns - 1) / g.ns) * g.wt;
+  // float planes; a partial 8-row run of a stencil task reads at most 7 rows past its plane (results
+  // discarded), which stays inside the following planes / the margin after MAG
+  const long long wG = (long long)(g.band_max + 10) * g.gs;
+  const long long wBL = (long long)(g.band_max + 4) * g.bs;
+  const long long wMAG = (long long)(g.band_max + 2) * g.Wc + 8LL * g.gs;
+  // the same region later holds the per-warp net scratch, bilateral weights, mask classes
+  const long long nets = max_i((MORPH_MAX_THREADS / 32) * NET_WARP_SCRATCH, 2 * g.ntiles + 25 * g.max_own);
+  g.off_bl = (int)((wG + 3) & ~3LL);
+  g.off_mag = (int)((g.off_bl + wBL + 3) & ~3LL);
+  long long bits0 = (g.off_mag + wMAG + 3) & ~3LL;
+  if (bits0 < ((nets + 3) & ~3LL)) bits0 = (nets + 3) & ~3LL;
+  g.off_bits = (int)bits0;
+  const long long tiles0 = (bits0 + 6LL * g.Hc * g.WW + 3) & ~3LL;
+  g.off_tiles = (int)tiles0;
+  const long long tw = (long long)g.ntiles * (2 + 8 + 5 + 9) + 512 + 64 + 16 + 260 + g.tile * g.tile + 4;
+  const long long w0 = (tiles0 + tw + 3) & ~3LL;
+  g.off_w = (int)w0;
+  g.words = (int)(w0 + CMLP_SMEM_FLOATS + MAPPER_SMEM_FLOATS + SOFTMASK_SMEM_FLOATS);
+  return (long long)g.words * 4;
+}
 
-// geometry + shared-memory layout; returns bytes of dynamic smem or a negative error
-static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size, bool nets, int threads) {
+// geometry + split + shared-memory layout; returns bytes of dynamic smem or a negative error
+static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size) {
   g.B = B; g.C = C; g.H = H; g.W = W;
   g.tile = mcaq_tile_size(H, grid_size);
   g.ht = H / g.tile; g.wt = W / g.tile;
   if (g.ht <= 0 || g.wt <= 0 || g.tile > 32 || g.tile < 4) return MCAQ_EINVAL;
   g.Hc = g.ht * g.tile; g.Wc = g.wt * g.tile;
   g.WW = (g.Wc + 31) / 32;
+  if (g.WW > 5) return MCAQ_ETOOBIG;          // hysteresis keeps a row of <= 5 words in registers
   g.ntiles = g.ht * g.wt;
   g.S = 0;
   for (int s = 2; s <= g.tile; s <<= 1) g.S++;
-  g.ns = pick_split(g.ht);
-  const long long NP = (long long)g.Hc * g.Wc, NW = (long long)g.Hc * g.WW;
-  const long long rowsum_w = (long long)g.Hc * g.wt * 4, lbp_w = (long long)g.ntiles * 10;
-  long long np1 = NP < rowsum_w ? rowsum_w : NP;
-  np1 = (np1 + 3) & ~3LL;
-  g.off_rowsum = (int)NP;                       // NP % 16 == 0
-  long long tail = NP + np1;
-  if (rowsum_w + lbp_w <= np1) {
-    g.off_lbp = (int)(NP + rowsum_w);
-  } else {
-    g.off_lbp = (int)tail;
-    tail += (lbp_w + 3) & ~3LL;
+  g.aligned = (H == g.Hc && W == g.Wc) ? 1 : 0;
+  g.gs = g.Wc + 4;
+  g.bs = g.Wc + 2;
+  g.ns = pick_split(B, g.ht, g.tile);
+  long long bytes = layout(g);
+  // planes too large for two CTAs per SM (or for one at all): split the image further
+  while (bytes > 112 * 1024 && g.ns * 2 <= 8 && g.ns * 2 <= g.ht && !g_force_split) {
+    g.ns *= 2;
+    bytes = layout(g);
   }
-  if (nets) {
-    (void)threads;
-    int npow2 = 1;
-    while (npow2 < g.ntiles) npow2 <<= 1;
-    long long need = CMLP_SMEM_FLOATS + max_i(CPX_ACT_FLOATS, 25 * g.ntiles);
-    need = max_i((int)need, MAPPER_SMEM_FLOATS + MAP_ACT_FLOATS);
-    need = max_i((int)need, npow2);
-    need = max_i((int)need, H * g.wt + 196 + 2 * g.ntiles);
-    if (tail < need) tail = (need + 3) & ~3LL;
-  }
-  g.off_tail = (int)tail;
-  const long long words = tail + 3 * NW + (long long)g.ntiles * (5 + 8 + 5) + 512 + 64 + 16 + 260 +
-                          g.tile * g.tile + 4;
-  return words * 4;
+  if (bytes > 227 * 1024) return MCAQ_ETOOBIG;
+  return bytes;
 }
 
 // threads per CTA from the pixels of the largest band
 static int pick_threads(const MorphGeom& g) {
-  const long long band = (long long)((g.ht + g.ns - 1) / g.ns) * g.tile * g.Wc;
-  return band <= 640 ? 128 : (band <= 4096 ? 256 : MORPH_THREADS);
+  const long long band = (long long)g.band_max * g.Wc;
+  return band <= 512 ? 128 : MORPH_MAX_THREADS;
 }
 
 static int launch_fused(FusedArgs& A, long long smem, int threads, cudaStream_t st) {
@@ -865,7 +1038,7 @@ extern "C" int mcaq_morph_phi(const float* sum_plane, int B, int C, int H, int W
   (void)consts;   // compiled in (mcaq_consts.cuh); argument kept for ABI stability
   if (!sum_plane || !phi || B <= 0 || C <= 0 || H <= 0 || W <= 0 || grid_size <= 0) return MCAQ_EINVAL;
   FusedArgs A = {};
-  const long long smem = plan(A.g, B, C, H, W, grid_size, false, 0);
+  const long long smem = plan(A.g, B, C, H, W, grid_size);
   if (smem < 0) return (int)smem;
   const int threads = pick_threads(A.g);
   A.sum_plane = sum_plane;
@@ -886,8 +1059,9 @@ extern "C" int mcaq_morph_fused(const float* sum_plane, const float* abs_plane, 
   if (!mapper && !linear_mapper) return MCAQ_EINVAL;
   if (softmask && (!abs_plane || !mask)) return MCAQ_EINVAL;
   if (keys && !packed_ranges) return MCAQ_EINVAL;
+  if (((uintptr_t)cmlp | (uintptr_t)mapper | (uintptr_t)softmask | (uintptr_t)mask) & 15) return MCAQ_EALIGN;
   FusedArgs A = {};
-  const long long smem = plan(A.g, B, C, H, W, grid_size, true, 0);
+  const long long smem = plan(A.g, B, C, H, W, grid_size);
   if (smem < 0) return (int)smem;
   const int threads = pick_threads(A.g);
   A.sum_plane = sum_plane; A.abs_plane = abs_plane;

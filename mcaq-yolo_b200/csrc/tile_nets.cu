@@ -10,62 +10,71 @@ constexpr int TN_WARPS = TN_THREADS / 32;
 __global__ void __launch_bounds__(TN_THREADS)
 complexity_kernel(const float* __restrict__ phi, int ht, int wt, const float* __restrict__ cmlp,
                   float* __restrict__ raw_out, float* __restrict__ out) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int ntiles = ht * wt;
-  float* w = sm;
-  float* act = w + CMLP_SMEM_FLOATS;
-  float* craw = sm + cpx_scratch_floats(ntiles);
+  float* w = sm;                                        // CMLP_SMEM_FLOATS
+  float* scratch = w + CMLP_SMEM_FLOATS;                // max(TN_WARPS * NET_WARP_SCRATCH, 25 * ntiles)
+  const int nscr = TN_WARPS * NET_WARP_SCRATCH > 25 * ntiles ? TN_WARPS * NET_WARP_SCRATCH : 25 * ntiles;
+  float* craw = scratch + ((nscr + 3) & ~3);
   float* cfin = craw + ntiles;
   const int b = blockIdx.x;
-  complexity_load_weights(cmlp, w);
+  copy_params(cmlp, w, CMLP_SMEM_FLOATS);
   __syncthreads();
-  complexity_mlp_range(phi + (long long)b * ntiles * 8, 0, ntiles, w, act, craw,
+  complexity_mlp_warps(phi + (long long)b * ntiles * 8, 0, ntiles, w, scratch, craw,
                        raw_out ? raw_out + (long long)b * ntiles : nullptr);
-  bilateral_range(craw, ht, wt, 0, ntiles, act, cfin, out + (long long)b * ntiles);
+  __syncthreads();
+  bilateral_range(craw, ht, wt, 0, ntiles, scratch, cfin, out + (long long)b * ntiles);
 }
 
 __global__ void __launch_bounds__(TN_THREADS)
 mapper_mlp_kernel(const float* __restrict__ cmap, int ntiles, const float* __restrict__ mp, float temperature,
                   int use_t, int continuous, float lo, float hi, float* __restrict__ out) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* w = sm;
-  float* act = w + MAPPER_SMEM_FLOATS;
-  float* bits_s = act + MAP_ACT_FLOATS;
+  float* scratch = w + MAPPER_SMEM_FLOATS;              // TN_WARPS * NET_WARP_SCRATCH
+  float* bits_s = scratch + TN_WARPS * NET_WARP_SCRATCH;
   const int b = blockIdx.x;
-  mapper_load_weights(mp, w);
+  copy_params(mp, w, MAPPER_SMEM_FLOATS);
   __syncthreads();
-  mapper_mlp_range(cmap + (long long)b * ntiles, 0, ntiles, w, act, temperature, use_t, continuous, lo, hi,
+  mapper_mlp_warps(cmap + (long long)b * ntiles, 0, ntiles, w, scratch, temperature, use_t, continuous, lo, hi,
                    bits_s, out + (long long)b * ntiles);
 }
 
 __global__ void __launch_bounds__(TN_THREADS)
-mapper_linear_kernel(const float* __restrict__ cmap, int ntiles, int npow2, float temperature, int use_t,
+mapper_linear_kernel(const float* __restrict__ cmap, int ntiles, float temperature, int use_t,
                      int continuous, float lo, float hi, float eps_spread, float* __restrict__ out) {
-  extern __shared__ float sm[];
-  float* srt = sm;
-  float* bits_s = srt + npow2;
+  extern __shared__ __align__(16) float sm[];
+  float* cm = sm;                        // [ntiles] staged complexity
+  float* bits_s = cm + ntiles;
+  float* sel = bits_s + ntiles;          // 4
   const int b = blockIdx.x;
-  mapper_linear_range(cmap + (long long)b * ntiles, ntiles, npow2, srt, 0, ntiles, temperature, use_t, continuous,
-                      lo, hi, eps_spread, bits_s, out + (long long)b * ntiles);
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) cm[t] = cmap[(long long)b * ntiles + t];
+  __syncthreads();
+  mapper_linear_range(cm, ntiles, sel, 0, ntiles, temperature, use_t, continuous, lo, hi, eps_spread, bits_s,
+                      out + (long long)b * ntiles);
 }
 
 __global__ void __launch_bounds__(TN_THREADS)
 soft_mask_kernel(const float* __restrict__ bit_map, int Ht, int Wt, const float* __restrict__ abs_plane,
                  int C, int H, int W, const float* __restrict__ prm, float* __restrict__ tiles_out,
                  float* __restrict__ mask) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x, nt = Ht * Wt;
   float* P = sm;                         // 196
-  float* act = P + 196;                  // [nt]
+  float* act = P + SOFTMASK_SMEM_FLOATS; // [nt]
   float* bn = act + nt;
   float* an = bn + nt;
   float* mt = an + nt;
   float* bits = mt + nt;                 // [nt] staged copy of the bit map
-  float* rows = bits + nt;               // [H*Wt]
-  float* red = rows + H * Wt;            // [32]
+  copy_params(prm, P, SOFTMASK_SMEM_FLOATS);
   for (int t = threadIdx.x; t < nt; t += blockDim.x) bits[t] = bit_map[(long long)b * nt + t];
-  const float amax = softmask_act_range(abs_plane + (long long)b * H * W, C, H, W, Ht, Wt, 0, Ht, rows, red, act);
-  softmask_head_range(bits, act, amax, Ht, Wt, 0, nt, prm, P, bn, an, mt,
+  softmask_act_generic(abs_plane + (long long)b * H * W, C, H, W, Ht, Wt, 0, Ht, act);
+  __syncthreads();
+  float amax = -INFINITY;
+  for (int t = threadIdx.x & 31; t < nt; t += 32) amax = fmaxf(amax, act[t]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  softmask_head_range(bits, act, amax, Ht, Wt, 0, nt, P, bn, an, mt,
                       tiles_out ? tiles_out + (long long)b * nt : nullptr);
   softmask_plane_rows(mt, P, H, W, Ht, Wt, 0, H, mask + (long long)b * H * W);
 }
@@ -79,7 +88,9 @@ extern "C" int mcaq_complexity(const float* phi, int B, int ht, int wt, const fl
   (void)consts;   // the stencil constants are compiled in (mcaq_consts.cuh); kept for ABI stability
   if (!phi || !cmlp || !complexity || B <= 0 || ht <= 0 || wt <= 0) return MCAQ_EINVAL;
   const int nt_ = ht * wt;
-  const size_t smem = (size_t)(CMLP_SMEM_FLOATS + (CPX_ACT_FLOATS > 25 * nt_ ? CPX_ACT_FLOATS : 25 * nt_) + 2 * nt_) * 4;
+  const int nscr = TN_WARPS * NET_WARP_SCRATCH > 25 * nt_ ? TN_WARPS * NET_WARP_SCRATCH : 25 * nt_;
+  const size_t smem = (size_t)(CMLP_SMEM_FLOATS + ((nscr + 3) & ~3) + 2 * nt_) * 4;
+  if ((uintptr_t)cmlp & 15) return MCAQ_EALIGN;
   if (smem > 200 * 1024) return MCAQ_ETOOBIG;
   if (smem > 48 * 1024) cudaFuncSetAttribute(complexity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   complexity_kernel<<<B, TN_THREADS, smem, (cudaStream_t)stream>>>(phi, ht, wt, cmlp, complexity_raw, complexity);
@@ -94,19 +105,18 @@ extern "C" int mcaq_bit_mapper(const float* complexity, int B, int ht, int wt, c
   const int ntiles = ht * wt;
   cudaStream_t st = (cudaStream_t)stream;
   if (mapper) {
-    const size_t smem = (size_t)(MAPPER_SMEM_FLOATS + MAP_ACT_FLOATS + ntiles) * 4;
+    const size_t smem = (size_t)(MAPPER_SMEM_FLOATS + TN_WARPS * NET_WARP_SCRATCH + ntiles) * 4;
+    if ((uintptr_t)mapper & 15) return MCAQ_EALIGN;
     if (smem > 200 * 1024) return MCAQ_ETOOBIG;
     if (smem > 48 * 1024) cudaFuncSetAttribute(mapper_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     mapper_mlp_kernel<<<B, TN_THREADS, smem, st>>>(complexity, ntiles, mapper, temperature, use_temperature,
                                                    continuous, min_bits, max_bits, bit_map);
   } else {
-    int npow2 = 1;
-    while (npow2 < ntiles) npow2 <<= 1;
-    const size_t smem = (size_t)(npow2 + ntiles) * 4;
+    const size_t smem = (size_t)(2 * ntiles + 4) * 4;
     if (smem > 200 * 1024) return MCAQ_ETOOBIG;
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(mapper_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mapper_linear_kernel<<<B, TN_THREADS, smem, st>>>(complexity, ntiles, npow2, temperature, use_temperature,
+    mapper_linear_kernel<<<B, TN_THREADS, smem, st>>>(complexity, ntiles, temperature, use_temperature,
                                                       continuous, min_bits, max_bits, eps_spread, bit_map);
   }
   MCAQ_LAUNCH_CHECK();
@@ -117,7 +127,8 @@ extern "C" int mcaq_soft_mask(const float* bit_map, int Ht, int Wt, const float*
                               int W, const float* softmask, float* mask_tiles, float* mask, void* stream) {
   if (!bit_map || !abs_plane || !softmask || !mask || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0)
     return MCAQ_EINVAL;
-  const size_t smem = (size_t)(196 + 5 * Ht * Wt + H * Wt + 32) * 4;
+  const size_t smem = (size_t)(SOFTMASK_SMEM_FLOATS + 5 * Ht * Wt) * 4;
+  if ((uintptr_t)softmask & 15) return MCAQ_EALIGN;
   if (smem > 200 * 1024) return MCAQ_ETOOBIG;
   if (smem > 48 * 1024) cudaFuncSetAttribute(soft_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   soft_mask_kernel<<<B, TN_THREADS, smem, (cudaStream_t)stream>>>(bit_map, Ht, Wt, abs_plane, C, H, W, softmask,

@@ -1,7 +1,13 @@
-// Block-cooperative device functions for the tile-level stages (complexity MLP + bilateral,
-// bit mappers, soft mask).  Used by the standalone kernels in tile_nets.cu and by the fused
-// per-image kernel in morph_fused.cu.  All threads of the CTA must call each function; `sm`
-// arguments are caller-provided shared-memory scratch of the documented size.
+// Device functions for the tile-level stages (complexity MLP + bilateral, bit mappers, soft
+// mask).  Used by the standalone kernels in tile_nets.cu and by the fused per-image kernel in
+// morph_fused.cu.
+//
+// The two MLPs run as warp-private pipelines: a warp carries a group of NET_TT tiles through all
+// layers (lane = output unit, activations in a per-warp shared-memory scratch read back as
+// broadcast LDS.128), so there is no CTA barrier between layers and the NET_TT independent FMA
+// chains hide each other's latency.  Parameter blocks arrive in the layout the host packs
+// (mcaq_yolo_b200/constants.py: weights transposed to [k][unit], BatchNorm folded), so staging
+// them into shared memory is a straight 16-byte copy.
 //
 // Arithmetic = oracle/mcaq_oracle.py: nn.Linear / conv = FMA chain over k from 0, bias last;
 // LayerNorm statistics = 32-lane xor-butterfly tree (element k and k+32 pre-added for D = 64);
@@ -24,77 +30,81 @@ __device__ __forceinline__ float warp_tree_sum(float v) {
   return v;
 }
 
-// out(t, m) = sum_k in[t][k] * Wt[k][m] as an FMA chain over k from 0 (nn.Linear's order), for nb
-// tiles.  A thread owns unit m for TT = 8 consecutive tiles: per 4 k it issues 8 LDS.128 of
-// activations (warp-broadcast: the 32 lanes of a warp share the tile group) and 4 conflict-free
-// weight loads for 32 FMAs.  in rows must be 16-byte aligned (in_stride % 4 == 0).
-template <int K_IN, int N_OUT, typename Epi>
-__device__ __forceinline__ void dense_tiled(const float* in, int in_stride, int nb, const float* Wt, Epi epi) {
-  constexpr int TT = 8;
-  static_assert(K_IN % 4 == 0 && N_OUT % 32 == 0, "dense_tiled shape");
-  const int ngroups = (nb + TT - 1) / TT;
-  for (int task = threadIdx.x; task < ngroups * N_OUT; task += blockDim.x) {
-    const int gi = task / N_OUT, m = task - gi * N_OUT;
-    const int tb = gi * TT;
-    float acc[TT];
-    const float4* ip[TT];
+// ---- parameter blocks (floats, every block a multiple of 4 so 16-byte copies work) -------------
+// complexity MLP: W0t[8][64] | b0[64] g1[64] be1[64] | W3t[64][32] | b3[32] g4[32] be4[32] | W6[32] b6 pad3
+constexpr int CMLP_SMEM_FLOATS = 512 + 192 + 2048 + 96 + 36;             // 2884 == MCAQ_CMLP_FLOATS
+// mapper: W0t[3][32] | b0 a0 be0 [32] | W3t[32][64] | b3 a3 be3 [64] | W6t[64][32] | b6 a6 be6 [32] | W9[32] b9 pad3
+constexpr int MAPPER_SMEM_FLOATS = 96 + 96 + 2048 + 192 + 2048 + 96 + 36;   // 4612 == MCAQ_MAPPER_FLOATS
+// soft mask: W0[8][2][3][3] | b0[8] | W2[2][8] | b2[2] | smooth[5][5] | pad1
+constexpr int SOFTMASK_SMEM_FLOATS = 196;                                   // == MCAQ_SOFTMASK_FLOATS
+
+constexpr int NET_TT = 4;                                    // tiles a warp carries through a net at once
+constexpr int NET_WARP_SCRATCH = NET_TT * (64 + 32 + 32 + 4);   // floats of scratch per warp (528)
+
+// plain cooperative copy global -> shared (n % 4 == 0, both 16-byte aligned)
+__device__ __forceinline__ void copy_params(const float* __restrict__ src, float* dst, int n) {
+  for (int i = threadIdx.x; i < n / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+}
+
+// asynchronous copy global -> shared (LDGSTS, 16 bytes per operation); pair with cp_async_wait_all
+__device__ __forceinline__ void copy_params_async(const float* __restrict__ src, float* dst, int n) {
+  for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 4 * i);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 4 * i) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// LayerNorm + ReLU of one value per lane (D = 32) or two values per lane (D = 64)
+__device__ __forceinline__ void ln64_relu(float& a0, float& a1, float g0, float g1, float be0, float be1) {
+  const float mean = __fdiv_rn(warp_tree_sum(__fadd_rn(a0, a1)), 64.f);
+  const float d0 = __fsub_rn(a0, mean), d1 = __fsub_rn(a1, mean);
+  const float var = __fdiv_rn(warp_tree_sum(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1))), 64.f);
+  const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
+  a0 = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g0), be0), 0.f);
+  a1 = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d1, rstd), g1), be1), 0.f);
+}
+__device__ __forceinline__ float ln32_relu(float a0, float g, float be) {
+  const float mean = __fdiv_rn(warp_tree_sum(a0), 32.f);
+  const float d0 = __fsub_rn(a0, mean);
+  const float var = __fdiv_rn(warp_tree_sum(__fmul_rn(d0, d0)), 32.f);
+  const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
+  return fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g), be), 0.f);
+}
+
+// out[j] (+)= sum_k act[j][k] * Wt[k][unit]: FMA chain over k from 0 for NET_TT tiles at once.
+// act rows are 16-byte aligned shared memory (broadcast LDS.128), Wt column reads are conflict-free.
+template <int K_IN, int N_OUT>
+__device__ __forceinline__ void dense_warp(const float* act, int act_stride, const float* Wt, int unit,
+                                           float (&acc)[NET_TT]) {
 #pragma unroll
-    for (int j = 0; j < TT; ++j) {
-      acc[j] = 0.f;
-      ip[j] = reinterpret_cast<const float4*>(in + min(tb + j, nb - 1) * in_stride);
+  for (int j = 0; j < NET_TT; ++j) acc[j] = 0.f;
+#pragma unroll 4
+  for (int k4 = 0; k4 < K_IN / 4; ++k4) {
+    const float w0 = Wt[(4 * k4 + 0) * N_OUT + unit], w1 = Wt[(4 * k4 + 1) * N_OUT + unit];
+    const float w2 = Wt[(4 * k4 + 2) * N_OUT + unit], w3 = Wt[(4 * k4 + 3) * N_OUT + unit];
+#pragma unroll
+    for (int j = 0; j < NET_TT; ++j) {
+      const float4 a = *reinterpret_cast<const float4*>(act + j * act_stride + 4 * k4);
+      acc[j] = fmaf(a.x, w0, acc[j]);
+      acc[j] = fmaf(a.y, w1, acc[j]);
+      acc[j] = fmaf(a.z, w2, acc[j]);
+      acc[j] = fmaf(a.w, w3, acc[j]);
     }
-#pragma unroll 2
-    for (int k4 = 0; k4 < K_IN / 4; ++k4) {
-      const float w0 = Wt[(4 * k4 + 0) * N_OUT + m], w1 = Wt[(4 * k4 + 1) * N_OUT + m];
-      const float w2 = Wt[(4 * k4 + 2) * N_OUT + m], w3 = Wt[(4 * k4 + 3) * N_OUT + m];
-#pragma unroll
-      for (int j = 0; j < TT; ++j) {
-        const float4 a = ip[j][k4];
-        acc[j] = fmaf(a.x, w0, acc[j]);
-        acc[j] = fmaf(a.y, w1, acc[j]);
-        acc[j] = fmaf(a.z, w2, acc[j]);
-        acc[j] = fmaf(a.w, w3, acc[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < TT; ++j)
-      if (tb + j < nb) epi(tb + j, m, acc[j]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// complexity MLP 8 -> 64 (LN, ReLU) -> 32 (LN, ReLU) -> 1, sigmoid; 5x5 bilateral; clamp
-// smem need: cpx_scratch_floats(ntiles) + 2*ntiles
+// complexity MLP 8 -> 64 (LN, ReLU) -> 32 (LN, ReLU) -> 1, sigmoid  (morphology.py:81-97)
+// craw[t] for t in [t_lo, t_hi).  phi: [ntiles][8] floats, 16-byte aligned rows (shared or global);
+// w: CMLP block in shared memory; scratch: NET_WARP_SCRATCH floats per warp.  Warp-level only: the
+// caller synchronises the CTA before anyone reads craw.
 // ---------------------------------------------------------------------------------------------
-constexpr int CMLP_SMEM_FLOATS = 512 + 192 + 2048 + 96 + 36;   // W0t b0 g1 be1 | W3t b3 g4 be4 | W6 b6
-
-__device__ __forceinline__ void complexity_load_weights(const float* __restrict__ cmlp, float* w) {
-  const int tid = threadIdx.x, NT = blockDim.x;
-  for (int i = tid; i < 512; i += NT) { const int m = i >> 3, k = i & 7; w[k * 64 + m] = __ldg(cmlp + i); }
-  for (int i = tid; i < 192; i += NT) w[512 + i] = __ldg(cmlp + 512 + i);
-  for (int i = tid; i < 2048; i += NT) { const int m = i >> 6, k = i & 63; w[704 + k * 32 + m] = __ldg(cmlp + 704 + i); }
-  for (int i = tid; i < 96; i += NT) w[2752 + i] = __ldg(cmlp + 2752 + i);
-  for (int i = tid; i < 33; i += NT) w[2848 + i] = __ldg(cmlp + 2848 + i);
-}
-
-// Tiles are processed in batches of NET_TB; within a batch every (tile, unit) output is one
-// thread's FMA chain, so the dense layers run at CTA width instead of one warp per tile.
-// All functions take a tile range [t_lo, t_hi): the fused kernel splits an image's tiles over the
-// CTAs of a cluster and all-gathers the results through distributed shared memory.
-constexpr int NET_TB = 128;
-constexpr int ROW64 = 68, ROW32 = 36;                  // padded, 16-byte aligned activation rows
-constexpr int CPX_ACT_FLOATS = NET_TB * (ROW64 + ROW32);   // h1 [TB][68], h2 [TB][36]
-
-__host__ __device__ __forceinline__ int cpx_scratch_floats(int ntiles) {
-  const int act = CPX_ACT_FLOATS, bil = ntiles * 25;
-  return CMLP_SMEM_FLOATS + (act > bil ? act : bil);
-}
-
-// craw[t] = sigmoid(MLP(phi[t])) for t in [t_lo, t_hi).  phi: [ntiles][8] (global or shared),
-// weights already in w, act: CPX_ACT_FLOATS scratch.
-__device__ __forceinline__ void complexity_mlp_range(const float* phi, int t_lo, int t_hi, const float* w,
-                                                     float* act, float* craw, float* __restrict__ raw_out) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
+__device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo, int t_hi, const float* w,
+                                                     float* scratch_all, float* craw, float* __restrict__ raw_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const float* W0t = w;
   const float* b0 = w + 512;
   const float* g1 = w + 576;
@@ -105,55 +115,70 @@ __device__ __forceinline__ void complexity_mlp_range(const float* phi, int t_lo,
   const float* be4 = w + 2816;
   const float* W6 = w + 2848;
   const float b6 = w[2880];
-  float* h1 = act;                       // [TB][68]
-  float* h2 = act + NET_TB * ROW64;      // [TB][36]
-  for (int t0 = t_lo; t0 < t_hi; t0 += NET_TB) {
-    const int nb = min(NET_TB, t_hi - t0);
-    for (int o = tid; o < nb * 64; o += NT) {     // layer 1: 8 -> 64
-      const int t = o >> 6, m = o & 63;
-      const float* in = phi + (t0 + t) * 8;
-      float acc = 0.f;
+  float* h1 = scratch_all + warp * NET_WARP_SCRATCH;      // [TT][64]
+  float* h2 = h1 + NET_TT * 64;                           // [TT][32]
+  for (int tg = t_lo + warp * NET_TT; tg < t_hi; tg += nwarps * NET_TT) {
+    float a0[NET_TT], a1[NET_TT];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc = fmaf(in[k], W0t[k * 64 + m], acc);
-      h1[t * ROW64 + m] = __fadd_rn(acc, b0[m]);
+    for (int j = 0; j < NET_TT; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+    float4 pa[NET_TT], pb[NET_TT];
+#pragma unroll
+    for (int j = 0; j < NET_TT; ++j) {
+      const float4* pr = reinterpret_cast<const float4*>(phi + min(tg + j, t_hi - 1) * 8);
+      pa[j] = pr[0];
+      pb[j] = pr[1];
     }
-    __syncthreads();
-    for (int t = warp; t < nb; t += nwarps) {     // LayerNorm(64) + ReLU, one warp per tile
-      const float a0 = h1[t * ROW64 + lane], a1 = h1[t * ROW64 + lane + 32];
-      const float mean = __fdiv_rn(warp_tree_sum(__fadd_rn(a0, a1)), 64.f);
-      const float d0 = __fsub_rn(a0, mean), d1 = __fsub_rn(a1, mean);
-      const float var = __fdiv_rn(warp_tree_sum(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1))), 64.f);
-      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
-      h1[t * ROW64 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g1[lane]), be1[lane]), 0.f);
-      h1[t * ROW64 + lane + 32] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d1, rstd), g1[lane + 32]), be1[lane + 32]), 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float w0 = W0t[k * 64 + lane], w1 = W0t[k * 64 + 32 + lane];
+#pragma unroll
+      for (int j = 0; j < NET_TT; ++j) {
+        const float p = k == 0 ? pa[j].x : k == 1 ? pa[j].y : k == 2 ? pa[j].z : k == 3 ? pa[j].w
+                      : k == 4 ? pb[j].x : k == 5 ? pb[j].y : k == 6 ? pb[j].z : pb[j].w;
+        a0[j] = fmaf(p, w0, a0[j]);
+        a1[j] = fmaf(p, w1, a1[j]);
+      }
     }
-    __syncthreads();
-    // layer 2: 64 -> 32, register tiled (8 tiles x 1 unit per thread)
-    dense_tiled<64, 32>(h1, ROW64, nb, W3t, [&](int t, int m, float acc) { h2[t * ROW32 + m] = __fadd_rn(acc, b3[m]); });
-    __syncthreads();
-    for (int t = warp; t < nb; t += nwarps) {     // LayerNorm(32) + ReLU
-      const float a0 = h2[t * ROW32 + lane];
-      const float mean = __fdiv_rn(warp_tree_sum(a0), 32.f);
-      const float d0 = __fsub_rn(a0, mean);
-      const float var = __fdiv_rn(warp_tree_sum(__fmul_rn(d0, d0)), 32.f);
-      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
-      h2[t * ROW32 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g4[lane]), be4[lane]), 0.f);
+    {
+      const float bb0 = b0[lane], bb1 = b0[lane + 32];
+      const float gg0 = g1[lane], gg1 = g1[lane + 32], ee0 = be1[lane], ee1 = be1[lane + 32];
+#pragma unroll
+      for (int j = 0; j < NET_TT; ++j) {
+        a0[j] = __fadd_rn(a0[j], bb0);
+        a1[j] = __fadd_rn(a1[j], bb1);
+        ln64_relu(a0[j], a1[j], gg0, gg1, ee0, ee1);
+        h1[j * 64 + lane] = a0[j];
+        h1[j * 64 + 32 + lane] = a1[j];
+      }
     }
-    __syncthreads();
-    for (int t = tid; t < nb; t += NT) {          // layer 3: 32 -> 1 and sigmoid, one thread per tile
+    __syncwarp();
+    float acc[NET_TT];
+    dense_warp<64, 32>(h1, 64, W3t, lane, acc);
+    {
+      const float bb = b3[lane], gg = g4[lane], ee = be4[lane];
+#pragma unroll
+      for (int j = 0; j < NET_TT; ++j) h2[j * 32 + lane] = ln32_relu(__fadd_rn(acc[j], bb), gg, ee);
+    }
+    __syncwarp();
+    if (lane < NET_TT && tg + lane < t_hi) {               // layer 3: 32 -> 1 and sigmoid, one lane per tile
       float z = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) z = fmaf(h2[t * ROW32 + k], W6[k], z);
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 a = *reinterpret_cast<const float4*>(h2 + lane * 32 + 4 * k4);
+        const float4 ww = *reinterpret_cast<const float4*>(W6 + 4 * k4);
+        z = fmaf(a.x, ww.x, z); z = fmaf(a.y, ww.y, z); z = fmaf(a.z, ww.z, z); z = fmaf(a.w, ww.w, z);
+      }
       const float c = sigmoid_exact(__fadd_rn(z, b6));
-      craw[t0 + t] = c;
-      if (raw_out) raw_out[t0 + t] = c;
+      craw[tg + lane] = c;
+      if (raw_out) raw_out[tg + lane] = c;
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
 // 5x5 bilateral filter with replicate padding (morphology.py:309-354) and clamp, for tiles
 // [t_lo, t_hi); craw must hold ALL tiles of the image.  wgt: 25*(t_hi-t_lo) floats of scratch.
+// Block-level (contains barriers).
 __device__ __forceinline__ void bilateral_range(const float* craw, int ht, int wt, int t_lo, int t_hi, float* wgt,
                                                 float* cfin, float* __restrict__ out) {
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -203,113 +228,124 @@ __device__ __forceinline__ float finish_bits(float bits, float temperature, int 
   return bits;
 }
 
-constexpr int MAPPER_SMEM_FLOATS = 192 + 2048 + 192 + 2048 + 96 + 36;   // W0 v0 | W3t v3 | W6t v6 | W9 b9
-
-__device__ __forceinline__ void mapper_load_weights(const float* __restrict__ mp, float* w) {
-  const int tid = threadIdx.x, NT = blockDim.x;
-  for (int i = tid; i < 192; i += NT) w[i] = __ldg(mp + i);
-  for (int i = tid; i < 2048; i += NT) { const int m = i >> 5, k = i & 31; w[192 + k * 64 + m] = __ldg(mp + 192 + i); }
-  for (int i = tid; i < 192; i += NT) w[2240 + i] = __ldg(mp + 2240 + i);
-  for (int i = tid; i < 2048; i += NT) { const int m = i >> 6, k = i & 63; w[2432 + k * 32 + m] = __ldg(mp + 2432 + i); }
-  for (int i = tid; i < 96; i += NT) w[4480 + i] = __ldg(mp + 4480 + i);
-  for (int i = tid; i < 33; i += NT) w[4576 + i] = __ldg(mp + 4576 + i);
-}
-
-constexpr int MAP_ACT_FLOATS = NET_TB * (4 + ROW32 + ROW64 + ROW32);   // zin [TB][4], g0 [TB][36], g1 [TB][68], g2 [TB][36]
-
-// bits_s[t] for t in [t_lo, t_hi); cmap indexed by absolute tile
-__device__ __forceinline__ void mapper_mlp_range(const float* cmap, int t_lo, int t_hi, const float* w, float* act,
-                                                 float temperature, int use_t, int continuous,
+// ComplexityToBitMappingNetwork (bit_allocation.py:218-280, eval BN folded): bits_s[t] for t in
+// [t_lo, t_hi); cmap indexed by absolute tile.  Warp-level only, like complexity_mlp_warps.
+__device__ __forceinline__ void mapper_mlp_warps(const float* cmap, int t_lo, int t_hi, const float* w,
+                                                 float* scratch_all, float temperature, int use_t, int continuous,
                                                  float lo, float hi, float* bits_s, float* __restrict__ out) {
-  const int tid = threadIdx.x, NT = blockDim.x;
-  const float* W0 = w;
-  const float* v0 = w + 96;
-  const float* W3t = w + 192;
-  const float* v3 = w + 2240;
-  const float* W6t = w + 2432;
-  const float* v6 = w + 4480;
-  const float* W9 = w + 4576;
-  float* zin = act;                      // [TB][4]
-  float* g0 = zin + NET_TB * 4;          // [TB][36]
-  float* g1 = g0 + NET_TB * ROW32;       // [TB][68]
-  float* g2 = g1 + NET_TB * ROW64;       // [TB][36]
-  for (int t0 = t_lo; t0 < t_hi; t0 += NET_TB) {
-    const int nb = min(NET_TB, t_hi - t0);
-    for (int t = tid; t < nb; t += NT) {          // z0 = [c, c^2, log1p(c)]  (Eq.13)
-      const float c = fminf(fmaxf(cmap[t0 + t], 0.f), 1.f);
-      zin[t * 4 + 0] = c;
-      zin[t * 4 + 1] = __fmul_rn(c, c);
-      zin[t * 4 + 2] = (float)log1p((double)c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float* W0t = w;                  // [3][32]
+  const float* v0 = w + 96;              // b, alpha, beta [32]
+  const float* W3t = w + 192;            // [32][64]
+  const float* v3 = w + 2240;            // b, alpha, beta [64]
+  const float* W6t = w + 2432;           // [64][32]
+  const float* v6 = w + 4480;            // b, alpha, beta [32]
+  const float* W9 = w + 4576;            // [32], b9
+  float* g1 = scratch_all + warp * NET_WARP_SCRATCH;      // [TT][64]
+  float* g0 = g1 + NET_TT * 64;                           // [TT][32]
+  float* g2 = g0 + NET_TT * 32;                           // [TT][32]
+  float* zin = g2 + NET_TT * 32;                          // [TT][4]
+  for (int tg = t_lo + warp * NET_TT; tg < t_hi; tg += nwarps * NET_TT) {
+    if (lane < NET_TT) {                                  // z0 = [c, c^2, log1p(c)]  (Eq.13)
+      const float c = fminf(fmaxf(cmap[min(tg + lane, t_hi - 1)], 0.f), 1.f);
+      *reinterpret_cast<float4*>(zin + lane * 4) = make_float4(c, __fmul_rn(c, c), (float)log1p((double)c), 0.f);
     }
-    __syncthreads();
-    for (int o = tid; o < nb * 32; o += NT) {     // 3 -> 32, BN, ReLU
-      const int t = o >> 5, m = o & 31;
-      float acc = __fmul_rn(zin[t * 4 + 0], W0[m * 3 + 0]);
-      acc = fmaf(zin[t * 4 + 1], W0[m * 3 + 1], acc);
-      acc = fmaf(zin[t * 4 + 2], W0[m * 3 + 2], acc);
-      const float x = __fadd_rn(acc, v0[m]);
-      g0[t * ROW32 + m] = fmaxf(__fadd_rn(__fmul_rn(x, v0[32 + m]), v0[64 + m]), 0.f);
+    __syncwarp();
+    {                                                     // 3 -> 32, BN, ReLU
+      const float w0 = W0t[lane], w1 = W0t[32 + lane], w2 = W0t[64 + lane];
+      const float bb = v0[lane], al = v0[32 + lane], be = v0[64 + lane];
+#pragma unroll
+      for (int j = 0; j < NET_TT; ++j) {
+        const float4 z = *reinterpret_cast<const float4*>(zin + j * 4);
+        float acc = __fmul_rn(z.x, w0);
+        acc = fmaf(z.y, w1, acc);
+        acc = fmaf(z.z, w2, acc);
+        const float x = __fadd_rn(acc, bb);
+        g0[j * 32 + lane] = fmaxf(__fadd_rn(__fmul_rn(x, al), be), 0.f);
+      }
     }
-    __syncthreads();
-    dense_tiled<32, 64>(g0, ROW32, nb, W3t, [&](int t, int m, float acc) {      // 32 -> 64, BN, ReLU
-      const float x = __fadd_rn(acc, v3[m]);
-      g1[t * ROW64 + m] = fmaxf(__fadd_rn(__fmul_rn(x, v3[64 + m]), v3[128 + m]), 0.f);
-    });
-    __syncthreads();
-    dense_tiled<64, 32>(g1, ROW64, nb, W6t, [&](int t, int m, float acc) {      // 64 -> 32, BN, ReLU
-      const float x = __fadd_rn(acc, v6[m]);
-      g2[t * ROW32 + m] = fmaxf(__fadd_rn(__fmul_rn(x, v6[32 + m]), v6[64 + m]), 0.f);
-    });
-    __syncthreads();
-    for (int t = tid; t < nb; t += NT) {          // 32 -> 1, sigmoid, Eq.17, temperature / STE
+    __syncwarp();
+    {                                                     // 32 -> 64, BN, ReLU (two units per lane)
+      float acc0[NET_TT], acc1[NET_TT];
+      dense_warp<32, 64>(g0, 32, W3t, lane, acc0);
+      dense_warp<32, 64>(g0, 32, W3t, lane + 32, acc1);
+      const float b_0 = v3[lane], a_0 = v3[64 + lane], e_0 = v3[128 + lane];
+      const float b_1 = v3[32 + lane], a_1 = v3[96 + lane], e_1 = v3[160 + lane];
+#pragma unroll
+      for (int j = 0; j < NET_TT; ++j) {
+        g1[j * 64 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(acc0[j], b_0), a_0), e_0), 0.f);
+        g1[j * 64 + 32 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(acc1[j], b_1), a_1), e_1), 0.f);
+      }
+    }
+    __syncwarp();
+    {                                                     // 64 -> 32, BN, ReLU
+      float acc[NET_TT];
+      dense_warp<64, 32>(g1, 64, W6t, lane, acc);
+      const float bb = v6[lane], al = v6[32 + lane], be = v6[64 + lane];
+#pragma unroll
+      for (int j = 0; j < NET_TT; ++j)
+        g2[j * 32 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(acc[j], bb), al), be), 0.f);
+    }
+    __syncwarp();
+    if (lane < NET_TT && tg + lane < t_hi) {              // 32 -> 1, sigmoid, Eq.17, temperature / STE
       float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) acc = fmaf(g2[t * ROW32 + k], W9[k], acc);
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 a = *reinterpret_cast<const float4*>(g2 + lane * 32 + 4 * k4);
+        const float4 ww = *reinterpret_cast<const float4*>(W9 + 4 * k4);
+        acc = fmaf(a.x, ww.x, acc); acc = fmaf(a.y, ww.y, acc); acc = fmaf(a.z, ww.z, acc); acc = fmaf(a.w, ww.w, acc);
+      }
       const float s = sigmoid_exact(__fadd_rn(acc, W9[32]));
       const float bits = finish_bits(__fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), s)), temperature, use_t,
                                      continuous, lo, hi);
-      bits_s[t0 + t] = bits;
-      if (out) out[t0 + t] = bits;
+      bits_s[tg + lane] = bits;
+      if (out) out[tg + lane] = bits;
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
-// torch.quantile(q, 'linear') on a sorted row: fp32 rank, torch.lerp formula
-__device__ __forceinline__ float quantile_sorted(const float* srt, int n, float q) {
+// torch.quantile(q, 'linear'): fp32 rank, torch.lerp formula on the two neighbouring order statistics
+__device__ __forceinline__ void quantile_ranks(int n, float q, int& lo, int& hi, float& w) {
   const float rank = __fmul_rn(q, (float)(n - 1));
-  const int lo = (int)floorf(rank), hi = (int)ceilf(rank);
-  const float w = __fsub_rn(rank, (float)lo);
-  const float a = srt[lo], bb = srt[hi];
+  lo = (int)floorf(rank);
+  hi = (int)ceilf(rank);
+  w = __fsub_rn(rank, (float)lo);
+}
+__device__ __forceinline__ float quantile_lerp(float a, float bb, float w) {
   const float diff = __fsub_rn(bb, a);
   if (w < 0.5f) return __fadd_rn(a, __fmul_rn(w, diff));
   return __fsub_rn(bb, __fmul_rn(diff, __fsub_rn(1.0f, w)));
 }
 
-// LinearBitMapper: quantiles over ALL tiles of the image (cmap: [ntiles]); writes bits for
-// [t_lo, t_hi).  srt: npow2 floats of scratch.
-__device__ __forceinline__ void mapper_linear_range(const float* cmap, int ntiles, int npow2, float* srt,
-                                                    int t_lo, int t_hi, float temperature, int use_t,
-                                                    int continuous, float lo, float hi, float eps_spread,
-                                                    float* bits_s, float* __restrict__ out) {
+// LinearBitMapper (bit_allocation.py:42-80): 2 % / 98 % quantiles over ALL tiles of the image
+// (cmap: [ntiles]) by rank counting (each element counts the elements ordered before it; the four
+// wanted order statistics are written by their owners), then bits for [t_lo, t_hi).  sel: 4 floats.
+// Block-level (contains barriers).
+__device__ __forceinline__ void mapper_linear_range(const float* cmap, int ntiles, float* sel, int t_lo, int t_hi,
+                                                    float temperature, int use_t, int continuous, float lo,
+                                                    float hi, float eps_spread, float* bits_s,
+                                                    float* __restrict__ out) {
   const int tid = threadIdx.x, NT = blockDim.x;
-  for (int i = tid; i < npow2; i += NT) srt[i] = i < ntiles ? cmap[i] : INFINITY;
-  __syncthreads();
-  for (int k = 2; k <= npow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < npow2; i += NT) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const float a = srt[i], bb = srt[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > bb) == up) { srt[i] = bb; srt[ixj] = a; }
-        }
-      }
-      __syncthreads();
+  int l0, h0, l1, h1;
+  float w0, w1;
+  quantile_ranks(ntiles, 0.02f, l0, h0, w0);
+  quantile_ranks(ntiles, 0.98f, l1, h1, w1);
+  for (int i = tid; i < ntiles; i += NT) {
+    const float v = cmap[i];
+    int r = 0;
+    for (int j = 0; j < ntiles; ++j) {
+      const float u = cmap[j];
+      r += (u < v || (u == v && j < i)) ? 1 : 0;
     }
+    if (r == l0) sel[0] = v;
+    if (r == h0) sel[1] = v;
+    if (r == l1) sel[2] = v;
+    if (r == h1) sel[3] = v;
   }
-  const float qlo = quantile_sorted(srt, ntiles, 0.02f);
-  const float qhi = quantile_sorted(srt, ntiles, 0.98f);
+  __syncthreads();
+  const float qlo = quantile_lerp(sel[0], sel[1], w0);
+  const float qhi = quantile_lerp(sel[2], sel[3], w1);
   const float spread = __fsub_rn(qhi, qlo);
   for (int t = t_lo + tid; t < t_hi; t += NT) {
     const float v = cmap[t];
@@ -325,67 +361,43 @@ __device__ __forceinline__ void mapper_linear_range(const float* cmap, int ntile
 }
 
 // ---------------------------------------------------------------------------------------------
-// learned soft mask (quantization.py:213-239), in three range-aware steps
-// packed params: W0[8][2][3][3] b0[8] W2[2][8] b2[2] smooth[5][5]  (195 floats)
+// learned soft mask (quantization.py:213-239)
+// packed params: W0[8][2][3][3] b0[8] W2[2][8] b2[2] smooth[5][5]  (195 floats + 1 pad)
 // ---------------------------------------------------------------------------------------------
-// (a) act[t] = mean over the tile's adaptive window of sum_c|x| / C, for tile rows [ty_lo, ty_hi);
-//     returns the maximum over those tiles (every thread gets it).  rows: H*Wt floats, red: 32.
-__device__ __forceinline__ float softmask_act_range(const float* __restrict__ ap, int C, int H, int W, int Ht,
-                                                    int Wt, int ty_lo, int ty_hi, float* rows, float* red,
-                                                    float* act) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
+// (a) generic tile activity: act[t] = mean over the tile's adaptive-pool window of sum_c|x| / C for
+//     tile rows [ty_lo, ty_hi): column sums top-to-bottom, then left-to-right (oracle order), one
+//     thread per tile.  Used when the window grid is not the analyzer's tile grid.
+__device__ __forceinline__ void softmask_act_generic(const float* __restrict__ ap, int C, int H, int W, int Ht,
+                                                     int Wt, int ty_lo, int ty_hi, float* act) {
   const float fC = (float)C;
   const float rC = __frcp_rn(fC);
-  const int y_lo = (ty_lo * H) / Ht, y_hi = (ty_hi * H + Ht - 1) / Ht;
-  for (int i = y_lo * Wt + tid; i < y_hi * Wt; i += NT) {
-    const int y = i / Wt, j = i - y * Wt;
-    const int xs = (j * W) / Wt, xe = ((j + 1) * W + Wt - 1) / Wt;
-    float s = 0.f;
-    for (int x0 = xs; x0 < xe; x0 += 8) {          // 8 independent loads, then the ordered sum
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = (x0 + u < xe) ? __ldg(ap + y * W + x0 + u) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (x0 + u < xe) {
-          const float av = fabsf(v[u]);
-          const float q = (av >= 1e-30f && av < 1e27f) ? div_markstein(v[u], fC, rC) : __fdiv_rn(v[u], fC);
-          s = __fadd_rn(s, q);
-        }
-    }
-    rows[i] = s;
-  }
-  __syncthreads();
-  float lmax = -INFINITY;
-  for (int t = ty_lo * Wt + tid; t < ty_hi * Wt; t += NT) {
+  for (int t = ty_lo * Wt + threadIdx.x; t < ty_hi * Wt; t += blockDim.x) {
     const int i = t / Wt, j = t - i * Wt;
     const int ys = (i * H) / Ht, ye = ((i + 1) * H + Ht - 1) / Ht;
     const int xs = (j * W) / Wt, xe = ((j + 1) * W + Wt - 1) / Wt;
-    float s = 0.f;
-    for (int y = ys; y < ye; ++y) s = __fadd_rn(s, rows[y * Wt + j]);
-    const float a = __fdiv_rn(s, (float)((ye - ys) * (xe - xs)));
-    act[t] = a;
-    lmax = fmaxf(lmax, a);
+    float tot = 0.f;
+    for (int x = xs; x < xe; ++x) {
+      float s = 0.f;
+      for (int y = ys; y < ye; ++y) {
+        const float v = __ldg(ap + y * W + x);
+        const float av = fabsf(v);
+        const float q = (av >= 1e-30f && av < 1e27f) ? div_markstein(v, fC, rC) : __fdiv_rn(v, fC);
+        s = __fadd_rn(s, q);
+      }
+      tot = __fadd_rn(tot, s);
+    }
+    act[t] = __fdiv_rn(tot, (float)((ye - ys) * (xe - xs)));
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  if (lane == 0) red[warp] = lmax;
-  __syncthreads();
-  float amax = red[0];
-  for (int w = 1; w < nwarps; ++w) amax = fmaxf(amax, red[w]);
-  __syncthreads();
-  return amax;
 }
 
 // (b) tile head for tiles [t_lo, t_hi): act / (amax + 1e-8), bits -> [0,1], conv3x3(2->8)+ReLU,
-//     conv1x1(8->2), softmax channel 0.  bits/act hold ALL tiles; P: 196 floats (params loaded
-//     here), bn/an: nt floats each of scratch.
+//     conv1x1(8->2), softmax channel 0.  bits/act hold ALL tiles; P: the parameter block in shared
+//     memory; bn/an: nt floats each of scratch.  Block-level (contains barriers).
 __device__ __forceinline__ void softmask_head_range(const float* bits, const float* act, float amax, int Ht, int Wt,
-                                                    int t_lo, int t_hi, const float* __restrict__ prm, float* P,
-                                                    float* bn, float* an, float* mt, float* __restrict__ tiles_out) {
+                                                    int t_lo, int t_hi, const float* P, float* bn, float* an,
+                                                    float* mt, float* __restrict__ tiles_out) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int nt = Ht * Wt;
-  for (int i = tid; i < 195; i += NT) P[i] = __ldg(prm + i);
   const float aden = __fadd_rn(amax, 1e-8f);
   for (int t = tid; t < nt; t += NT) {
     an[t] = __fdiv_rn(act[t], aden);
@@ -436,8 +448,8 @@ __device__ __forceinline__ void softmask_head_range(const float* bits, const flo
   __syncthreads();
 }
 
-// (c) rows [h_lo, h_hi) of m = smooth5x5(nearest_upsample(mt)), replicate padding, FMA chain over
-//     taps in row-major order.  mt holds ALL tiles; P holds the params (smooth kernel at +170).
+// (c) generic: rows [h_lo, h_hi) of m = smooth5x5(nearest_upsample(mt)), replicate padding, FMA
+//     chain over taps in row-major order.  mt holds ALL tiles; P holds the params (smooth kernel at +170).
 __device__ __forceinline__ void softmask_plane_rows(const float* mt, const float* P, int H, int W, int Ht, int Wt,
                                                     int h_lo, int h_hi, float* __restrict__ mo) {
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -456,6 +468,59 @@ __device__ __forceinline__ void softmask_plane_rows(const float* mt, const float
       for (int kx = 0; kx < 5; ++kx) acc = fmaf(mt[iy * Wt + ix[kx]], ks[ky * 5 + kx], acc);
     }
     mo[p] = acc;
+  }
+}
+
+// (c') tile-aligned planes (H == Ht*tile, W == Wt*tile, tile a power of two >= 4): inside a tile the
+//     25 taps of a pixel come from at most 3x3 neighbouring tiles and the pattern depends only on the
+//     pixel's offset class (0, 1, interior, tile-2, tile-1) per axis, so every tile has <= 25 distinct
+//     mask values.  cls[(t - t_lo)*25 + cy*5 + cx] is that value (same FMA chain as the generic path).
+__device__ __forceinline__ int mask_class(int d, int tile) { return d < 2 ? d : (d >= tile - 2 ? d - (tile - 5) : 2); }
+
+__device__ __forceinline__ void softmask_class_table(const float* mt, const float* P, int Ht, int Wt, int t_lo,
+                                                     int t_hi, float* cls) {
+  const float* ks = P + 170;
+  for (int o = threadIdx.x; o < (t_hi - t_lo) * 25; o += blockDim.x) {
+    const int tl = o / 25, c = o - tl * 25;
+    const int cy = c / 5, cx = c - cy * 5;
+    const int t = t_lo + tl;
+    const int ty = t / Wt, tx = t - ty * Wt;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      // tile-row offset of tap ky for class cy: rows above the tile for (cy=0: ky<2, cy=1: ky<1),
+      // below for (cy=3: ky>3, cy=4: ky>2)
+      const int oy = (ky < 2 - cy) ? -1 : ((ky > 6 - cy) ? 1 : 0);
+      const int yy = min(max(ty + oy, 0), Ht - 1);
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const int ox = (kx < 2 - cx) ? -1 : ((kx > 6 - cx) ? 1 : 0);
+        const int xx = min(max(tx + ox, 0), Wt - 1);
+        acc = fmaf(mt[yy * Wt + xx], ks[ky * 5 + kx], acc);
+      }
+    }
+    cls[o] = acc;
+  }
+}
+
+// rows [h_lo, h_hi) of m from the class table (tiles [t_lo, ...) start at tile row h_lo / tile);
+// one float4 (4 pixels of one tile) per thread-iteration.
+__device__ __forceinline__ void softmask_plane_from_classes(const float* cls, int W, int Wt, int tile, int tshift,
+                                                            int t_lo, int h_lo, int h_hi, float* __restrict__ mo) {
+  const int W4 = W >> 2;
+  const int n4 = (h_hi - h_lo) * W4;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int hr = i / W4, w = (i - hr * W4) << 2;
+    const int h = h_lo + hr;
+    const int t = (h >> tshift) * Wt + (w >> tshift);
+    const float* c = cls + (t - t_lo) * 25 + mask_class(h & (tile - 1), tile) * 5;
+    const int d = w & (tile - 1);
+    float4 v;
+    v.x = c[mask_class(d, tile)];
+    v.y = c[mask_class(d + 1, tile)];
+    v.z = c[mask_class(d + 2, tile)];
+    v.w = c[mask_class(d + 3, tile)];
+    *reinterpret_cast<float4*>(mo + (long long)h * W + w) = v;
   }
 }
 

@@ -26,8 +26,9 @@ kernel == oracle bit-for-bit on every discrete quantity):
   torch's vectorised path handles the pixel (all pixels when H*W % 32 == 0).
 * `nn.Linear` is a sequential FMA chain over k starting from 0 with the bias
   added last (bit-identical to torch CPU for out_features > 1).
-* tile float sums are "row then column": each tile row left-to-right, then
-  the row sums top-to-bottom; LayerNorm statistics use a 32-lane butterfly tree.
+* tile float sums are "column then row": each tile column top-to-bottom, then
+  the column sums left-to-right (one GPU thread owns a column); LayerNorm
+  statistics use a 32-lane butterfly tree.
 * Otsu cumulative sums accumulate in fp64 and round to fp32 per element
   (what torch.cumsum does on CPU; exact, hence order independent).
 * transcendental functions are evaluated in fp64 and rounded to fp32.
@@ -281,16 +282,17 @@ def sobel(img: np.ndarray):
 # ----------------------------------------------------------------------------
 
 def tile_sum_f32(p: np.ndarray, tile: int) -> np.ndarray:
-    """Float tile sums, row-then-column order.  p: (B,Hc,Wc) -> (B,ht,wt)."""
+    """Float tile sums, column-then-row order: each tile column top-to-bottom, then the
+    column sums left-to-right.  p: (B,Hc,Wc) -> (B,ht,wt)."""
     B, Hc, Wc = p.shape
     ht, wt = Hc // tile, Wc // tile
     v = p.reshape(B, ht, tile, wt, tile)
-    rows = np.zeros((B, ht, tile, wt), dtype=f32)
-    for x in range(tile):
-        rows = rows + v[:, :, :, :, x]
-    out = np.zeros((B, ht, wt), dtype=f32)
+    cols = np.zeros((B, ht, wt, tile), dtype=f32)
     for y in range(tile):
-        out = out + rows[:, :, y, :]
+        cols = cols + v[:, :, y, :, :]
+    out = np.zeros((B, ht, wt), dtype=f32)
+    for x in range(tile):
+        out = out + cols[:, :, :, x]
     return out
 
 
@@ -780,12 +782,12 @@ def soft_mask_tiles(bit_map: np.ndarray, abs_sum: np.ndarray, C: int, w: dict,
     for i in range(Ht):
         for j in range(Wt):
             win = amean[:, ys[i]:ye[i], xs[j]:xe[j]]
-            rows = np.zeros((B, win.shape[1]), dtype=f32)
-            for x in range(win.shape[2]):
-                rows = rows + win[:, :, x]
+            cols = np.zeros((B, win.shape[2]), dtype=f32)
+            for y in range(win.shape[1]):                     # column sums top-to-bottom ...
+                cols = cols + win[:, y, :]
             tot = np.zeros(B, dtype=f32)
-            for y in range(win.shape[1]):
-                tot = tot + rows[:, y]
+            for x in range(win.shape[2]):                     # ... then left-to-right
+                tot = tot + cols[:, x]
             act[:, i, j] = tot / f32(win.shape[1] * win.shape[2])
     act = (act / (act.max(axis=(1, 2), keepdims=True) + f32(1e-8))).astype(f32)
     bits_norm = np.clip(((bit_map.astype(f32) - f32(2.0)) / f32(6.0)).astype(f32), f32(0), f32(1))

@@ -328,9 +328,13 @@ def test_cluster_split_is_bit_identical(name, linear, M, W):
     s, ab, _ = ops.reduce_planes(x)
     outs = []
     try:
-        for ns in (1, 2, 4, 0):
+        for ns in (0, 1, 2, 4, 8):
             lib.mcaq_debug_cluster_split(ns)
-            r = ops.morph_fused(s, ab, c.C, c.grid, cm, mp, sm, 1.0, want_phi=True)
+            try:
+                r = ops.morph_fused(s, ab, c.C, c.grid, cm, mp, sm, 1.0, want_phi=True)
+            except RuntimeError as e:           # a forced split may not fit shared memory (160x160 on one CTA)
+                assert ns != 0 and "on-chip budget" in str(e)
+                continue
             torch.cuda.synchronize()
             outs.append(r)
     finally:

@@ -46,23 +46,28 @@ def unpack_bits(words: torch.Tensor, Wc: int) -> np.ndarray:
 
 
 def packed_params(W, K):
-    """Device parameter blocks built from the golden fixtures' state_dicts."""
-    import torch.nn as nn
+    """Device parameter blocks built from the golden fixtures' state_dicts, in the layout
+    include/mcaq_b200.h documents (weights transposed to [k][unit], eval BN folded, zero pads)."""
     a = W["analyzer"]
-    cm = np.concatenate([a[f"complexity_mlp.{i}.{n}"].ravel() for i in (0, 1, 3, 4, 6) for n in ("weight", "bias")])
+    z3 = np.zeros(3, np.float32)
+    cm = np.concatenate([a["complexity_mlp.0.weight"].T.ravel(), a["complexity_mlp.0.bias"],
+                         a["complexity_mlp.1.weight"], a["complexity_mlp.1.bias"],
+                         a["complexity_mlp.3.weight"].T.ravel(), a["complexity_mlp.3.bias"],
+                         a["complexity_mlp.4.weight"], a["complexity_mlp.4.bias"],
+                         a["complexity_mlp.6.weight"].ravel(), a["complexity_mlp.6.bias"].ravel(), z3])
     m = W["mapper"]
     parts = []
     for li, bi in ((0, 1), (3, 4), (6, 7)):
         invstd = (1.0 / np.sqrt(m[f"mapping_network.{bi}.running_var"].astype(np.float64) + 1e-5)).astype(np.float32)
         alpha = (invstd * m[f"mapping_network.{bi}.weight"]).astype(np.float32)
         beta = (m[f"mapping_network.{bi}.bias"] - (m[f"mapping_network.{bi}.running_mean"] * alpha).astype(np.float32)).astype(np.float32)
-        parts += [m[f"mapping_network.{li}.weight"].ravel(), m[f"mapping_network.{li}.bias"].ravel(), alpha, beta]
-    parts += [m["mapping_network.9.weight"].ravel(), m["mapping_network.9.bias"].ravel()]
+        parts += [m[f"mapping_network.{li}.weight"].T.ravel(), m[f"mapping_network.{li}.bias"].ravel(), alpha, beta]
+    parts += [m["mapping_network.9.weight"].ravel(), m["mapping_network.9.bias"].ravel(), z3]
     mp = np.concatenate(parts)
     q = W["quantizer"]
     sm = np.concatenate([q["soft_mask.net.0.weight"].ravel(), q["soft_mask.net.0.bias"].ravel(),
                          q["soft_mask.net.2.weight"].ravel(), q["soft_mask.net.2.bias"].ravel(),
-                         q["soft_mask.smooth_kernel"].ravel()])
+                         q["soft_mask.smooth_kernel"].ravel(), z3[:1]])
     assert cm.size == K.CMLP_FLOATS and mp.size == K.MAPPER_FLOATS and sm.size == K.SOFTMASK_FLOATS
     return dev(cm.astype(np.float32)), dev(mp.astype(np.float32)), dev(sm.astype(np.float32))
 

@@ -24,8 +24,12 @@ for (C, H) in ((64, 80), (128, 40), (256, 20), (128, 160), (256, 80), (512, 40))
     s, ab, k = ops.reduce_planes(x)
     for ns in splits:
         lib.mcaq_debug_cluster_split(ns)
-        for _ in range(3):
-            ops.morph_fused(s, ab, C, 8, cm, mp, sm, 1.0)
+        try:
+            for _ in range(3):
+                ops.morph_fused(s, ab, C, 8, cm, mp, sm, 1.0)
+        except RuntimeError as e:
+            print(f"K2 C={C:3d} H={H:3d} split={ns}: {e}")
+            continue
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

@@ -4,7 +4,8 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from mcaq_yolo_b200 import ops, constants as K, modules as M
+from mcaq_yolo_b200 import ops, _lib, constants as K, modules as M
+_lib.load().mcaq_debug_cluster_split(int(os.environ.get('MCAQ_K2_SPLIT', '0')))
 from golden_util import weights
 C, H = int(sys.argv[1]), int(sys.argv[2])
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 64

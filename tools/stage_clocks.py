@@ -7,13 +7,15 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from mcaq_yolo_b200 import ops, _lib, constants as K, modules as M
 from golden_util import weights
 lib = _lib.load()
-names = ["S0-1 load/norm", "S3 adaptive", "S4 lbp+sobel", "S5 phi2/3", "S6 blur", "S7|S8 otsu|mag", "S9 nms",
-         "S10 hyst", "S11 counts", "S11b boxes", "S12 phi", "N1 complexity", "N2 mapper", "N3 softmask"]
+names = ["L load+minmax", "N normalise", "T1 blur|adapt|lbp|act", "T2 mag+sync", "T3 otsu+nms+sync", "T4 hysteresis",
+         "T5 counts+boxes", "phi + weights", "N1 cmlp+gather", "N1 bilateral", "N2 mapper", "N3 softmask"]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+lib.mcaq_debug_cluster_split(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 a, m, q = M.build_fixture_modules(weights(), "cuda")
 cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_network(m.mapping_network), K.pack_soft_mask(q.soft_mask)
 for (C, H) in ((64, 80), (128, 40), (256, 20), (128, 160)):
-    x = (torch.randn(B, C, H, H, device="cuda") * 2).to(torch.bfloat16)
+    x = torch.nn.functional.interpolate(torch.randn(B, C, H // 8, H // 8, device="cuda"), size=(H, H), mode="bicubic")
+    x = (x + 0.1 * torch.randn_like(x)).to(torch.bfloat16)
     s, ab, k = ops.reduce_planes(x)
     clk = torch.zeros(B, 16, dtype=torch.int64, device="cuda")
     lib.mcaq_debug_stage_clocks(clk.data_ptr())
@@ -22,8 +24,8 @@ for (C, H) in ((64, 80), (128, 40), (256, 20), (128, 160)):
     torch.cuda.synchronize()
     lib.mcaq_debug_stage_clocks(None)
     c = clk.cpu().numpy()
-    d = (c[:, 1:15] - c[:, 0:14]).mean(0)
-    tot = (c[:, 14] - c[:, 0]).mean()
+    d = (c[:, 1:13] - c[:, 0:12]).mean(0)
+    tot = (c[:, 12] - c[:, 0]).mean()
     print(f"C={C} H={H}: total {tot:.0f} cycles = {tot / 1.965e3:.1f} us @1.965GHz")
-    for i in range(14):
-        print(f"   {names[i]:16s} {d[i]:9.0f} cyc  {100 * d[i] / tot:5.1f}%")
+    for i in range(12):
+        print(f"   {names[i]:24s} {d[i]:9.0f} cyc  {100 * d[i] / tot:5.1f}%")
