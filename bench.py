@@ -48,7 +48,14 @@ def parse():
     ap.add_argument("--no-streams", action="store_true", help="run the three scales on one stream")
     ap.add_argument("--unfused", action="store_true", help="module-by-module path (9 launches per scale)")
     ap.add_argument("--nccl-in-graph", action="store_true", help="capture the range all-reduce inside one graph per step")
+    ap.add_argument("--nccl-ranges", action="store_true",
+                    help="multi-GPU: merge the ranges with an NCCL all-reduce between K2 and K3 instead of the "
+                         "in-kernel peer-memory exchange")
     ap.add_argument("--sharded", action="store_true", help="use the multi-rank phase split even at world size 1")
+    ap.add_argument("--inflight", type=int, default=4, choices=[1, 2, 4],
+                    help="steps in flight: consecutive steps alternate between this many streams (each with its own "
+                         "workspace), so the latency-bound morphology kernel of one step overlaps the HBM sweeps of "
+                         "its neighbours; 1 = strictly serial steps")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -210,20 +217,31 @@ def run_native(args):
     alg_bytes_step = 3 * esize * elems * B            # K1 read + K3 read + K3 write
 
     from mcaq_yolo_b200.fused import FusedHotPath
-    hot = FusedHotPath(analyzer, mapper, quantizers, temperature=1.0, streams=not args.no_streams)
+    nslot = 1 if (args.unfused or args.nccl_ranges or args.sharded) else args.inflight
+    hots = []
+    for _slot in range(nslot):
+        exchanges = None
+        if world > 1 and not args.nccl_ranges and not args.unfused:
+            # batch sharded over the GPUs of the node: ranges merged inside K2 / K3 over peer memory
+            from mcaq_yolo_b200.peer import RangeExchange
+            exchanges = [RangeExchange.create(C) for C, _, _ in shapes]
+        hots.append(FusedHotPath(analyzer, mapper, quantizers, temperature=1.0, streams=not args.no_streams,
+                                 exchanges=exchanges))
+    hot = hots[0]
+    slot_streams = [torch.cuda.Stream(device=dev) for _ in range(nslot)]
 
     sharded = None
-    if (world > 1 or args.sharded) and not args.unfused:
+    if ((world > 1 and args.nccl_ranges) or args.sharded) and not args.unfused:
         # multi-rank: the range all-reduce is kept out of the captured graphs (fused.ShardedHotPath)
         from mcaq_yolo_b200.fused import ShardedHotPath
         sharded = ShardedHotPath(analyzer, mapper, quantizers, shapes, dev, 1.0)
 
-    def step(feats):
+    def step(feats, slot=0):
         if args.unfused:
             return [M.mcaq_hook_forward(x, analyzer, mapper, q, temperature=1.0) for x, q in zip(feats, quantizers)]
         if sharded is not None:
             return sharded.run(feats)
-        return hot.run(feats)
+        return hots[slot].run(feats)
 
     def barrier():
         if world > 1:
@@ -233,7 +251,7 @@ def run_native(args):
     with torch.no_grad():
         # ---- warm-up (eager) primes host-side caches, then optional CUDA-graph capture ------
         for i in range(max(3, args.warmup)):
-            step(sets[i % INPUT_SETS])
+            step(sets[i % INPUT_SETS], (i % INPUT_SETS) % nslot)
         torch.cuda.synchronize()
         ops.LAUNCHES = 0
         step(sets[0])
@@ -263,13 +281,14 @@ def run_native(args):
         elif not args.no_graph:
             try:
                 graphs, keep = [], []
-                for s in sets:
+                for j, s in enumerate(sets):
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        keep.append(step(s))
+                    with torch.cuda.graph(g, stream=slot_streams[j % nslot]):
+                        keep.append(step(s, j % nslot))
                     graphs.append(g)
-                for g in graphs:
-                    g.replay()
+                for j, g in enumerate(graphs):
+                    with torch.cuda.stream(slot_streams[j % nslot]):
+                        g.replay()
                 torch.cuda.synchronize()
             except Exception as e:       # capture unsupported: time eager launches
                 sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager\n")
@@ -290,10 +309,25 @@ def run_native(args):
                 gB1.replay()
                 torch.cuda.current_stream().wait_event(done)
                 gB2.replay()
-            elif graphs is not None:
-                graphs[i % INPUT_SETS].replay()
             else:
-                step(sets[i % INPUT_SETS])
+                j = i % INPUT_SETS
+                with torch.cuda.stream(slot_streams[j % nslot]):     # steps alternate between the slot streams
+                    if graphs is not None:
+                        graphs[j].replay()
+                    else:
+                        step(sets[j], j % nslot)
+
+        def fork_slots():
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            for st in slot_streams:
+                st.wait_event(ev)
+
+        def join_slots():
+            for st in slot_streams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                torch.cuda.current_stream().wait_event(ev)
 
         for i in range(args.warmup):
             run_step(i)
@@ -304,8 +338,10 @@ def run_native(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        fork_slots()
         for i in range(args.steps):
             run_step(i)
+        join_slots()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -393,42 +429,59 @@ def run_native(args):
         }
 
         # ---- end to end through the public module API with HOST buffers ---------------------------
-        host_in = [torch.empty((B, C, H, Wd), dtype=tdtype).pin_memory() for C, H, Wd in shapes]
-        for h, d in zip(host_in, sets[0]):
-            h.copy_(d)
-        host_out = [torch.empty_like(h).pin_memory() for h in host_in]
-        host_bits = [None] * len(shapes)
-        dev_in = [torch.empty_like(d) for d in sets[0]]
+        # One set of pinned host buffers / device staging buffers per in-flight slot: step i uploads its
+        # inputs, runs the hook bodies and downloads features_q + bit maps on slot stream i % nslot;
+        # before a slot is reused the host waits for that slot's previous step (the consumer has its
+        # result), so uploads of one step overlap downloads of the previous one (PCIe is full duplex).
+        host_in = [[torch.empty((B, C, H, Wd), dtype=tdtype).pin_memory() for C, H, Wd in shapes] for _ in range(nslot)]
+        for hs in host_in:
+            for h, d in zip(hs, sets[0]):
+                h.copy_(d)
+        host_out = [[torch.empty_like(h).pin_memory() for h in hs] for hs in host_in]
+        host_bits = [[None] * len(shapes) for _ in range(nslot)]
+        dev_in = [[torch.empty_like(d) for d in sets[0]] for _ in range(nslot)]
+        done_ev = [None] * nslot
 
-        def e2e_step():
-            for h, d in zip(host_in, dev_in):
-                d.copy_(h, non_blocking=True)
-            recs = step(dev_in)
-            for i, r in enumerate(recs):
-                host_out[i].copy_(r["features_q"], non_blocking=True)
-                if host_bits[i] is None:
-                    host_bits[i] = torch.empty(r["bit_map"].shape, dtype=torch.float32).pin_memory()
-                host_bits[i].copy_(r["bit_map"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()      # the caller reads the results on the host
+        def e2e_step(i):
+            sl = i % nslot
+            if done_ev[sl] is not None:
+                done_ev[sl].synchronize()                      # the caller has read this slot's previous result
+            with torch.cuda.stream(slot_streams[sl]):
+                for h, d in zip(host_in[sl], dev_in[sl]):
+                    d.copy_(h, non_blocking=True)
+                recs = step(dev_in[sl], sl)
+                for k, r in enumerate(recs):
+                    host_out[sl][k].copy_(r["features_q"], non_blocking=True)
+                    if host_bits[sl][k] is None:
+                        host_bits[sl][k] = torch.empty(r["bit_map"].shape, dtype=torch.float32).pin_memory()
+                    host_bits[sl][k].copy_(r["bit_map"], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(slot_streams[sl])
+                done_ev[sl] = ev
 
-        for _ in range(3):
-            e2e_step()
+        def e2e_drain():
+            for ev in done_ev:
+                if ev is not None:
+                    ev.synchronize()
+
+        for i in range(2 * nslot):
+            e2e_step(i)
+        e2e_drain()
         nsteps_e2e = min(args.steps, 20)
+        nsteps_e2e -= nsteps_e2e % nslot
         barrier()
         t0 = time.perf_counter()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(nsteps_e2e):
-            e2e_step()
-        a1.record()
-        barrier()
+        for i in range(nsteps_e2e):
+            e2e_step(i)
+        e2e_drain()
         wall = time.perf_counter() - t0
-        te = torch.tensor([max(a0.elapsed_time(a1) * 1e-3, wall if world == 1 else 0.0)], device=dev, dtype=torch.float64)
+        barrier()
+        te = torch.tensor([wall], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_value = world * B * nsteps_e2e / float(te.item())
-        h2d = sum(h.numel() * h.element_size() for h in host_in)
-        d2h = sum(h.numel() * h.element_size() for h in host_out) + sum(hb.numel() * 4 for hb in host_bits)
+        h2d = sum(h.numel() * h.element_size() for h in host_in[0])
+        d2h = sum(h.numel() * h.element_size() for h in host_out[0]) + sum(hb.numel() * 4 for hb in host_bits[0])
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -436,15 +489,18 @@ def run_native(args):
         "dtype": "f32 arithmetic on %s feature maps" % dtype_name, "data": "synthetic",
         "config": {"workload": args.workload, "per_gpu_batch": B, "shapes_CHW": shapes, "grid": grid, "bits": "2-8",
                    "mapper": "MLP (fixture weights)", "soft_mask": True, "ranges": "dynamic per batch"
-                   + (" (all-reduced MIN over ranks)" if world > 1 else ""),
+                   + ("" if world == 1 else (" (all-reduced MIN over ranks, NCCL)" if sharded is not None else
+                                             " (min over ranks inside K2/K3 through NVLink peer memory, no collective launch)")),
                    "l2": "%d rotating input sets (%.0f MB) > 126 MB L2, no flush" % (INPUT_SETS, INPUT_SETS * esize * elems * B / 1e6),
                    "launch": ("cuda-graph replay" if graphs is not None else "eager")
                    + (", module-by-module" if args.unfused else ", fused K1/K2/K3 per scale")
-                   + ("" if args.no_streams or args.unfused or world > 1 else ", one stream per scale")
-                   + (", ranges all-reduce (NCCL, eager, side stream) between graph segments" if world > 1 else "")},
+                   + ("" if args.no_streams or args.unfused or sharded is not None else ", one stream per scale")
+                   + (", %d steps in flight (alternating streams, one workspace each)" % nslot if nslot > 1 else "")
+                   + (", ranges all-reduce (NCCL, eager, side stream) between graph segments" if sharded is not None else "")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": nsteps_e2e, "api": "FusedHotPath.run(feats) (the hook bodies install() registers), pinned host buffers"},
+                "steps": nsteps_e2e, "api": "FusedHotPath.run(feats) (the hook bodies install() registers), pinned host "
+                "buffers, H2D + hooks + D2H per step, %d slot(s) double-buffered, host wall clock" % nslot},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": roofline,
@@ -457,6 +513,12 @@ def run_native(args):
         sys.stdout.flush()
         os.write(out_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        # orderly shutdown; a watchdog guarantees the process exits even if NCCL teardown stalls
+        import threading
+        threading.Thread(target=lambda: (time.sleep(30), os._exit(0)), daemon=True).start()
+        graphs = keep = None
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

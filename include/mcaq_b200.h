@@ -146,6 +146,38 @@ MCAQ_API int mcaq_morph_fused(const float* sum_plane, const float* abs_plane, in
                               float max_bits, float eps_spread, float* phi, float* complexity,
                               float* bit_map, float* mask, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU, batch sharded): per-channel range merge over peer memory.
+ * The reference has no data parallelism; parity with its single-process batch needs min/max over
+ * the whole batch (quantization.py:423-426, 650-654).  Each rank owns one exchange buffer per scale
+ * (mcaq_xchg_bytes) that every other rank of the node maps through CUDA IPC.  K2's first CTA
+ * (mcaq_morph_fused_xchg) stores this rank's [min, -max] into every rank's buffer and releases the
+ * step number; K3 (mcaq_tile_quantize_xchg) acquires the flags and takes the minimum over ranks
+ * while it builds its scale / zero-point rows.  No collective launch, no host synchronisation.
+ */
+MCAQ_API long long mcaq_xchg_bytes(int C, int world);
+MCAQ_API int mcaq_xchg_alloc(long long bytes, void** out);           /* cudaMalloc + zero */
+MCAQ_API int mcaq_xchg_free(void* p);
+MCAQ_API int mcaq_xchg_export(void* p, void* handle64);              /* cudaIpcGetMemHandle */
+MCAQ_API int mcaq_xchg_open(const void* handle64, void** out);       /* cudaIpcOpenMemHandle */
+MCAQ_API int mcaq_xchg_close(void* p);
+/* stand-alone halves of the protocol (tests, host-driven use): publish `packed` as this rank's
+ * next step / wait for all ranks and write the merged vector */
+MCAQ_API int mcaq_xchg_publish(void* const* peers, int rank, int world, const float* packed, int C, void* stream);
+MCAQ_API int mcaq_xchg_merge(const void* local, int world, int C, float* packed, void* stream);
+
+MCAQ_API int mcaq_morph_fused_xchg(const float* sum_plane, const float* abs_plane, int B, int C, int H, int W,
+                                   int grid_size, int32_t* keys, float* packed_ranges, const float* cmlp,
+                                   const float* mapper, int linear_mapper, const float* softmask,
+                                   float temperature, int use_temperature, int continuous, float min_bits,
+                                   float max_bits, float eps_spread, float* phi, float* complexity,
+                                   float* bit_map, float* mask, void* const* xchg_peers, int xchg_rank,
+                                   int xchg_world, void* stream);
+
+MCAQ_API int mcaq_tile_quantize_xchg(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                                     const float* bit_map, int Ht, int Wt, const void* xchg_local, int world,
+                                     float* qtable_ws, float* packed_ws, const float* mask, void* stream);
+
 /* phi -> complexity (MLP + LayerNorm + sigmoid, 5x5 bilateral, clamp)  morphology.py:959-968 */
 MCAQ_API int mcaq_complexity(const float* phi, int B, int ht, int wt, const float* cmlp, const float* consts,
                     float* complexity_raw /* nullable */, float* complexity, void* stream);
@@ -170,8 +202,8 @@ MCAQ_API int mcaq_selftest_division(const float* scales, int nscales, unsigned f
 /* debug: device buffer of 16 clock64() stamps per image written by mcaq_morph_phi (NULL disables) */
 MCAQ_API void mcaq_debug_stage_clocks(long long* dev_buf);
 
-/* debug / tuning: force the number of CTAs (cluster size 1, 2 or 4) an image is split over in the
- * morphology kernel; 0 = automatic */
+/* debug / tuning: force the number of CTAs (cluster size 1, 2, 4 or 8) an image is split over in
+ * the morphology kernel; 0 = automatic */
 MCAQ_API void mcaq_debug_cluster_split(int ns);
 
 /* tile size rule of the analyzer (morphology.py:359-376) */

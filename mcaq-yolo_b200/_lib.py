@@ -1,7 +1,7 @@
 """ctypes binding of libmcaq_b200.so (declared in include/mcaq_b200.h)."""
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_uint, c_ulonglong, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_uint, c_ulonglong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libmcaq_b200.so")
@@ -43,6 +43,20 @@ PROTOTYPES = {
                                 c_void_p]),
     "mcaq_bit_mapper": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_int, c_int,
                                 c_float, c_float, c_float, c_void_p, c_void_p]),
+    "mcaq_xchg_bytes": (c_longlong, [c_int, c_int]),
+    "mcaq_xchg_alloc": (c_int, [c_longlong, POINTER(c_void_p)]),
+    "mcaq_xchg_free": (c_int, [c_void_p]),
+    "mcaq_xchg_export": (c_int, [c_void_p, c_void_p]),
+    "mcaq_xchg_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "mcaq_xchg_close": (c_int, [c_void_p]),
+    "mcaq_xchg_publish": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mcaq_xchg_merge": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mcaq_morph_fused_xchg": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_float, c_float,
+                                      c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                      c_void_p]),
+    "mcaq_tile_quantize_xchg": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                        c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcaq_soft_mask": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p]),
 }
@@ -67,6 +81,8 @@ def load():
             fn = getattr(lib, name)          # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("MCAQ_K2_SPLIT"):        # tuning aid: force the morphology kernel's cluster split
+            lib.mcaq_debug_cluster_split(int(os.environ["MCAQ_K2_SPLIT"]))
         _lib = lib
     return _lib
 

@@ -34,6 +34,7 @@
 // fp64-rounded literals; Otsu sums are exact in fp64.
 #include <cooperative_groups.h>
 
+#include "peer_exchange.cuh"
 #include "tile_nets.cuh"
 
 namespace cg = cooperative_groups;
@@ -59,6 +60,7 @@ struct FusedArgs {
   const float* abs_plane;      // for the soft mask (NULL: no mask stage)
   int* keys;                   // K1 range keys: decoded into `packed` and re-armed by CTA 0 (NULL: skip)
   float* packed;
+  XchgPeers px;                // world > 1: CTA 0 also publishes `packed` to every rank (peer_exchange.cuh)
   const float* cmlp;           // NULL: stop after phi
   const float* mapper;         // packed MLP mapper, or NULL with linear_mapper != 0
   const float* softmask;
@@ -489,7 +491,10 @@ __device__ __forceinline__ void task_hysteresis(const Ctx& c, int R0, int lane) 
   }
 }
 
-__global__ void __launch_bounds__(MORPH_MAX_THREADS, 2)
+// 64 registers per thread (4 CTAs of 256 threads fit the register file): the kernel is issue / latency
+// bound, so resident CTAs of other images, scales and steps -- and the HBM-bound K1 / K3 CTAs --
+// fill its idle issue slots
+__global__ void __launch_bounds__(MORPH_MAX_THREADS, 4)
 morph_fused_kernel(const FusedArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const MorphGeom& g = A.g;
@@ -497,7 +502,7 @@ morph_fused_kernel(const FusedArgs A) {
   const int NW = g.Hc * g.WW;
   float* G = S;
   float* BL = S + g.off_bl;
-  float* MAG = S + g.off_mag;
+  float* MAG = S;                                              // aliases G (dead after T1)
   uint32_t* BIN = reinterpret_cast<uint32_t*>(S + g.off_bits);
   uint32_t* DIR0 = BIN + NW;
   uint32_t* DIR1 = DIR0 + NW;
@@ -518,10 +523,12 @@ morph_fused_kernel(const FusedArgs A) {
   float* mmx = red + 64;                                       // [16] per-rank min / max
   float* lutn = mmx + 16;                                      // [260] log(N + 1)
   float* lutp = lutn + 260;                                    // [tile^2 + 1 (+pad)] log2(k / tile^2 + 1e-10)
-  float* wts = S + g.off_w;                                    // CMLP | MAPPER | SOFTMASK parameter blocks
-  float* w_cmlp = wts;
-  float* w_map = wts + CMLP_SMEM_FLOATS;
-  float* w_sm = w_map + MAPPER_SMEM_FLOATS;
+  // the three parameter blocks (31 KB) are read through L1 (__ldg-style coalesced loads) where they
+  // are used: every CTA of every image shares the same lines, and shared memory stays free for a
+  // second resident CTA
+  const float* w_cmlp = A.cmlp;
+  const float* w_map = A.mapper;
+  float* w_sm = lutn;                                          // soft-mask block (196 floats) staged over the dead LUT
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NT = blockDim.x, nwarps = NT >> 5;
@@ -540,12 +547,6 @@ morph_fused_kernel(const FusedArgs A) {
   STAGE_CLOCK(0);
   if (ns > 1) cl.barrier_arrive();      // paired with the wait before the first DSMEM store
 
-  // parameter blocks: asynchronous 16-byte copies, consumed after the pixel stages
-  if (A.cmlp) {
-    copy_params_async(A.cmlp, w_cmlp, CMLP_SMEM_FLOATS);
-    if (A.mapper) copy_params_async(A.mapper, w_map, MAPPER_SMEM_FLOATS);
-    if (A.softmask) copy_params_async(A.softmask, w_sm, SOFTMASK_SMEM_FLOATS);
-  }
   {
     const float* src = tile == 4 ? kc::LOG2P_4 : (tile == 8 ? kc::LOG2P_8 : (tile == 16 ? kc::LOG2P_16 : kc::LOG2P_32));
     for (int i = tid; i < 257; i += NT) lutn[i] = __ldg(kc::LOGN1 + i);
@@ -559,6 +560,28 @@ morph_fused_kernel(const FusedArgs A) {
       A.packed[g.C + ch] = -key_float(A.keys[g.C + ch]);
       A.keys[ch] = MCAQ_KEY_POS_INF;
       A.keys[g.C + ch] = MCAQ_KEY_NEG_INF;
+    }
+    if (A.px.world > 1) {
+      // multi-GPU: this rank's [min, -max] goes into slot `rank` of every rank's exchange buffer,
+      // then the step number is released system-wide; K3 acquires it (peer_exchange.cuh)
+      int* stepw = reinterpret_cast<int*>(red);
+      if (tid == 0) {
+        int* ep = reinterpret_cast<int*>(A.px.base[A.px.rank]);
+        const int e = *ep + 1;
+        *ep = e;
+        stepw[0] = e;
+      }
+      __syncthreads();
+      const int e = stepw[0];
+      for (int p = 0; p < A.px.world; ++p) {
+        float* dst = A.px.base[p] + XCHG_SLOTS + (long long)((e & 1) * A.px.world + A.px.rank) * 2 * g.C;
+        for (int i = tid; i < 2 * g.C; i += NT) dst[i] = A.packed[i];       // own stores, same thread
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid < A.px.world)
+        st_release_sys(reinterpret_cast<int*>(A.px.base[tid]) + XCHG_FLAGS + 8 * (e & 1) + A.px.rank, e);
+      __syncthreads();               // `red` is reused below
     }
   }
 
@@ -852,8 +875,8 @@ morph_fused_kernel(const FusedArgs A) {
   if (A.bin_dbg)
     for (int i = r_lo * WW + tid; i < r_hi * WW; i += NT) A.bin_dbg[(long long)b * NW + i] = BIN[i];
   if (!A.cmlp) return;                       // last remote access was before the strong / weak sync
-  cp_async_wait_all();
-  __syncthreads();
+  __syncthreads();                           // phi8 complete; lutn / lutp are dead from here on
+  if (A.softmask) copy_params(A.softmask, w_sm, SOFTMASK_SMEM_FLOATS);
   STAGE_CLOCK(8);
 
   // all-gather of a per-tile array: own tiles -> every peer
@@ -930,8 +953,10 @@ extern "C" void mcaq_debug_cluster_split(int ns) { g_force_split = ns; }
 
 static int g_sm_count = 0;
 
-// CTAs per image: tile rows are split over a thread-block cluster (portable size <= 8) so that the
-// launch fills the GPU (two CTAs fit an SM) without shrinking a band below one 8-row run
+// CTAs per image: a single CTA per image costs the least SM time (no halo recomputation, no
+// cluster barriers), so an image is split by tile rows over a thread-block cluster (portable size
+// <= 8) only while the launch would otherwise leave most SMs idle (2 * B * ns <= SM count / 2), and
+// never below one 8-row run per CTA
 static int pick_split(int B, int ht, int tile) {
   if (g_sm_count == 0) {
     int dev = 0;
@@ -943,7 +968,7 @@ static int pick_split(int B, int ht, int tile) {
   if (g_force_split == 1 || g_force_split == 2 || g_force_split == 4 || g_force_split == 8) {
     ns = g_force_split;
   } else {
-    while (ns < 8 && B * ns * 2 <= 2 * g_sm_count && (ht / (ns * 2)) * tile >= 8) ns *= 2;
+    while (ns < 8 && B * ns * 4 <= g_sm_count && (ht / (ns * 2)) * tile >= 8) ns *= 2;
   }
   while (ns > ht) ns >>= 1;
   return ns < 1 ? 1 : ns;
@@ -954,15 +979,14 @@ static long long layout(MorphGeom& g) {
   g.band_max = ((g.ht + g.ns - 1) / g.ns) * g.tile;
   g.max_own = ((g.ht + g.ns - 1) / g.ns) * g.wt;
   // float planes; a partial 8-row run of a stencil task reads at most 7 rows past its plane (results
-  // discarded), which stays inside the following planes / the margin after MAG
-  const long long wG = (long long)(g.band_max + 10) * g.gs;
-  const long long wBL = (long long)(g.band_max + 4) * g.bs;
-  const long long wMAG = (long long)(g.band_max + 2) * g.Wc + 8LL * g.gs;
+  // discarded), which stays inside the following plane / the margin after BL
+  const long long wG = (long long)(g.band_max + 10) * g.gs;      // also holds MAG ((band+2) * Wc) after T1
+  const long long wBL = (long long)(g.band_max + 4) * g.bs + 8LL * g.gs;
   // the same region later holds the per-warp net scratch, bilateral weights, mask classes
   const long long nets = max_i((MORPH_MAX_THREADS / 32) * NET_WARP_SCRATCH, 2 * g.ntiles + 25 * g.max_own);
   g.off_bl = (int)((wG + 3) & ~3LL);
-  g.off_mag = (int)((g.off_bl + wBL + 3) & ~3LL);
-  long long bits0 = (g.off_mag + wMAG + 3) & ~3LL;
+  g.off_mag = 0;
+  long long bits0 = (g.off_bl + wBL + 3) & ~3LL;
   if (bits0 < ((nets + 3) & ~3LL)) bits0 = (nets + 3) & ~3LL;
   g.off_bits = (int)bits0;
   const long long tiles0 = (bits0 + 6LL * g.Hc * g.WW + 3) & ~3LL;
@@ -970,7 +994,7 @@ static long long layout(MorphGeom& g) {
   const long long tw = (long long)g.ntiles * (2 + 8 + 5 + 9) + 512 + 64 + 16 + 260 + g.tile * g.tile + 4;
   const long long w0 = (tiles0 + tw + 3) & ~3LL;
   g.off_w = (int)w0;
-  g.words = (int)(w0 + CMLP_SMEM_FLOATS + MAPPER_SMEM_FLOATS + SOFTMASK_SMEM_FLOATS);
+  g.words = (int)w0;
   return (long long)g.words * 4;
 }
 
@@ -1054,6 +1078,18 @@ extern "C" int mcaq_morph_fused(const float* sum_plane, const float* abs_plane, 
                                 float temperature, int use_temperature, int continuous, float min_bits,
                                 float max_bits, float eps_spread, float* phi, float* complexity,
                                 float* bit_map, float* mask, void* stream) {
+  return mcaq_morph_fused_xchg(sum_plane, abs_plane, B, C, H, W, grid_size, keys, packed_ranges, cmlp, mapper,
+                               linear_mapper, softmask, temperature, use_temperature, continuous, min_bits,
+                               max_bits, eps_spread, phi, complexity, bit_map, mask, nullptr, 0, 1, stream);
+}
+
+extern "C" int mcaq_morph_fused_xchg(const float* sum_plane, const float* abs_plane, int B, int C, int H, int W,
+                                     int grid_size, int32_t* keys, float* packed_ranges, const float* cmlp,
+                                     const float* mapper, int linear_mapper, const float* softmask,
+                                     float temperature, int use_temperature, int continuous, float min_bits,
+                                     float max_bits, float eps_spread, float* phi, float* complexity,
+                                     float* bit_map, float* mask, void* const* xchg_peers, int xchg_rank,
+                                     int xchg_world, void* stream) {
   if (!sum_plane || !cmlp || !complexity || !bit_map || B <= 0 || C <= 0 || H <= 0 || W <= 0 || grid_size <= 0)
     return MCAQ_EINVAL;
   if (!mapper && !linear_mapper) return MCAQ_EINVAL;
@@ -1066,6 +1102,16 @@ extern "C" int mcaq_morph_fused(const float* sum_plane, const float* abs_plane, 
   const int threads = pick_threads(A.g);
   A.sum_plane = sum_plane; A.abs_plane = abs_plane;
   A.keys = keys; A.packed = packed_ranges;
+  if (xchg_world > 1) {
+    if (!keys || !xchg_peers || xchg_world > XCHG_MAX_RANKS || xchg_rank < 0 || xchg_rank >= xchg_world)
+      return MCAQ_EINVAL;
+    for (int i = 0; i < xchg_world; ++i) {
+      if (!xchg_peers[i]) return MCAQ_EINVAL;
+      A.px.base[i] = reinterpret_cast<float*>(xchg_peers[i]);
+    }
+    A.px.rank = xchg_rank;
+    A.px.world = xchg_world;
+  }
   A.cmlp = cmlp; A.mapper = mapper; A.softmask = softmask;
   A.run_mapper = 1; A.linear_mapper = linear_mapper; A.use_t = use_temperature; A.continuous = continuous;
   A.temperature = temperature; A.lo = min_bits; A.hi = max_bits; A.eps_spread = eps_spread;

@@ -1,0 +1,61 @@
+// Per-channel range exchange between the GPUs of one node over peer memory (NVLink / NVSwitch).
+//
+// The batch is sharded over R ranks (one process per GPU); the only value the inference path has
+// to merge is the per-channel [min, -max] vector (2C floats).  Instead of a collective
+// launch between K2 and K3, the exchange is folded into the two kernels:
+//   * K2's first CTA stores this rank's vector into slot `rank` of EVERY rank's exchange buffer
+//     (plain stores through the peer mapping), fences, then publishes the step number in every
+//     rank's flag word with a system-scope release store;
+//   * every K3 CTA acquires the R flag words of its LOCAL buffer (spins until all carry the current
+//     step) and takes the minimum over the R slots while it builds its {scale, zero_point} rows.
+// Slots and flags are double buffered by step parity: a rank can run at most one step ahead of a
+// peer (its next K3 waits for the peer's next K2), so a slot is never overwritten while it can
+// still be read.  No host involvement, no extra launch, capturable in a CUDA graph.
+//
+// Buffer layout (4-byte words):  [0] step counter of the owning rank   [16 + 8*par + q] flag of
+// rank q   [32 + ((par*R + q) * 2C) ...] slot of rank q, par = step & 1.
+#pragma once
+#include "common.cuh"
+
+namespace mcaq {
+
+constexpr int XCHG_MAX_RANKS = 8;
+constexpr int XCHG_FLAGS = 16;
+constexpr int XCHG_SLOTS = 32;
+
+struct XchgPeers {
+  float* base[XCHG_MAX_RANKS];   // exchange buffer of every rank (own entry = local memory)
+  int rank, world;
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// current step of the local buffer (written by this rank's K2 earlier in stream order)
+__device__ __forceinline__ int xchg_step(const float* local) {
+  return *reinterpret_cast<const volatile int*>(local);
+}
+
+// thread q < world spins until rank q has published step e in the local buffer
+__device__ __forceinline__ void xchg_wait(const float* local, int world, int e, int q) {
+  if (q < world) {
+    const int* f = reinterpret_cast<const int*>(local) + XCHG_FLAGS + 8 * (e & 1) + q;
+    while (ld_acquire_sys(f) != e) __nanosleep(64);
+  }
+}
+
+// min over ranks of element idx (< 2C) of the step-e slots of the local buffer
+__device__ __forceinline__ float xchg_min(const float* local, int world, int C2, int e, int idx) {
+  const volatile float* s = local + XCHG_SLOTS + (long long)((e & 1) * world) * C2 + idx;
+  float m = s[0];
+  for (int q = 1; q < world; ++q) m = fminf(m, s[(long long)q * C2]);
+  return m;
+}
+
+}  // namespace mcaq

@@ -12,15 +12,12 @@ complexity_kernel(const float* __restrict__ phi, int ht, int wt, const float* __
                   float* __restrict__ raw_out, float* __restrict__ out) {
   extern __shared__ __align__(16) float sm[];
   const int ntiles = ht * wt;
-  float* w = sm;                                        // CMLP_SMEM_FLOATS
-  float* scratch = w + CMLP_SMEM_FLOATS;                // max(TN_WARPS * NET_WARP_SCRATCH, 25 * ntiles)
+  float* scratch = sm;                                  // max(TN_WARPS * NET_WARP_SCRATCH, 25 * ntiles)
   const int nscr = TN_WARPS * NET_WARP_SCRATCH > 25 * ntiles ? TN_WARPS * NET_WARP_SCRATCH : 25 * ntiles;
   float* craw = scratch + ((nscr + 3) & ~3);
   float* cfin = craw + ntiles;
   const int b = blockIdx.x;
-  copy_params(cmlp, w, CMLP_SMEM_FLOATS);
-  __syncthreads();
-  complexity_mlp_warps(phi + (long long)b * ntiles * 8, 0, ntiles, w, scratch, craw,
+  complexity_mlp_warps(phi + (long long)b * ntiles * 8, 0, ntiles, cmlp, scratch, craw,
                        raw_out ? raw_out + (long long)b * ntiles : nullptr);
   __syncthreads();
   bilateral_range(craw, ht, wt, 0, ntiles, scratch, cfin, out + (long long)b * ntiles);
@@ -30,13 +27,10 @@ __global__ void __launch_bounds__(TN_THREADS)
 mapper_mlp_kernel(const float* __restrict__ cmap, int ntiles, const float* __restrict__ mp, float temperature,
                   int use_t, int continuous, float lo, float hi, float* __restrict__ out) {
   extern __shared__ __align__(16) float sm[];
-  float* w = sm;
-  float* scratch = w + MAPPER_SMEM_FLOATS;              // TN_WARPS * NET_WARP_SCRATCH
+  float* scratch = sm;                                  // TN_WARPS * NET_WARP_SCRATCH
   float* bits_s = scratch + TN_WARPS * NET_WARP_SCRATCH;
   const int b = blockIdx.x;
-  copy_params(mp, w, MAPPER_SMEM_FLOATS);
-  __syncthreads();
-  mapper_mlp_warps(cmap + (long long)b * ntiles, 0, ntiles, w, scratch, temperature, use_t, continuous, lo, hi,
+  mapper_mlp_warps(cmap + (long long)b * ntiles, 0, ntiles, mp, scratch, temperature, use_t, continuous, lo, hi,
                    bits_s, out + (long long)b * ntiles);
 }
 
@@ -89,7 +83,7 @@ extern "C" int mcaq_complexity(const float* phi, int B, int ht, int wt, const fl
   if (!phi || !cmlp || !complexity || B <= 0 || ht <= 0 || wt <= 0) return MCAQ_EINVAL;
   const int nt_ = ht * wt;
   const int nscr = TN_WARPS * NET_WARP_SCRATCH > 25 * nt_ ? TN_WARPS * NET_WARP_SCRATCH : 25 * nt_;
-  const size_t smem = (size_t)(CMLP_SMEM_FLOATS + ((nscr + 3) & ~3) + 2 * nt_) * 4;
+  const size_t smem = (size_t)(((nscr + 3) & ~3) + 2 * nt_) * 4;
   if ((uintptr_t)cmlp & 15) return MCAQ_EALIGN;
   if (smem > 200 * 1024) return MCAQ_ETOOBIG;
   if (smem > 48 * 1024) cudaFuncSetAttribute(complexity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -105,7 +99,7 @@ extern "C" int mcaq_bit_mapper(const float* complexity, int B, int ht, int wt, c
   const int ntiles = ht * wt;
   cudaStream_t st = (cudaStream_t)stream;
   if (mapper) {
-    const size_t smem = (size_t)(MAPPER_SMEM_FLOATS + TN_WARPS * NET_WARP_SCRATCH + ntiles) * 4;
+    const size_t smem = (size_t)(TN_WARPS * NET_WARP_SCRATCH + ntiles) * 4;
     if ((uintptr_t)mapper & 15) return MCAQ_EALIGN;
     if (smem > 200 * 1024) return MCAQ_ETOOBIG;
     if (smem > 48 * 1024) cudaFuncSetAttribute(mapper_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

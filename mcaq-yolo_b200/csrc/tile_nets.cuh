@@ -6,8 +6,8 @@
 // layers (lane = output unit, activations in a per-warp shared-memory scratch read back as
 // broadcast LDS.128), so there is no CTA barrier between layers and the NET_TT independent FMA
 // chains hide each other's latency.  Parameter blocks arrive in the layout the host packs
-// (mcaq_yolo_b200/constants.py: weights transposed to [k][unit], BatchNorm folded), so staging
-// them into shared memory is a straight 16-byte copy.
+// (mcaq_yolo_b200/constants.py: weights transposed to [k][unit], BatchNorm folded) and are read
+// in place through L1 (coalesced per-lane loads; every CTA shares the same 30 KB).
 //
 // Arithmetic = oracle/mcaq_oracle.py: nn.Linear / conv = FMA chain over k from 0, bias last;
 // LayerNorm statistics = 32-lane xor-butterfly tree (element k and k+32 pre-added for D = 64);
@@ -77,14 +77,14 @@ __device__ __forceinline__ float ln32_relu(float a0, float g, float be) {
 // out[j] (+)= sum_k act[j][k] * Wt[k][unit]: FMA chain over k from 0 for NET_TT tiles at once.
 // act rows are 16-byte aligned shared memory (broadcast LDS.128), Wt column reads are conflict-free.
 template <int K_IN, int N_OUT>
-__device__ __forceinline__ void dense_warp(const float* act, int act_stride, const float* Wt, int unit,
+__device__ __forceinline__ void dense_warp(const float* act, int act_stride, const float* __restrict__ Wt, int unit,
                                            float (&acc)[NET_TT]) {
 #pragma unroll
   for (int j = 0; j < NET_TT; ++j) acc[j] = 0.f;
 #pragma unroll 4
   for (int k4 = 0; k4 < K_IN / 4; ++k4) {
-    const float w0 = Wt[(4 * k4 + 0) * N_OUT + unit], w1 = Wt[(4 * k4 + 1) * N_OUT + unit];
-    const float w2 = Wt[(4 * k4 + 2) * N_OUT + unit], w3 = Wt[(4 * k4 + 3) * N_OUT + unit];
+    const float w0 = __ldg(Wt + (4 * k4 + 0) * N_OUT + unit), w1 = __ldg(Wt + (4 * k4 + 1) * N_OUT + unit);
+    const float w2 = __ldg(Wt + (4 * k4 + 2) * N_OUT + unit), w3 = __ldg(Wt + (4 * k4 + 3) * N_OUT + unit);
 #pragma unroll
     for (int j = 0; j < NET_TT; ++j) {
       const float4 a = *reinterpret_cast<const float4*>(act + j * act_stride + 4 * k4);
@@ -99,11 +99,13 @@ __device__ __forceinline__ void dense_warp(const float* act, int act_stride, con
 // ---------------------------------------------------------------------------------------------
 // complexity MLP 8 -> 64 (LN, ReLU) -> 32 (LN, ReLU) -> 1, sigmoid  (morphology.py:81-97)
 // craw[t] for t in [t_lo, t_hi).  phi: [ntiles][8] floats, 16-byte aligned rows (shared or global);
-// w: CMLP block in shared memory; scratch: NET_WARP_SCRATCH floats per warp.  Warp-level only: the
+// w: CMLP block in GLOBAL memory (read through L1, shared by every CTA); scratch: NET_WARP_SCRATCH
+// floats of shared memory per warp.  Warp-level only: the
 // caller synchronises the CTA before anyone reads craw.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo, int t_hi, const float* w,
-                                                     float* scratch_all, float* craw, float* __restrict__ raw_out) {
+__device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo, int t_hi,
+                                                     const float* __restrict__ w, float* scratch_all, float* craw,
+                                                     float* __restrict__ raw_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const float* W0t = w;
   const float* b0 = w + 512;
@@ -114,7 +116,7 @@ __device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo,
   const float* g4 = w + 2784;
   const float* be4 = w + 2816;
   const float* W6 = w + 2848;
-  const float b6 = w[2880];
+  const float b6 = __ldg(w + 2880);
   float* h1 = scratch_all + warp * NET_WARP_SCRATCH;      // [TT][64]
   float* h2 = h1 + NET_TT * 64;                           // [TT][32]
   for (int tg = t_lo + warp * NET_TT; tg < t_hi; tg += nwarps * NET_TT) {
@@ -130,7 +132,7 @@ __device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo,
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float w0 = W0t[k * 64 + lane], w1 = W0t[k * 64 + 32 + lane];
+      const float w0 = __ldg(W0t + k * 64 + lane), w1 = __ldg(W0t + k * 64 + 32 + lane);
 #pragma unroll
       for (int j = 0; j < NET_TT; ++j) {
         const float p = k == 0 ? pa[j].x : k == 1 ? pa[j].y : k == 2 ? pa[j].z : k == 3 ? pa[j].w
@@ -140,8 +142,8 @@ __device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo,
       }
     }
     {
-      const float bb0 = b0[lane], bb1 = b0[lane + 32];
-      const float gg0 = g1[lane], gg1 = g1[lane + 32], ee0 = be1[lane], ee1 = be1[lane + 32];
+      const float bb0 = __ldg(b0 + lane), bb1 = __ldg(b0 + lane + 32);
+      const float gg0 = __ldg(g1 + lane), gg1 = __ldg(g1 + lane + 32), ee0 = __ldg(be1 + lane), ee1 = __ldg(be1 + lane + 32);
 #pragma unroll
       for (int j = 0; j < NET_TT; ++j) {
         a0[j] = __fadd_rn(a0[j], bb0);
@@ -155,7 +157,7 @@ __device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo,
     float acc[NET_TT];
     dense_warp<64, 32>(h1, 64, W3t, lane, acc);
     {
-      const float bb = b3[lane], gg = g4[lane], ee = be4[lane];
+      const float bb = __ldg(b3 + lane), gg = __ldg(g4 + lane), ee = __ldg(be4 + lane);
 #pragma unroll
       for (int j = 0; j < NET_TT; ++j) h2[j * 32 + lane] = ln32_relu(__fadd_rn(acc[j], bb), gg, ee);
     }
@@ -165,7 +167,7 @@ __device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo,
 #pragma unroll
       for (int k4 = 0; k4 < 8; ++k4) {
         const float4 a = *reinterpret_cast<const float4*>(h2 + lane * 32 + 4 * k4);
-        const float4 ww = *reinterpret_cast<const float4*>(W6 + 4 * k4);
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(W6 + 4 * k4));
         z = fmaf(a.x, ww.x, z); z = fmaf(a.y, ww.y, z); z = fmaf(a.z, ww.z, z); z = fmaf(a.w, ww.w, z);
       }
       const float c = sigmoid_exact(__fadd_rn(z, b6));
@@ -230,7 +232,7 @@ __device__ __forceinline__ float finish_bits(float bits, float temperature, int 
 
 // ComplexityToBitMappingNetwork (bit_allocation.py:218-280, eval BN folded): bits_s[t] for t in
 // [t_lo, t_hi); cmap indexed by absolute tile.  Warp-level only, like complexity_mlp_warps.
-__device__ __forceinline__ void mapper_mlp_warps(const float* cmap, int t_lo, int t_hi, const float* w,
+__device__ __forceinline__ void mapper_mlp_warps(const float* cmap, int t_lo, int t_hi, const float* __restrict__ w,
                                                  float* scratch_all, float temperature, int use_t, int continuous,
                                                  float lo, float hi, float* bits_s, float* __restrict__ out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -252,8 +254,8 @@ __device__ __forceinline__ void mapper_mlp_warps(const float* cmap, int t_lo, in
     }
     __syncwarp();
     {                                                     // 3 -> 32, BN, ReLU
-      const float w0 = W0t[lane], w1 = W0t[32 + lane], w2 = W0t[64 + lane];
-      const float bb = v0[lane], al = v0[32 + lane], be = v0[64 + lane];
+      const float w0 = __ldg(W0t + lane), w1 = __ldg(W0t + 32 + lane), w2 = __ldg(W0t + 64 + lane);
+      const float bb = __ldg(v0 + lane), al = __ldg(v0 + 32 + lane), be = __ldg(v0 + 64 + lane);
 #pragma unroll
       for (int j = 0; j < NET_TT; ++j) {
         const float4 z = *reinterpret_cast<const float4*>(zin + j * 4);
@@ -269,8 +271,8 @@ __device__ __forceinline__ void mapper_mlp_warps(const float* cmap, int t_lo, in
       float acc0[NET_TT], acc1[NET_TT];
       dense_warp<32, 64>(g0, 32, W3t, lane, acc0);
       dense_warp<32, 64>(g0, 32, W3t, lane + 32, acc1);
-      const float b_0 = v3[lane], a_0 = v3[64 + lane], e_0 = v3[128 + lane];
-      const float b_1 = v3[32 + lane], a_1 = v3[96 + lane], e_1 = v3[160 + lane];
+      const float b_0 = __ldg(v3 + lane), a_0 = __ldg(v3 + 64 + lane), e_0 = __ldg(v3 + 128 + lane);
+      const float b_1 = __ldg(v3 + 32 + lane), a_1 = __ldg(v3 + 96 + lane), e_1 = __ldg(v3 + 160 + lane);
 #pragma unroll
       for (int j = 0; j < NET_TT; ++j) {
         g1[j * 64 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(acc0[j], b_0), a_0), e_0), 0.f);
@@ -281,7 +283,7 @@ __device__ __forceinline__ void mapper_mlp_warps(const float* cmap, int t_lo, in
     {                                                     // 64 -> 32, BN, ReLU
       float acc[NET_TT];
       dense_warp<64, 32>(g1, 64, W6t, lane, acc);
-      const float bb = v6[lane], al = v6[32 + lane], be = v6[64 + lane];
+      const float bb = __ldg(v6 + lane), al = __ldg(v6 + 32 + lane), be = __ldg(v6 + 64 + lane);
 #pragma unroll
       for (int j = 0; j < NET_TT; ++j)
         g2[j * 32 + lane] = fmaxf(__fadd_rn(__fmul_rn(__fadd_rn(acc[j], bb), al), be), 0.f);
@@ -292,10 +294,10 @@ __device__ __forceinline__ void mapper_mlp_warps(const float* cmap, int t_lo, in
 #pragma unroll
       for (int k4 = 0; k4 < 8; ++k4) {
         const float4 a = *reinterpret_cast<const float4*>(g2 + lane * 32 + 4 * k4);
-        const float4 ww = *reinterpret_cast<const float4*>(W9 + 4 * k4);
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(W9 + 4 * k4));
         acc = fmaf(a.x, ww.x, acc); acc = fmaf(a.y, ww.y, acc); acc = fmaf(a.z, ww.z, acc); acc = fmaf(a.w, ww.w, acc);
       }
-      const float s = sigmoid_exact(__fadd_rn(acc, W9[32]));
+      const float s = sigmoid_exact(__fadd_rn(acc, __ldg(W9 + 32)));
       const float bits = finish_bits(__fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), s)), temperature, use_t,
                                      continuous, lo, hi);
       bits_s[tg + lane] = bits;

@@ -67,8 +67,10 @@ class ScaleWorkspace:
 
 
 def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, temperature, ws: ScaleWorkspace | None,
-                        layer: int = -1) -> dict:
-    """Eval-mode hook body for one scale in three launches.  Returns the aux record."""
+                        layer: int = -1, xchg=None) -> dict:
+    """Eval-mode hook body for one scale in three launches.  Returns the aux record.
+    xchg: a peer.RangeExchange when the batch is sharded over the GPUs of a node -- the range merge
+    then happens inside K2 / K3 over peer memory instead of a collective between them."""
     B, C, H, W = feat.shape
     x = feat if feat.is_contiguous() else feat.contiguous()
     frozen = quantizer._is_frozen() and quantizer.running_min is not None
@@ -88,9 +90,12 @@ def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, tempera
                         None if linear else K.pack_mapping_network(mapper.mapping_network),
                         None if sm is None else K.pack_soft_mask(sm),
                         temperature, False, ws.keys if need_ranges else None,
-                        mapper.min_bits, mapper.max_bits, getattr(mapper, "eps_spread", 1e-3))
+                        mapper.min_bits, mapper.max_bits, getattr(mapper, "eps_spread", 1e-3),
+                        xchg=xchg if need_ranges else None)
     if frozen:
         y = ops.tile_quantize_ranges(x, r["bit_map"], None, quantizer.running_min, quantizer.running_max, r["mask"])
+    elif xchg is not None and xchg.world > 1:
+        y = ops.tile_quantize_ranges(x, r["bit_map"], r["packed"], None, None, r["mask"], xchg=xchg)
     else:
         packed = r["packed"]
         if sync:
@@ -144,12 +149,15 @@ class FusedHotPath:
     """The three hooks of one forward as a stand-alone object (bench.py, serving without the model
     wrapper): `run(feats)` takes the C3/C4/C5 maps and returns the aux records."""
 
-    def __init__(self, analyzer, mapper, quantizers, temperature: float = 1.0, streams: bool = True):
+    def __init__(self, analyzer, mapper, quantizers, temperature: float = 1.0, streams: bool = True,
+                 exchanges=None):
         self.analyzer, self.mapper, self.quantizers = analyzer, mapper, list(quantizers)
         self.temperature = temperature
         self.ws = [None] * len(self.quantizers)
         self.use_streams = streams
         self.side = None
+        # one peer.RangeExchange per scale when the batch is sharded over the GPUs of a node
+        self.xchg = list(exchanges) if exchanges is not None else [None] * len(self.quantizers)
 
     @torch.no_grad()
     def run(self, feats):
@@ -158,7 +166,7 @@ class FusedHotPath:
             out = []
             for i, x in enumerate(feats):
                 rec, self.ws[i] = fused_scale_forward(x, self.analyzer, self.mapper, self.quantizers[i],
-                                                      self.temperature, self.ws[i], i)
+                                                      self.temperature, self.ws[i], i, self.xchg[i])
                 out.append(rec)
             return out
         # scales are independent: fork one stream per extra scale so K2's per-image latency of one
@@ -175,12 +183,12 @@ class FusedHotPath:
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 out[i], self.ws[i] = fused_scale_forward(feats[i], self.analyzer, self.mapper, self.quantizers[i],
-                                                         self.temperature, self.ws[i], i)
+                                                         self.temperature, self.ws[i], i, self.xchg[i])
                 ev = torch.cuda.Event()
                 ev.record(st)
                 joins.append(ev)
         out[0], self.ws[0] = fused_scale_forward(feats[0], self.analyzer, self.mapper, self.quantizers[0],
-                                                 self.temperature, self.ws[0], 0)
+                                                 self.temperature, self.ws[0], 0, self.xchg[0])
         for ev in joins:
             cur.wait_event(ev)
         if not torch.cuda.is_current_stream_capturing():

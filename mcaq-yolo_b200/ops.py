@@ -281,7 +281,7 @@ def morph_fused(sum_plane: torch.Tensor, abs_plane: torch.Tensor | None, C: int,
                 cmlp: torch.Tensor, mapper: torch.Tensor | None, softmask: torch.Tensor | None,
                 temperature, continuous: bool = False, keys: torch.Tensor | None = None,
                 min_bits: float = 2.0, max_bits: float = 8.0, eps_spread: float = 1e-3,
-                want_phi: bool = False):
+                want_phi: bool = False, xchg=None):
     """K2 in one launch: phi -> complexity -> bit map -> soft mask (include/mcaq_b200.h
     mcaq_morph_fused).  mapper=None selects the linear mapper.  Returns a dict with
     complexity (B,ht,wt), bit_map (B,ht,wt), mask (B,H,W) or None, packed ranges or None, phi or None."""
@@ -297,17 +297,24 @@ def morph_fused(sum_plane: torch.Tensor, abs_plane: torch.Tensor | None, C: int,
     packed = torch.empty((2 * C,), device=dev, dtype=torch.float32) if keys is not None else None
     use_t = temperature is not None
     t = max(float(temperature), 0.1) if use_t else 1.0
-    _call("mcaq_morph_fused", sum_plane.data_ptr(), _ptr(abs_plane), B, int(C), H, W, int(grid_size), _ptr(keys),
-          _ptr(packed), cmlp.data_ptr(), _ptr(mapper), int(mapper is None), _ptr(softmask), t, int(use_t),
-          int(continuous), float(min_bits), float(max_bits), float(eps_spread), _ptr(phi), cpx.data_ptr(),
-          bits.data_ptr(), _ptr(mask), _stream())
+    args = (sum_plane.data_ptr(), _ptr(abs_plane), B, int(C), H, W, int(grid_size), _ptr(keys),
+            _ptr(packed), cmlp.data_ptr(), _ptr(mapper), int(mapper is None), _ptr(softmask), t, int(use_t),
+            int(continuous), float(min_bits), float(max_bits), float(eps_spread), _ptr(phi), cpx.data_ptr(),
+            bits.data_ptr(), _ptr(mask))
+    if xchg is not None and xchg.world > 1:
+        # multi-GPU: the first CTA also publishes this rank's ranges to every rank (peer.RangeExchange)
+        import ctypes
+        _call("mcaq_morph_fused_xchg", *args, ctypes.addressof(xchg.peers), xchg.rank, xchg.world, _stream())
+    else:
+        _call("mcaq_morph_fused", *args, _stream())
     return {"complexity": cpx, "bit_map": bits, "mask": mask, "packed": packed, "phi": phi}
 
 
 def tile_quantize_ranges(x: torch.Tensor, bit_map: torch.Tensor, packed: torch.Tensor | None = None,
                          running_min: torch.Tensor | None = None, running_max: torch.Tensor | None = None,
-                         mask: torch.Tensor | None = None, out: torch.Tensor | None = None):
-    """K3 with the per-channel ranges given directly (no table kernel)."""
+                         mask: torch.Tensor | None = None, out: torch.Tensor | None = None, xchg=None):
+    """K3 with the per-channel ranges given directly (no table kernel).  With `xchg` (a
+    peer.RangeExchange of world > 1) the ranges are the minimum over the ranks' published vectors."""
     _need_cuda(x, bit_map, packed, running_min, running_max, mask)
     x = x if x.is_contiguous() else x.contiguous()
     B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
@@ -319,6 +326,11 @@ def tile_quantize_ranges(x: torch.Tensor, bit_map: torch.Tensor, packed: torch.T
     vec = 4 if x.dtype == torch.float32 else 8
     needs_ws = not ((H * W) % vec == 0 and W % 4 == 0 and W % Wt == 0 and (W // Wt) % 4 == 0)
     ws = torch.empty((7, C, 2), device=x.device, dtype=torch.float32) if needs_ws else None
+    if xchg is not None and xchg.world > 1:
+        pws = torch.empty((2 * C,), device=x.device, dtype=torch.float32) if needs_ws else None
+        _call("mcaq_tile_quantize_xchg", x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W, bit_map.data_ptr(),
+              Ht, Wt, xchg.local, xchg.world, _ptr(ws), _ptr(pws), _ptr(mask), _stream())
+        return y
     _call("mcaq_tile_quantize_ranges", x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W, bit_map.data_ptr(),
           Ht, Wt, _ptr(packed), _ptr(running_min), _ptr(running_max), _ptr(ws), _ptr(mask), _stream())
     return y

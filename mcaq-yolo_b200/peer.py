@@ -1,0 +1,88 @@
+"""Per-channel range exchange between the GPUs of one node over peer memory (csrc/peer_exchange.cuh).
+
+One `RangeExchange` per scale and rank: a small device buffer that every other rank of the node maps
+through CUDA IPC.  K2 of each rank stores its `[min, -max]` vector into every rank's buffer and K3
+takes the minimum over ranks, so a batch sharded over R GPUs quantizes with the ranges of the whole
+batch (what the single-process reference computes, quantization.py:423-426, 650-654) without a
+collective launch between the two kernels.  `torch.distributed` is only used once, at construction,
+to swap the 64-byte IPC handles.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+MAX_RANKS = 8
+
+
+class RangeExchange:
+    def __init__(self, C: int, rank: int, world: int, local_ptr: int, peer_ptrs, owner=None):
+        self.C, self.rank, self.world = int(C), int(rank), int(world)
+        self.local = int(local_ptr)
+        self.peers = (ctypes.c_void_p * MAX_RANKS)(*([int(p) for p in peer_ptrs] + [None] * (MAX_RANKS - world)))
+        self._owner = owner            # keeps shared state (virtual ranks) alive
+        self._opened = []
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def _alloc(C: int, world: int) -> int:
+        lib = _lib.load()
+        nbytes = lib.mcaq_xchg_bytes(int(C), int(world))
+        if nbytes <= 0:
+            raise ValueError(f"bad exchange geometry C={C} world={world} (at most {MAX_RANKS} ranks)")
+        out = ctypes.c_void_p()
+        _lib.check(lib.mcaq_xchg_alloc(nbytes, ctypes.byref(out)), "mcaq_xchg_alloc")
+        return int(out.value)
+
+    @classmethod
+    def create(cls, C: int, group=None) -> "RangeExchange":
+        """Collective over `group` (all ranks on ONE node): allocate, swap IPC handles, map peers."""
+        import torch.distributed as dist
+        lib = _lib.load()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        local = cls._alloc(C, world)
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(lib.mcaq_xchg_export(local, handle), "mcaq_xchg_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        ptrs, opened = [], []
+        for r, h in enumerate(handles):
+            if r == rank:
+                ptrs.append(local)
+                continue
+            out = ctypes.c_void_p()
+            _lib.check(lib.mcaq_xchg_open(ctypes.create_string_buffer(h, 64), ctypes.byref(out)), "mcaq_xchg_open")
+            ptrs.append(int(out.value))
+            opened.append(int(out.value))
+        ex = cls(C, rank, world, local, ptrs)
+        ex._opened = opened
+        dist.barrier(group)            # nobody publishes before every rank has mapped every buffer
+        return ex
+
+    @classmethod
+    def virtual(cls, C: int, world: int):
+        """`world` exchange objects inside ONE process on one GPU (all buffers local): lets a
+        single-GPU test drive the protocol with several virtual ranks on one stream."""
+        bufs = [cls._alloc(C, world) for _ in range(world)]
+        return [cls(C, r, world, bufs[r], bufs, owner=bufs) for r in range(world)]
+
+    # ------------------------------------------------------------------ host-driven halves (tests)
+    def publish(self, packed: torch.Tensor):
+        from . import ops
+        ops._call("mcaq_xchg_publish", ctypes.addressof(self.peers), self.rank, self.world, packed.data_ptr(),
+                  self.C, ops._stream())
+
+    def merged(self, device) -> torch.Tensor:
+        from . import ops
+        out = torch.empty((2 * self.C,), device=device, dtype=torch.float32)
+        ops._call("mcaq_xchg_merge", self.local, self.world, self.C, out.data_ptr(), ops._stream())
+        return out
+
+    def close(self):
+        lib = _lib.load()
+        for p in self._opened:
+            lib.mcaq_xchg_close(p)
+        self._opened = []
