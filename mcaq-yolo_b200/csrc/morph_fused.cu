@@ -90,6 +90,11 @@ __device__ __forceinline__ float div_exact(float x, float d, float rinv) {
   return __fdiv_rn(x, d);
 }
 
+// x / C for the channel mean: an exact scaling when C is a power of two (every YOLOv8 width)
+__device__ __forceinline__ float div_channels(float x, float fC, float rC, bool pow2) {
+  return pow2 ? __fmul_rn(x, rC) : div_exact(x, fC, rC);
+}
+
 // direction bin of the NMS (morphology.py:430-444).  Slope tests with a 1e-5 relative guard band
 // decide all but boundary cases; those take the literal atan2f path.
 __device__ __forceinline__ int nms_bin(float gx, float gy) {
@@ -284,18 +289,18 @@ __device__ __forceinline__ void task_lbp_var(const Ctx& c, int ty, int k, int la
   }
   if (valid && (lane & (tile - 1)) == 0) {
     const int t = ty * c.wt + (x >> c.tshift);
-    const float ntile2 = (float)(tile * tile);
+    const float rtile2 = 1.0f / (float)(tile * tile);        // tile^2 is a power of two: x * rtile2 == x / tile^2
     float ent = 0.f;
 #pragma unroll
     for (int kk = 0; kk < 10; ++kk) {
       const int n = (h[kk >> 1] >> (16 * (kk & 1))) & 0xffff;
       if (lbp_dbg) lbp_dbg[t * 10 + kk] = n;
-      const float pr = __fdiv_rn((float)n, ntile2);
+      const float pr = __fmul_rn((float)n, rtile2);
       ent = __fadd_rn(ent, __fmul_rn(pr, lutp[n]));                // log2(p + 1e-10)
     }
     phis[t * 2 + 0] = __fdiv_rn(-ent, kc::LOG2_10);
-    const float mx_ = __fdiv_rn(s0, ntile2), mx2 = __fdiv_rn(s1, ntile2);
-    const float my_ = __fdiv_rn(s2, ntile2), my2 = __fdiv_rn(s3, ntile2);
+    const float mx_ = __fmul_rn(s0, rtile2), mx2 = __fmul_rn(s1, rtile2);
+    const float my_ = __fmul_rn(s2, rtile2), my2 = __fmul_rn(s3, rtile2);
     const float vx = fmaxf(__fsub_rn(mx2, __fmul_rn(mx_, mx_)), 0.f);
     const float vy = fmaxf(__fsub_rn(my2, __fmul_rn(my_, my_)), 0.f);
     const float v = __fadd_rn(vx, vy);
@@ -306,7 +311,7 @@ __device__ __forceinline__ void task_lbp_var(const Ctx& c, int ty, int k, int la
 // ---- T1d: tile activity of the soft mask (quantization.py:224-226) for tile row ty under word k when
 //      the adaptive-pool windows are the analyzer's tiles: mean over the tile of sum_c|x| / C.
 __device__ __forceinline__ void task_act(const Ctx& c, const float* __restrict__ ap, int W, float fC, float rC,
-                                         int ty, int k, int lane, float* act) {
+                                         bool cpow2, int ty, int k, int lane, float* act) {
   const int x = 32 * k + lane;
   const bool valid = x < c.Wc;
   const int xr = valid ? x : c.Wc - 1;
@@ -318,12 +323,12 @@ __device__ __forceinline__ void task_act(const Ctx& c, const float* __restrict__
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = __ldg(p + (j0 + u) * W);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) s = __fadd_rn(s, div_exact(v[u], fC, rC));
+    for (int u = 0; u < 4; ++u) s = __fadd_rn(s, div_channels(v[u], fC, rC, cpow2));
   }
   const float q = s;
   for (int j = 1; j < tile; ++j) s = __fadd_rn(s, __shfl_down_sync(0xffffffffu, q, j));
   if (valid && (lane & (tile - 1)) == 0)
-    act[ty * c.wt + (x >> c.tshift)] = __fdiv_rn(s, (float)(tile * tile));
+    act[ty * c.wt + (x >> c.tshift)] = __fmul_rn(s, 1.0f / (float)(tile * tile));   // exact scaling
 }
 
 // ---- T2: L1 magnitude of Sobel(BL) (morphology.py:496-497) for rows [r0, min(r0+RT, rend)) -> MAG and
@@ -600,6 +605,7 @@ morph_fused_kernel(const FusedArgs A) {
   const float* sp = A.sum_plane + (long long)b * g.H * g.W;
   const float fC = (float)g.C;
   const float rC = __frcp_rn(fC);
+  const bool cpow2 = (g.C & (g.C - 1)) == 0;
   float lmin = INFINITY, lmax = -INFINITY;
   for (int i = tid; i < 512; i += NT) hist[i] = 0;               // hist + hloc
   {
@@ -623,7 +629,7 @@ morph_fused_kernel(const FusedArgs A) {
           const int r = r_lo - 5 + lr0 + u;
           if (lr0 + u < nrows) {
             const bool in = xok && r >= 0 && r < Hc;
-            const float q = in ? div_exact(v[u], fC, rC) : 0.f;
+            const float q = in ? div_channels(v[u], fC, rC, cpow2) : 0.f;
             G[(lr0 + u) * g.gs + c0] = q;
             if (in && r >= r_lo && r < r_hi) { lmin = fminf(lmin, q); lmax = fmaxf(lmax, q); }
           }
@@ -697,7 +703,7 @@ morph_fused_kernel(const FusedArgs A) {
       } else {
         const int q = task - nadapt - nblur - nlbp;
         const int tyl = q / WW, k = q - tyl * WW;
-        task_act(c, ap, g.W, fC, rC, tr0 + tyl, k, lane, act_s);
+        task_act(c, ap, g.W, fC, rC, cpow2, tr0 + tyl, k, lane, act_s);
       }
     }
     if (A.softmask && A.abs_plane && !g.aligned)
@@ -928,7 +934,7 @@ morph_fused_kernel(const FusedArgs A) {
     if (ns > 1) { publish(mt_s); cl.sync(); }
     float* mo = A.mask + (long long)b * g.H * g.W;
     if (g.aligned) {
-      softmask_class_table(mt_s, w_sm, g.ht, g.wt, t_lo, t_hi, cls);
+      softmask_class_table(mt_s, w_sm, g.ht, g.wt, tile, t_lo, t_hi, cls);
       __syncthreads();
       softmask_plane_from_classes(cls, g.W, g.wt, tile, tshift, t_lo, r_lo, r_hi, mo);
     } else {

@@ -32,7 +32,40 @@ struct VecIO<T, 1> {
   __device__ __forceinline__ static void unpack(const Raw& r, float* f) { f[0] = r; }
 };
 
-template <typename T, int VEC, int G, bool RANGES>
+// running min / max of everything a thread has seen of one channel.  bf16 keeps two packed partials
+// (even / odd elements of the vectors) and updates them with 2-wide HMNMX2 straight on the raw words;
+// the extremes of bf16 data are bf16 values, so nothing is lost.  fp32 keeps plain floats.
+template <typename T, int VEC>
+struct MinMaxAcc {
+  float lo, hi;
+  __device__ __forceinline__ void init() { lo = INFINITY; hi = -INFINITY; }
+  __device__ __forceinline__ void update(const typename VecIO<T, VEC>::Raw& r) {
+    float d[VEC];
+    VecIO<T, VEC>::unpack(r, d);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { lo = fminf(lo, d[e]); hi = fmaxf(hi, d[e]); }
+  }
+  __device__ __forceinline__ float vmin() const { return lo; }
+  __device__ __forceinline__ float vmax() const { return hi; }
+};
+template <>
+struct MinMaxAcc<__nv_bfloat16, 8> {
+  __nv_bfloat162 lo, hi;
+  __device__ __forceinline__ static __nv_bfloat162 as2(uint32_t w) { return *reinterpret_cast<__nv_bfloat162*>(&w); }
+  __device__ __forceinline__ void init() { lo = as2(0x7f807f80u); hi = as2(0xff80ff80u); }
+  __device__ __forceinline__ void update(const uint4& r) {
+    const __nv_bfloat162 a = as2(r.x), b = as2(r.y), c = as2(r.z), d = as2(r.w);
+    lo = __hmin2(lo, __hmin2(__hmin2(a, b), __hmin2(c, d)));
+    hi = __hmax2(hi, __hmax2(__hmax2(a, b), __hmax2(c, d)));
+  }
+  __device__ __forceinline__ float vmin() const { return fminf(__low2float(lo), __high2float(lo)); }
+  __device__ __forceinline__ float vmax() const { return fmaxf(__low2float(hi), __high2float(hi)); }
+};
+
+// RMODE: 0 no ranges, 1 per-vector warp reduction (any C), 2 per-thread running min / max in
+// registers when the CTA's G warps cover all channel chunks in one pass (a warp then always owns
+// the same 16 channels), reduced across the warp once per CTA
+template <typename T, int VEC, int G, int RMODE>
 __global__ void __launch_bounds__(32 * G)
 reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
                      float* __restrict__ sum_plane, float* __restrict__ abs_plane,
@@ -40,6 +73,13 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
   constexpr int NT = 32 * G;
   constexpr int STRIP = 32 * VEC;                 // pixels per strip
   constexpr int NOUT = (2 * STRIP + NT - 1) / NT; // outputs owned per thread in the fold
+  constexpr bool RANGES = RMODE == 1;             // shared-memory range table + per-vector REDUX
+  constexpr bool ACC = RMODE == 2;                // register accumulators, npass == 1
+  MinMaxAcc<T, VEC> mm[16];
+  if (ACC) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) mm[j].init();
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* part = reinterpret_cast<float*>(smem_raw);           // [2][G][STRIP]
   int* smin = reinterpret_cast<int*>(part + 2 * G * STRIP);   // [C]
@@ -69,6 +109,7 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
 #pragma unroll
     for (int k = 0; k < NOUT; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; acc2[k] = 0.f; }
 
+#pragma unroll 1
     for (int pass = 0; pass < npass; ++pass) {
       const int gi = pass * G + warp;             // chunk index of this warp
       const int c0 = gi << 4;
@@ -101,6 +142,9 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
             a[e] = __fadd_rn(a[e], fabsf(d[e]));
             lo = fminf(lo, d[e]);
             hi = fmaxf(hi, d[e]);
+          }
+          if (ACC) {
+            if (active && j < nch) mm[j].update(raw[j]);
           }
           if (RANGES) {
             const bool ok = active && j < nch;
@@ -165,6 +209,24 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
       atomicMax(keys + C + c, smax[c]);
     }
   }
+  if (ACC) {
+    // one warp reduction per owned channel for the whole CTA; lane j publishes channel c0 + j
+    const int gi = warp;
+    if (gi < ngroups) {
+      const int nch = (gi < nfull) ? 16 : tail;
+      int mymin = MCAQ_KEY_POS_INF, mymax = MCAQ_KEY_NEG_INF;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int kmin = __reduce_min_sync(0xffffffffu, float_key(mm[j].vmin()));
+        const int kmax = __reduce_max_sync(0xffffffffu, float_key(mm[j].vmax()));
+        if (lane == j) { mymin = kmin; mymax = kmax; }
+      }
+      if (lane < nch) {
+        atomicMin(keys + (gi << 4) + lane, mymin);
+        atomicMax(keys + C + (gi << 4) + lane, mymax);
+      }
+    }
+  }
 }
 
 __global__ void ranges_reset_kernel(int* keys, int C) {
@@ -223,19 +285,17 @@ static int launch_reduce(const T* x, int B, int C, int HW, float* sp, float* ap,
   const long long total = (long long)B * spi;
   const size_t smem = (size_t)2 * G * 32 * VEC * sizeof(float) + (size_t)2 * C * sizeof(int);
   // persistent CTAs: a few per SM so 16 loads x 32*G threads cover the HBM latency
-  const int per_sm = G >= 8 ? 4 : (G >= 4 ? 8 : 16);
+  const int per_sm = G >= 16 ? 2 : (G >= 8 ? 4 : (G >= 4 ? 8 : 16));
   long long grid = (long long)num_sms() * per_sm;
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;
-  if (keys) {
-    auto k = reduce_planes_kernel<T, VEC, G, true>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<(unsigned)grid, 32 * G, smem, st>>>(x, B, C, HW, sp, ap, keys, spi, total);
-  } else {
-    auto k = reduce_planes_kernel<T, VEC, G, false>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<(unsigned)grid, 32 * G, smem, st>>>(x, B, C, HW, sp, ap, keys, spi, total);
-  }
+  const int npass = ((C + 15) / 16 + G - 1) / G;
+  void (*k)(const T*, int, int, int, float*, float*, int*, int, long long);
+  if (!keys) k = reduce_planes_kernel<T, VEC, G, 0>;
+  else if (VEC > 1 && npass == 1) k = reduce_planes_kernel<T, VEC, G, 2>;
+  else k = reduce_planes_kernel<T, VEC, G, 1>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<(unsigned)grid, 32 * G, smem, st>>>(x, B, C, HW, sp, ap, keys, spi, total);
   MCAQ_LAUNCH_CHECK();
   return 0;
 }
@@ -243,6 +303,7 @@ static int launch_reduce(const T* x, int B, int C, int HW, float* sp, float* ap,
 template <typename T, int VEC>
 static int dispatch_groups(const T* x, int B, int C, int HW, float* sp, float* ap, int* keys, cudaStream_t st) {
   const int ngroups = (C + 15) / 16;
+  if (ngroups >= 16) return launch_reduce<T, VEC, 16>(x, B, C, HW, sp, ap, keys, st);
   if (ngroups >= 8) return launch_reduce<T, VEC, 8>(x, B, C, HW, sp, ap, keys, st);
   if (ngroups >= 3) return launch_reduce<T, VEC, 4>(x, B, C, HW, sp, ap, keys, st);
   if (ngroups == 2) return launch_reduce<T, VEC, 2>(x, B, C, HW, sp, ap, keys, st);

@@ -23,6 +23,10 @@ __device__ __forceinline__ float sigmoid_exact(float z) {
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
 }
 
+// n / d for 0 <= n, n * d < 2^32, with magic = 2^32 / d + 1 (one IMAD.HI instead of the division sequence)
+__device__ __forceinline__ uint32_t div_magic(int d) { return 0xffffffffu / (uint32_t)d + 1u; }
+__device__ __forceinline__ int fast_div(int n, uint32_t magic) { return (int)__umulhi((uint32_t)n, magic); }
+
 // sum over the 32 lanes in xor-butterfly order; every lane returns the same bits
 __device__ __forceinline__ float warp_tree_sum(float v) {
 #pragma unroll
@@ -59,17 +63,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // LayerNorm + ReLU of one value per lane (D = 32) or two values per lane (D = 64)
 __device__ __forceinline__ void ln64_relu(float& a0, float& a1, float g0, float g1, float be0, float be1) {
-  const float mean = __fdiv_rn(warp_tree_sum(__fadd_rn(a0, a1)), 64.f);
+  const float mean = __fmul_rn(warp_tree_sum(__fadd_rn(a0, a1)), 0.015625f);        // / 64, exact scaling
   const float d0 = __fsub_rn(a0, mean), d1 = __fsub_rn(a1, mean);
-  const float var = __fdiv_rn(warp_tree_sum(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1))), 64.f);
+  const float var = __fmul_rn(warp_tree_sum(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1))), 0.015625f);
   const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
   a0 = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g0), be0), 0.f);
   a1 = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d1, rstd), g1), be1), 0.f);
 }
 __device__ __forceinline__ float ln32_relu(float a0, float g, float be) {
-  const float mean = __fdiv_rn(warp_tree_sum(a0), 32.f);
+  const float mean = __fmul_rn(warp_tree_sum(a0), 0.03125f);                          // / 32, exact scaling
   const float d0 = __fsub_rn(a0, mean);
-  const float var = __fdiv_rn(warp_tree_sum(__fmul_rn(d0, d0)), 32.f);
+  const float var = __fmul_rn(warp_tree_sum(__fmul_rn(d0, d0)), 0.03125f);
   const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
   return fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g), be), 0.f);
 }
@@ -185,10 +189,11 @@ __device__ __forceinline__ void bilateral_range(const float* craw, int ht, int w
                                                 float* cfin, float* __restrict__ out) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int n = t_hi - t_lo;
+  const uint32_t mwt = div_magic(wt);
   for (int o = tid; o < n * 25; o += NT) {        // range weights for all (tile, tap) pairs in parallel
     const int tl = o / 25, tap = o - tl * 25;
     const int t = t_lo + tl;
-    const int y = t / wt, x = t - y * wt;
+    const int y = fast_div(t, mwt), x = t - y * wt;
     const int ky = tap / 5, kx = tap - ky * 5;
     const int yy = min(max(y + ky - 2, 0), ht - 1), xx = min(max(x + kx - 2, 0), wt - 1);
     const float d = __fsub_rn(craw[yy * wt + xx], craw[t]);
@@ -198,7 +203,7 @@ __device__ __forceinline__ void bilateral_range(const float* craw, int ht, int w
   __syncthreads();
   for (int tl = tid; tl < n; tl += NT) {          // ordered accumulation of the 25 taps
     const int t = t_lo + tl;
-    const int y = t / wt, x = t - y * wt;
+    const int y = fast_div(t, mwt), x = t - y * wt;
     float num = 0.f, den = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) {
@@ -410,8 +415,9 @@ __device__ __forceinline__ void softmask_head_range(const float* bits, const flo
   const float* b0 = P + 144;
   const float* W2 = P + 152;
   const float* b2 = P + 168;
+  const uint32_t mwt = div_magic(Wt);
   for (int t = t_lo + tid; t < t_hi; t += NT) {
-    const int i = t / Wt, j = t - i * Wt;
+    const int i = fast_div(t, mwt), j = t - i * Wt;
     float hid[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
@@ -479,29 +485,43 @@ __device__ __forceinline__ void softmask_plane_rows(const float* mt, const float
 //     mask values.  cls[(t - t_lo)*25 + cy*5 + cx] is that value (same FMA chain as the generic path).
 __device__ __forceinline__ int mask_class(int d, int tile) { return d < 2 ? d : (d >= tile - 2 ? d - (tile - 5) : 2); }
 
-__device__ __forceinline__ void softmask_class_table(const float* mt, const float* P, int Ht, int Wt, int t_lo,
-                                                     int t_hi, float* cls) {
-  const float* ks = P + 170;
-  for (int o = threadIdx.x; o < (t_hi - t_lo) * 25; o += blockDim.x) {
-    const int tl = o / 25, c = o - tl * 25;
-    const int cy = c / 5, cx = c - cy * 5;
-    const int t = t_lo + tl;
-    const int ty = t / Wt, tx = t - ty * Wt;
-    float acc = 0.f;
+__device__ __forceinline__ void softmask_class_table(const float* mt, const float* P, int Ht, int Wt, int tile,
+                                                     int t_lo, int t_hi, float* cls) {
+  // one thread per tile: 3x3 tile neighbourhood (replicate clamped) and the 5x5 kernel in registers,
+  // all 25 classes unrolled so every tap is a register-register FFMA
+  const uint32_t mwt = div_magic(Wt);
+  for (int t = t_lo + threadIdx.x; t < t_hi; t += blockDim.x) {
+    const int ty = fast_div(t, mwt), tx = t - ty * Wt;
+    float n[3][3], ks[25];
 #pragma unroll
-    for (int ky = 0; ky < 5; ++ky) {
-      // tile-row offset of tap ky for class cy: rows above the tile for (cy=0: ky<2, cy=1: ky<1),
-      // below for (cy=3: ky>3, cy=4: ky>2)
-      const int oy = (ky < 2 - cy) ? -1 : ((ky > 6 - cy) ? 1 : 0);
-      const int yy = min(max(ty + oy, 0), Ht - 1);
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = min(max(ty + dy - 1, 0), Ht - 1);
 #pragma unroll
-      for (int kx = 0; kx < 5; ++kx) {
-        const int ox = (kx < 2 - cx) ? -1 : ((kx > 6 - cx) ? 1 : 0);
-        const int xx = min(max(tx + ox, 0), Wt - 1);
-        acc = fmaf(mt[yy * Wt + xx], ks[ky * 5 + kx], acc);
+      for (int dx = 0; dx < 3; ++dx) n[dy][dx] = mt[yy * Wt + min(max(tx + dx - 1, 0), Wt - 1)];
+    }
+#pragma unroll
+    for (int i = 0; i < 25; ++i) ks[i] = P[170 + i];
+    float* dst = cls + (t - t_lo) * 25;
+#pragma unroll
+    for (int cy = 0; cy < 5; ++cy) {
+#pragma unroll
+      for (int cx = 0; cx < 5; ++cx) {
+        if (tile == 4 && (cy == 2 || cx == 2)) continue;      // a 4-pixel tile has no interior class
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+          // tile-row offset of tap ky for class cy: the tile above for (cy=0: ky<2, cy=1: ky<1), the
+          // tile below for (cy=3: ky>3, cy=4: ky>2)
+          const int oy = (ky < 2 - cy) ? -1 : ((ky > 6 - cy) ? 1 : 0);
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const int ox = (kx < 2 - cx) ? -1 : ((kx > 6 - cx) ? 1 : 0);
+            acc = fmaf(n[1 + oy][1 + ox], ks[ky * 5 + kx], acc);
+          }
+        }
+        dst[cy * 5 + cx] = acc;
       }
     }
-    cls[o] = acc;
   }
 }
 
@@ -511,8 +531,9 @@ __device__ __forceinline__ void softmask_plane_from_classes(const float* cls, in
                                                             int t_lo, int h_lo, int h_hi, float* __restrict__ mo) {
   const int W4 = W >> 2;
   const int n4 = (h_hi - h_lo) * W4;
+  const uint32_t mw4 = div_magic(W4);
   for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-    const int hr = i / W4, w = (i - hr * W4) << 2;
+    const int hr = fast_div(i, mw4), w = (i - hr * W4) << 2;
     const int h = h_lo + hr;
     const int t = (h >> tshift) * Wt + (w >> tshift);
     const float* c = cls + (t - t_lo) * 25 + mask_class(h & (tile - 1), tile) * 5;
