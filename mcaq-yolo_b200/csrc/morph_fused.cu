@@ -95,6 +95,16 @@ __device__ __forceinline__ float div_channels(float x, float fC, float rC, bool 
   return pow2 ? __fmul_rn(x, rC) : div_exact(x, fC, rC);
 }
 
+// literal atan2 binning for the rare pixels within the guard band of a bin boundary (not inlined: rare)
+static __device__ __noinline__ int nms_bin_exact(float gx, float gy) {
+  float ang = __fmul_rn(atan2f(gy, gx), kc::RAD2DEG);
+  if (ang < 0.f) ang = __fadd_rn(ang, 180.f);
+  if (ang < 22.5f || ang >= 157.5f) return 0;
+  if (ang < 67.5f) return 1;
+  if (ang < 112.5f) return 2;
+  return 3;
+}
+
 // direction bin of the NMS (morphology.py:430-444).  Slope tests with a 1e-5 relative guard band
 // decide all but boundary cases; those take the literal atan2f path.
 __device__ __forceinline__ int nms_bin(float gx, float gy) {
@@ -104,12 +114,7 @@ __device__ __forceinline__ int nms_bin(float gx, float gy) {
   if (ay < a * 0.99999f) return 0;
   if (ay > a * 1.00001f && ay < b * 0.99999f) return ((gx > 0.f) == (gy > 0.f)) ? 1 : 3;
   if (ay > b * 1.00001f) return 2;
-  float ang = __fmul_rn(atan2f(gy, gx), kc::RAD2DEG);
-  if (ang < 0.f) ang = __fadd_rn(ang, 180.f);
-  if (ang < 22.5f || ang >= 157.5f) return 0;
-  if (ang < 67.5f) return 1;
-  if (ang < 112.5f) return 2;
-  return 3;
+  return nms_bin_exact(gx, gy);
 }
 
 // Sobel responses from a 3x3 window of zero-padded values: FMA chain over the taps in row-major
@@ -679,7 +684,8 @@ morph_fused_kernel(const FusedArgs A) {
   {
     const int b_lo = max(r_lo - 2, 0), b_hi = min(r_hi + 2, Hc);          // blur rows
     const int nblur = ((b_hi - b_lo + 7) >> 3) * WW;
-    const int RTa = tile >= 8 ? 8 : 4;
+    const int RTa = 4;                 // 4-row runs: the unrolled 11x11 body (15 KB) stays resident in the
+                                       // instruction cache and is re-used by every run of every warp
     const int nadapt = ((r_hi - r_lo) / RTa) * WW;
     const int nlbp = (tr1 - tr0) * WW;
     const bool fast_act = A.softmask && A.abs_plane && g.aligned;
@@ -689,8 +695,7 @@ morph_fused_kernel(const FusedArgs A) {
     for (int task = warp; task < ntask; task += nwarps) {
       if (task < nadapt) {
         const int rg = task / WW, k = task - rg * WW;
-        if (RTa == 8) task_adaptive<8>(c, cl, r_lo + rg * 8, k, lane);
-        else task_adaptive<4>(c, cl, r_lo + rg * 4, k, lane);
+        task_adaptive<4>(c, cl, r_lo + rg * 4, k, lane);
       } else if (task < nadapt + nblur) {
         const int q = task - nadapt;
         const int rg = q / WW, k = q - rg * WW;
@@ -832,8 +837,10 @@ morph_fused_kernel(const FusedArgs A) {
     const int* a = acc + t * 9;
     const int Sn = g.S;
     float y[5];
+#pragma unroll 1
     for (int i = 0; i < Sn; ++i) y[i] = lutn[a[4 + i]];                         // log(N_s + 1)
     float w_sum = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll 1
     for (int i = 0; i < Sn; ++i) {
       w_sum = __fadd_rn(w_sum, kc::FW[i]);
       sx = __fadd_rn(sx, __fmul_rn(kc::FW[i], kc::FLOG[i]));
@@ -841,6 +848,7 @@ morph_fused_kernel(const FusedArgs A) {
     }
     const float x_mean = __fdiv_rn(sx, w_sum), y_mean = __fdiv_rn(sy, w_sum);
     float cov = 0.f, var = 0.f;
+#pragma unroll 1
     for (int i = 0; i < Sn; ++i) {
       const float dx = __fsub_rn(kc::FLOG[i], x_mean);
       cov = __fadd_rn(cov, __fmul_rn(__fmul_rn(kc::FW[i], dx), __fsub_rn(y[i], y_mean)));

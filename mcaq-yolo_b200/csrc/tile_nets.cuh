@@ -18,8 +18,14 @@
 
 namespace mcaq {
 
+// fp64 transcendentals rounded once to fp32 (the oracle's contract).  Deliberately NOT inlined: each
+// expansion is ~1.5 KB of straight-line code used once per call site, and the per-image kernel is
+// instruction-fetch bound.
+static __device__ __noinline__ float exp_f64(float x) { return (float)exp((double)x); }
+static __device__ __noinline__ float log1p_f64(float x) { return (float)log1p((double)x); }
+
 __device__ __forceinline__ float sigmoid_exact(float z) {
-  const float e = (float)exp((double)(-z));
+  const float e = exp_f64(-z);
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
 }
 
@@ -198,7 +204,7 @@ __device__ __forceinline__ void bilateral_range(const float* craw, int ht, int w
     const int yy = min(max(y + ky - 2, 0), ht - 1), xx = min(max(x + kx - 2, 0), wt - 1);
     const float d = __fsub_rn(craw[yy * wt + xx], craw[t]);
     const float arg = __fdiv_rn(-__fmul_rn(d, d), kc::BILAT_DEN);
-    wgt[o] = __fmul_rn(kc::BILAT[tap], (float)exp((double)arg));
+    wgt[o] = __fmul_rn(kc::BILAT[tap], exp_f64(arg));
   }
   __syncthreads();
   for (int tl = tid; tl < n; tl += NT) {          // ordered accumulation of the 25 taps
@@ -255,7 +261,7 @@ __device__ __forceinline__ void mapper_mlp_warps(const float* cmap, int t_lo, in
   for (int tg = t_lo + warp * NET_TT; tg < t_hi; tg += nwarps * NET_TT) {
     if (lane < NET_TT) {                                  // z0 = [c, c^2, log1p(c)]  (Eq.13)
       const float c = fminf(fmaxf(cmap[min(tg + lane, t_hi - 1)], 0.f), 1.f);
-      *reinterpret_cast<float4*>(zin + lane * 4) = make_float4(c, __fmul_rn(c, c), (float)log1p((double)c), 0.f);
+      *reinterpret_cast<float4*>(zin + lane * 4) = make_float4(c, __fmul_rn(c, c), log1p_f64(c), 0.f);
     }
     __syncwarp();
     {                                                     // 3 -> 32, BN, ReLU
@@ -447,8 +453,8 @@ __device__ __forceinline__ void softmask_head_range(const float* bits, const flo
       lg[o] = __fadd_rn(acc, b2[o]);
     }
     const float mx = fmaxf(lg[0], lg[1]);
-    const float e0 = (float)exp((double)__fsub_rn(lg[0], mx));
-    const float e1 = (float)exp((double)__fsub_rn(lg[1], mx));
+    const float e0 = exp_f64(__fsub_rn(lg[0], mx));
+    const float e1 = exp_f64(__fsub_rn(lg[1], mx));
     const float m = __fdiv_rn(e0, __fadd_rn(e0, e1));
     mt[t] = m;
     if (tiles_out) tiles_out[t] = m;
