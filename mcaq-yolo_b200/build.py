@@ -42,7 +42,8 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        extra = os.environ.get("MCAQ_NVCC_EXTRA", "").split()          # tuning aid: extra -D switches
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out, _ = p.communicate()

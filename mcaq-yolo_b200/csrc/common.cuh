@@ -1,5 +1,11 @@
 // Shared device helpers for the MCAQ sm_100a kernels.
 #pragma once
+#ifndef K3_MAGIC
+#define K3_MAGIC 0
+#endif
+#ifndef K3_MINB
+#define K3_MINB 1
+#endif
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -30,6 +36,13 @@ __device__ __forceinline__ float key_float(int k) {
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+// coherent (in-place safe) streaming load: no L1 allocation, but not the read-only path
+__device__ __forceinline__ uint4 ldg_noalloc(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
@@ -104,7 +117,15 @@ __device__ __forceinline__ float div_markstein(float x, float scale, float rinv)
 __device__ __forceinline__ float quant_code_fast(float x, float scale, float zp, float rinv, float qmin,
                                                  float qmax) {
   const float t = __fadd_rn(div_markstein(x, scale, rinv), zp);
+#if K3_MAGIC
+  // rint on the FMA pipe (the conversion unit runs at 1/8 rate): (t + 1.5*2^23) - 1.5*2^23 is the
+  // round-half-even integer for |t| < 2^22; beyond that the result only has to stay outside
+  // [qmin, qmax] (|q| <= 128), which it does; copysign restores rintf's signed zero
+  const float r = copysignf(__fsub_rn(__fadd_rn(t, 12582912.f), 12582912.f), t);
+  return fminf(fmaxf(r, qmin), qmax);
+#else
   return fminf(fmaxf(rintf(t), qmin), qmax);
+#endif
 }
 __device__ __forceinline__ float dequant(float q, float scale, float zp) {
   return __fmul_rn(__fsub_rn(q, zp), scale);

@@ -199,7 +199,7 @@ constexpr int QV_UNROLL = 8;
 constexpr int QV_ROW = QV_CHUNK + 1;
 
 template <typename T, int VEC, bool HAS_MASK, bool CODES>
-__global__ void __launch_bounds__(QV_THREADS)
+__global__ void __launch_bounds__(QV_THREADS, K3_MINB)
 tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
                          const float* __restrict__ bit_map, const float2* __restrict__ qtable,
                          const float* __restrict__ mask, int8_t* __restrict__ codes, bool inplace,
@@ -248,45 +248,63 @@ tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
     }
   }
   const long long base = ((long long)b * g.C + c_begin) * g.HW + pix;
-  const T* xp = x + base;
-  T* yp = y + base;
+  // running byte pointers: one 64-bit add per channel instead of re-deriving base + c * HW
+  const char* xb = reinterpret_cast<const char*>(x + base);
+  char* yb = reinterpret_cast<char*>(y + base);
+  const long long sb = (long long)g.HW * (long long)sizeof(T);
+  (void)inplace;                       // loads are coherent (ld.global, no L1 allocation): y may alias x
+  // one channel of the thread's pixel vector: quantize / dequantize / mask, store, optional codes
+  auto emit = [&](const uint4& rawv, int c, char* dst) {
+    float xv[VEC], out[VEC];
+    Elem<T>::unpack(rawv, xv);
+    uint32_t cpack[NSEG];
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+      const float4 p = tab[trow[s] + c];
+      uint32_t cp = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float q = quant_code_fast(xv[4 * s + e], p.x, p.y, p.z, qmin[s], qmax[s]);
+        float d = dequant(q, p.x, p.y);
+        if (HAS_MASK) d = __fmul_rn(d, m[4 * s + e]);
+        out[4 * s + e] = d;
+        if (CODES) cp |= ((uint32_t)(int)q & 0xffu) << (8 * e);
+      }
+      cpack[s] = cp;
+    }
+    stg_stream(dst, Elem<T>::pack(out));
+    if (CODES) {
+      uint32_t* cdst = reinterpret_cast<uint32_t*>(codes + base + (long long)c * g.HW);
+#pragma unroll
+      for (int s = 0; s < NSEG; ++s) cdst[s] = cpack[s];
+    }
+  };
+  if (nch == QV_CHUNK) {
+    // full chunk (the common case): no per-channel predicates, the whole channel walk unrolled so
+    // the table offsets are immediates
+#pragma unroll
+    for (int c0 = 0; c0 < QV_CHUNK; c0 += QV_UNROLL) {
+      uint4 raw[QV_UNROLL];
+#pragma unroll
+      for (int u = 0; u < QV_UNROLL; ++u) { raw[u] = ldg_noalloc(xb); xb += sb; }
+#pragma unroll
+      for (int u = 0; u < QV_UNROLL; ++u) { emit(raw[u], c0 + u, yb); yb += sb; }
+    }
+    return;
+  }
 #pragma unroll 1
   for (int c0 = 0; c0 < nch; c0 += QV_UNROLL) {
     uint4 raw[QV_UNROLL];
 #pragma unroll
-    for (int u = 0; u < QV_UNROLL; ++u) {
-      if (c0 + u < nch) {
-        const T* p = xp + (long long)(c0 + u) * g.HW;
-        raw[u] = inplace ? ldg_plain(p) : ldg_stream(p);
-      }
-    }
+    for (int u = 0; u < QV_UNROLL; ++u)
+      if (c0 + u < nch) raw[u] = ldg_noalloc(xb + u * sb);
 #pragma unroll
     for (int u = 0; u < QV_UNROLL; ++u) {
       if (c0 + u >= nch) break;
-      float xv[VEC], out[VEC];
-      Elem<T>::unpack(raw[u], xv);
-      uint32_t cpack[NSEG];
-#pragma unroll
-      for (int s = 0; s < NSEG; ++s) {
-        const float4 p = tab[trow[s] + c0 + u];
-        uint32_t cp = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float q = quant_code_fast(xv[4 * s + e], p.x, p.y, p.z, qmin[s], qmax[s]);
-          float d = dequant(q, p.x, p.y);
-          if (HAS_MASK) d = __fmul_rn(d, m[4 * s + e]);
-          out[4 * s + e] = d;
-          if (CODES) cp |= ((uint32_t)(int)q & 0xffu) << (8 * e);
-        }
-        cpack[s] = cp;
-      }
-      stg_stream(yp + (long long)(c0 + u) * g.HW, Elem<T>::pack(out));
-      if (CODES) {
-        uint32_t* cdst = reinterpret_cast<uint32_t*>(codes + base + (long long)(c0 + u) * g.HW);
-#pragma unroll
-        for (int s = 0; s < NSEG; ++s) cdst[s] = cpack[s];
-      }
+      emit(raw[u], c0 + u, yb + u * sb);
     }
+    xb += QV_UNROLL * sb;
+    yb += QV_UNROLL * sb;
   }
 }
 
