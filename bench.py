@@ -52,10 +52,11 @@ def parse():
                     help="multi-GPU: merge the ranges with an NCCL all-reduce between K2 and K3 instead of the "
                          "in-kernel peer-memory exchange")
     ap.add_argument("--sharded", action="store_true", help="use the multi-rank phase split even at world size 1")
-    ap.add_argument("--inflight", type=int, default=4, choices=[1, 2, 4],
+    ap.add_argument("--inflight", type=int, default=4, choices=[1, 2, 4, 8],
                     help="steps in flight: consecutive steps alternate between this many streams (each with its own "
                          "workspace), so the latency-bound morphology kernel of one step overlaps the HBM sweeps of "
                          "its neighbours; 1 = strictly serial steps")
+    ap.add_argument("--input-sets", type=int, default=0, help="rotating input sets (default 4, or --inflight if larger)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -163,7 +164,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -195,6 +196,8 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- native arm
 def run_native(args):
+    global INPUT_SETS
+    INPUT_SETS = max(args.input_sets or INPUT_SETS, args.inflight)
     import torch
     import torch.distributed as dist
 
@@ -366,7 +369,21 @@ def run_native(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        # nvidia-smi samples every 50 ms: when the K timed steps are shorter than that, keep the same
+        # load running (untimed) for half a second so the clock / throttle samples are taken under it
+        burst = 0
+        if ms < 400.0:
+            burst = int(min(20000, 500.0 / max(ms / args.steps, 1e-3)))
+            burst -= burst % INPUT_SETS
+            fork_slots()
+            for i in range(burst):
+                run_step(i)
+            join_slots()
+            barrier()
         clocks = sampler.stop() if rank == 0 else None
+        if clocks is not None:
+            clocks["note"] = ("sampled over the timed region" if burst == 0 else
+                              "sampled over the timed region plus %d untimed steps of the same load" % burst)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
