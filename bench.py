@@ -250,7 +250,7 @@ def run_native(args):
             from mcaq_yolo_b200.peer import RangeExchange
             exchanges = [RangeExchange.create(C) for C, _, _ in shapes]
         hots.append(FusedHotPath(analyzer, mapper, quantizers, temperature=1.0, streams=not args.no_streams,
-                                 exchanges=exchanges))
+                                 exchanges=exchanges, latency=(nslot == 1)))
     hot = hots[0]
     slot_streams = [torch.cuda.Stream(device=dev) for _ in range(nslot)]
 
@@ -369,11 +369,17 @@ def run_native(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        ms_per_step = ms_total / args.steps
         # nvidia-smi samples every 50 ms: when the K timed steps are shorter than that, keep the same
         # load running (untimed) for half a second so the clock / throttle samples are taken under it
+        # (the count derives from the all-reduced time: every rank must run the same number of steps)
         burst = 0
-        if ms < 400.0:
-            burst = int(min(20000, 500.0 / max(ms / args.steps, 1e-3)))
+        if ms_total < 400.0:
+            burst = int(min(20000, 500.0 / max(ms_per_step, 1e-3)))
             burst -= burst % INPUT_SETS
             fork_slots()
             for i in range(burst):
@@ -384,11 +390,6 @@ def run_native(args):
         if clocks is not None:
             clocks["note"] = ("sampled over the timed region" if burst == 0 else
                               "sampled over the timed region plus %d untimed steps of the same load" % burst)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        ms_per_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total * 1e-3)
 
         # ---- roofline attribution: each kernel of each scale timed live with CUDA events around a

@@ -206,6 +206,11 @@ MCAQ_API void mcaq_debug_stage_clocks(long long* dev_buf);
  * the morphology kernel; 0 = automatic */
 MCAQ_API void mcaq_debug_cluster_split(int ns);
 
+/* split policy of the morphology kernel: 0 (default) throughput -- one CTA per image unless the batch
+ * is too small to fill half the GPU (for callers that keep several launches in flight); 1 latency --
+ * every image split over a thread-block cluster, two CTAs per SM (serial callers: the forward hook) */
+MCAQ_API void mcaq_morph_policy(int latency);
+
 /* tile size rule of the analyzer (morphology.py:359-376) */
 MCAQ_API int mcaq_tile_size(int H, int grid_size);
 

@@ -16,6 +16,7 @@ PROTOTYPES = {
     "mcaq_selftest_division": (c_int, [c_void_p, c_int, c_uint, c_uint, c_ulonglong, c_void_p, c_void_p]),
     "mcaq_debug_stage_clocks": (None, [c_void_p]),
     "mcaq_debug_cluster_split": (None, [c_int]),
+    "mcaq_morph_policy": (None, [c_int]),
     "mcaq_ranges_reset": (c_int, [c_void_p, c_int, c_void_p]),
     "mcaq_reduce_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -966,6 +966,11 @@ static int g_force_split = 0;
 extern "C" void mcaq_debug_cluster_split(int ns) { g_force_split = ns; }
 
 static int g_sm_count = 0;
+static int g_latency_mode = 0;
+// split policy: 0 (default) = throughput -- fewest CTAs per image that still fill about half the GPU,
+// for callers that keep several launches in flight; 1 = latency -- split every image over as many
+// cluster CTAs as fit two per SM, for a serial caller (the forward hook inside a model)
+extern "C" void mcaq_morph_policy(int latency) { g_latency_mode = latency ? 1 : 0; }
 
 // CTAs per image: a single CTA per image costs the least SM time (no halo recomputation, no
 // cluster barriers), so an image is split by tile rows over a thread-block cluster (portable size
@@ -982,7 +987,8 @@ static int pick_split(int B, int ht, int tile) {
   if (g_force_split == 1 || g_force_split == 2 || g_force_split == 4 || g_force_split == 8) {
     ns = g_force_split;
   } else {
-    while (ns < 8 && B * ns * 4 <= g_sm_count && (ht / (ns * 2)) * tile >= 8) ns *= 2;
+    const int cap = g_latency_mode ? 2 * g_sm_count : g_sm_count / 2;      // CTAs of one launch
+    while (ns < 8 && B * ns * 2 <= cap && (ht / (ns * 2)) * tile >= 8) ns *= 2;
   }
   while (ns > ht) ns >>= 1;
   return ns < 1 ? 1 : ns;

@@ -121,6 +121,8 @@ class FusedMcaqHook:
         self.model = model
         self.layer_idx = layer_idx
         self.ws = None
+        from . import _lib
+        _lib.load().mcaq_morph_policy(1)      # hooks run serially inside the backbone: latency policy
 
     def __call__(self, module, inputs, output):
         model = self.model
@@ -150,7 +152,7 @@ class FusedHotPath:
     wrapper): `run(feats)` takes the C3/C4/C5 maps and returns the aux records."""
 
     def __init__(self, analyzer, mapper, quantizers, temperature: float = 1.0, streams: bool = True,
-                 exchanges=None):
+                 exchanges=None, latency: bool = False):
         self.analyzer, self.mapper, self.quantizers = analyzer, mapper, list(quantizers)
         self.temperature = temperature
         self.ws = [None] * len(self.quantizers)
@@ -158,6 +160,9 @@ class FusedHotPath:
         self.side = None
         # one peer.RangeExchange per scale when the batch is sharded over the GPUs of a node
         self.xchg = list(exchanges) if exchanges is not None else [None] * len(self.quantizers)
+        # latency=True: a serial caller -- split every image over a cluster (library-wide policy switch)
+        from . import _lib
+        _lib.load().mcaq_morph_policy(1 if latency else 0)
 
     @torch.no_grad()
     def run(self, feats):
