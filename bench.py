@@ -529,7 +529,7 @@ def run_native(args):
         "config": {"workload": args.workload, "per_gpu_batch": B, "shapes_CHW": shapes, "grid": grid, "bits": "2-8",
                    "mapper": "MLP (fixture weights)", "soft_mask": True, "ranges": "dynamic per batch"
                    + ("" if world == 1 else (" (all-reduced MIN over ranks, NCCL)" if sharded is not None else
-                                             " (min over ranks inside K2/K3 through NVLink peer memory, no collective launch)")),
+                                             " (min over ranks inside K2 through NVLink peer memory, no collective launch)")),
                    "l2": "%d rotating input sets (%.0f MB) > 126 MB L2, no flush" % (INPUT_SETS, INPUT_SETS * esize * elems * B / 1e6),
                    "launch": ("cuda-graph replay" if graphs is not None else "eager")
                    + (", module-by-module" if args.unfused else ", fused K1/K2/K3 per scale")

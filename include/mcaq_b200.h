@@ -152,8 +152,10 @@ MCAQ_API int mcaq_morph_fused(const float* sum_plane, const float* abs_plane, in
  * the whole batch (quantization.py:423-426, 650-654).  Each rank owns one exchange buffer per scale
  * (mcaq_xchg_bytes) that every other rank of the node maps through CUDA IPC.  K2's first CTA
  * (mcaq_morph_fused_xchg) stores this rank's [min, -max] into every rank's buffer and releases the
- * step number; K3 (mcaq_tile_quantize_xchg) acquires the flags and takes the minimum over ranks
- * while it builds its scale / zero-point rows.  No collective launch, no host synchronisation.
+ * step number when the kernel starts, and waits for all ranks / writes the minimum into
+ * packed_ranges when it ends; K3 then runs unchanged on packed_ranges.  No collective launch, no
+ * host synchronisation.  mcaq_tile_quantize_xchg is the host-driven form (one-CTA merge kernel +
+ * K3) for callers that publish with mcaq_xchg_publish.
  */
 MCAQ_API long long mcaq_xchg_bytes(int C, int world);
 MCAQ_API int mcaq_xchg_alloc(long long bytes, void** out);           /* cudaMalloc + zero */

@@ -564,6 +564,7 @@ morph_fused_kernel(const FusedArgs A) {
   }
   // K1 -> K3 hand-off of the per-channel ranges: decode the atomics' integer keys to floats and
   // re-arm the keys for the next sweep (stream order: K1 done, K3 not started)
+  int xstep = 0;                                   // multi-GPU: exchange step published by this launch
   if (A.keys && blockIdx.x == 0) {
     for (int ch = tid; ch < g.C; ch += NT) {
       A.packed[ch] = key_float(A.keys[ch]);
@@ -573,7 +574,8 @@ morph_fused_kernel(const FusedArgs A) {
     }
     if (A.px.world > 1) {
       // multi-GPU: this rank's [min, -max] goes into slot `rank` of every rank's exchange buffer,
-      // then the step number is released system-wide; K3 acquires it (peer_exchange.cuh)
+      // then the step number is released system-wide; this same CTA merges at the end of the kernel
+      // (peer_exchange.cuh)
       int* stepw = reinterpret_cast<int*>(red);
       if (tid == 0) {
         int* ep = reinterpret_cast<int*>(A.px.base[A.px.rank]);
@@ -583,6 +585,7 @@ morph_fused_kernel(const FusedArgs A) {
       }
       __syncthreads();
       const int e = stepw[0];
+      xstep = e;
       for (int p = 0; p < A.px.world; ++p) {
         float* dst = A.px.base[p] + XCHG_SLOTS + (long long)((e & 1) * A.px.world + A.px.rank) * 2 * g.C;
         for (int i = tid; i < 2 * g.C; i += NT) dst[i] = A.packed[i];       // own stores, same thread
@@ -594,6 +597,18 @@ morph_fused_kernel(const FusedArgs A) {
       __syncthreads();               // `red` is reused below
     }
   }
+
+  // multi-GPU: the launch's first CTA finishes by waiting for every rank's ranges of this step and
+  // writing their minimum over `packed` (what K3 reads).  Only this one CTA per launch ever spins, and it
+  // does so after its own work, so a waiting kernel can never starve the peers' publishers of SMs.
+  auto merge_ranges = [&]() {
+    if (xstep == 0) return;
+    const float* local = A.px.base[A.px.rank];
+    __syncthreads();
+    xchg_wait(local, A.px.world, xstep, tid);
+    __syncthreads();
+    for (int i = tid; i < 2 * g.C; i += NT) A.packed[i] = xchg_min(local, A.px.world, 2 * g.C, xstep, i);
+  };
 
   Ctx c;
   c.gs = g.gs; c.bs = g.bs;
@@ -925,6 +940,7 @@ morph_fused_kernel(const FusedArgs A) {
   STAGE_CLOCK(11);
   if (!A.softmask || !A.abs_plane) {
     if (ns > 1) cl.sync();                   // nobody leaves while a peer may still write into it
+    merge_ranges();
     return;
   }
   // ---- N3: soft mask (quantization.py:213-239): tile head (own tiles) + m rows (own band) -----------
@@ -950,6 +966,7 @@ morph_fused_kernel(const FusedArgs A) {
     }
   }
   STAGE_CLOCK(12);
+  merge_ranges();
 }
 
 }  // namespace mcaq

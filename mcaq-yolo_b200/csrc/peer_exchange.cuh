@@ -5,12 +5,16 @@
 // launch between K2 and K3, the exchange is folded into the two kernels:
 //   * K2's first CTA stores this rank's vector into slot `rank` of EVERY rank's exchange buffer
 //     (plain stores through the peer mapping), fences, then publishes the step number in every
-//     rank's flag word with a system-scope release store;
-//   * every K3 CTA acquires the R flag words of its LOCAL buffer (spins until all carry the current
-//     step) and takes the minimum over the R slots while it builds its {scale, zero_point} rows.
+//     rank's flag word with a system-scope release store -- at the START of the kernel;
+//   * the same CTA, at the END of the kernel (≈ 100 us later, when the peers' vectors have long
+//     arrived), acquires the R flag words of its LOCAL buffer (spins until all carry the current
+//     step), takes the minimum over the R slots and writes it over the `packed` vector K3 reads.
+// Exactly one CTA per launch can ever wait, and only after its own work: CTAs of a wide kernel
+// spinning on a peer could occupy the SMs the peer-facing publisher of another in-flight step needs
+// (a cross-GPU resource deadlock when several steps are in flight).
 // Slots and flags are double buffered by step parity: a rank can run at most one step ahead of a
-// peer (its next K3 waits for the peer's next K2), so a slot is never overwritten while it can
-// still be read.  No host involvement, no extra launch, capturable in a CUDA graph.
+// peer (its next merge waits for the peer's next publish), so a slot is never overwritten while it
+// can still be read.  No host involvement, no extra launch, capturable in a CUDA graph.
 //
 // Buffer layout (4-byte words):  [0] step counter of the owning rank   [16 + 8*par + q] flag of
 // rank q   [32 + ((par*R + q) * 2C) ...] slot of rank q, par = step & 1.

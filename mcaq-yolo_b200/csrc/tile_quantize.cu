@@ -171,20 +171,12 @@ struct QRanges {
   const float* packed;
   const float* rmin;
   const float* rmax;
-  const float* xchg;      // multi-GPU: local exchange buffer (peer_exchange.cuh), merged over xworld ranks
-  int xworld;
 };
 
-// {scale, zero_point} of (channel c, bits bi+2)  (quantization.py:41-66); step = exchange step (xchg only)
-__device__ __forceinline__ float2 qparams_from_ranges(const QRanges& rg, int C, int c, int bi, int step) {
-  float mn, mx;
-  if (rg.xchg) {
-    mn = xchg_min(rg.xchg, rg.xworld, 2 * C, step, c);
-    mx = -xchg_min(rg.xchg, rg.xworld, 2 * C, step, C + c);
-  } else {
-    mn = rg.packed ? __ldg(rg.packed + c) : __ldg(rg.rmin + c);
-    mx = rg.packed ? -__ldg(rg.packed + C + c) : __ldg(rg.rmax + c);
-  }
+// {scale, zero_point} of (channel c, bits bi+2)  (quantization.py:41-66)
+__device__ __forceinline__ float2 qparams_from_ranges(const QRanges& rg, int C, int c, int bi) {
+  const float mn = rg.packed ? __ldg(rg.packed + c) : __ldg(rg.rmin + c);
+  const float mx = rg.packed ? -__ldg(rg.packed + C + c) : __ldg(rg.rmax + c);
   float qmin, qmax;
   bit_limits(bi, qmin, qmax);
   const float rng = fmaxf(__fsub_rn(mx, mn), 1e-8f);
@@ -208,18 +200,12 @@ tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
   __shared__ float4 tab[7 * QV_ROW];               // {scale, zero_point, RN(1/scale), -}
   const int c_begin = blockIdx.y * QV_CHUNK;
   const int nch = min(QV_CHUNK, g.C - c_begin);
-  int step = 0;
-  if (rg.xchg) {                                   // wait until every rank has published this step's ranges
-    step = xchg_step(rg.xchg);
-    xchg_wait(rg.xchg, rg.xworld, step, threadIdx.x);
-    __syncthreads();
-  }
   for (int i = threadIdx.x; i < 7 * QV_CHUNK; i += QV_THREADS) {
     const int bi = i / QV_CHUNK, cl = i - bi * QV_CHUNK;
     if (cl < nch) {
       float2 p;
       if (qtable) p = __ldg(qtable + (long long)bi * g.C + c_begin + cl);
-      else p = qparams_from_ranges(rg, g.C, c_begin + cl, bi, step);
+      else p = qparams_from_ranges(rg, g.C, c_begin + cl, bi);
       tab[bi * QV_ROW + cl] = make_float4(p.x, p.y, __frcp_rn(p.x), 0.f);
     }
   }
@@ -498,7 +484,7 @@ static QGeom make_geom(int B, int C, int H, int W, int Ht, int Wt, int VEC) {
 template <typename T, int VEC>
 static int launch_quant(const T* x, T* y, int B, int C, int H, int W, const float* bit_map, int Ht, int Wt,
                         const float* qtable, const float* mask, int8_t* codes, cudaStream_t st,
-                        QRanges rg = QRanges{nullptr, nullptr, nullptr, nullptr, 0}) {
+                        QRanges rg = QRanges{nullptr, nullptr, nullptr}) {
   QGeom g = make_geom(B, C, H, W, Ht, Wt, VEC);
   const bool inplace = (const void*)x == (const void*)y;
   const float2* qt = (const float2*)qtable;
@@ -604,7 +590,7 @@ extern "C" int mcaq_tile_quantize_ranges(const void* x, void* y, int dtype, int 
   int rc = check_common(x, y, B, C, H, W, bit_map, Ht, Wt, &dummy);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  QRanges rg{packed, running_min, running_max, nullptr, 0};
+  QRanges rg{packed, running_min, running_max};
   const bool vec = dtype == MCAQ_F32 ? seg_ok(x, y, mask, nullptr, H * W, W, Wt, 4)
                                      : seg_ok(x, y, mask, nullptr, H * W, W, Wt, 8);
   if (vec) {
@@ -623,35 +609,19 @@ extern "C" int mcaq_tile_quantize_ranges(const void* x, void* y, int dtype, int 
   return mcaq_tile_quantize(x, y, dtype, B, C, H, W, bit_map, Ht, Wt, qtable_ws, mask, nullptr, stream);
 }
 
-// Multi-GPU form of mcaq_tile_quantize_ranges: the per-channel ranges are the minimum over the
-// `world` slots of this rank's exchange buffer (written by every rank's K2, peer_exchange.cuh); each
-// CTA waits for the current step's flags itself.  Odd geometries merge into packed_ws first.
+// Multi-GPU, host-driven form of mcaq_tile_quantize_ranges: a one-CTA kernel waits for the `world`
+// ranks' published ranges of the current step and writes their minimum to packed_ws
+// (peer_exchange.cuh), then the regular K3 runs on it.  (The fused path does not need this: the
+// morphology kernel's first CTA merges at its end.)  The wait is confined to that single CTA on
+// purpose: CTAs of a bandwidth kernel spinning on a peer could starve the very kernel they wait for.
 extern "C" int mcaq_tile_quantize_xchg(const void* x, void* y, int dtype, int B, int C, int H, int W,
                                        const float* bit_map, int Ht, int Wt, const void* xchg_local, int world,
                                        float* qtable_ws, float* packed_ws, const float* mask, void* stream) {
-  if (!xchg_local || world <= 0 || world > XCHG_MAX_RANKS) return MCAQ_EINVAL;
-  float dummy = 0.f;
-  int rc = check_common(x, y, B, C, H, W, bit_map, Ht, Wt, &dummy);
+  if (!xchg_local || !packed_ws || world <= 0 || world > XCHG_MAX_RANKS) return MCAQ_EINVAL;
+  int rc = mcaq_xchg_merge(xchg_local, world, C, packed_ws, stream);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  QRanges rg{nullptr, nullptr, nullptr, reinterpret_cast<const float*>(xchg_local), world};
-  const bool vec = dtype == MCAQ_F32 ? seg_ok(x, y, mask, nullptr, H * W, W, Wt, 4)
-                                     : seg_ok(x, y, mask, nullptr, H * W, W, Wt, 8);
-  if (vec) {
-    if (dtype == MCAQ_F32)
-      return launch_quant<float, 4>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, nullptr, mask, nullptr, st, rg);
-    if (dtype == MCAQ_BF16) {
-      typedef __nv_bfloat16 bf;
-      return launch_quant<bf, 8>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, nullptr, mask, nullptr, st, rg);
-    }
-    return MCAQ_EDTYPE;
-  }
-  if (!qtable_ws || !packed_ws) return MCAQ_EINVAL;
-  rc = mcaq_xchg_merge(xchg_local, world, C, packed_ws, stream);
-  if (rc) return rc;
-  rc = mcaq_build_qtable(packed_ws, nullptr, nullptr, C, qtable_ws, stream);
-  if (rc) return rc;
-  return mcaq_tile_quantize(x, y, dtype, B, C, H, W, bit_map, Ht, Wt, qtable_ws, mask, nullptr, stream);
+  return mcaq_tile_quantize_ranges(x, y, dtype, B, C, H, W, bit_map, Ht, Wt, packed_ws, nullptr, nullptr,
+                                   qtable_ws, mask, stream);
 }
 
 extern "C" int mcaq_tile_quantize_train_fwd(const void* x, void* y, int dtype, int B, int C, int H, int W,

@@ -95,7 +95,8 @@ def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, tempera
     if frozen:
         y = ops.tile_quantize_ranges(x, r["bit_map"], None, quantizer.running_min, quantizer.running_max, r["mask"])
     elif xchg is not None and xchg.world > 1:
-        y = ops.tile_quantize_ranges(x, r["bit_map"], r["packed"], None, None, r["mask"], xchg=xchg)
+        # K2's first CTA published this rank's ranges at its start and merged all ranks' at its end
+        y = ops.tile_quantize_ranges(x, r["bit_map"], r["packed"], None, None, r["mask"])
     else:
         packed = r["packed"]
         if sync:

@@ -314,7 +314,8 @@ def tile_quantize_ranges(x: torch.Tensor, bit_map: torch.Tensor, packed: torch.T
                          running_min: torch.Tensor | None = None, running_max: torch.Tensor | None = None,
                          mask: torch.Tensor | None = None, out: torch.Tensor | None = None, xchg=None):
     """K3 with the per-channel ranges given directly (no table kernel).  With `xchg` (a
-    peer.RangeExchange of world > 1) the ranges are the minimum over the ranks' published vectors."""
+    peer.RangeExchange of world > 1, host-driven use) a one-CTA kernel first merges the ranks'
+    published vectors; the fused path passes the already merged `packed` of morph_fused instead."""
     _need_cuda(x, bit_map, packed, running_min, running_max, mask)
     x = x if x.is_contiguous() else x.contiguous()
     B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
@@ -327,7 +328,7 @@ def tile_quantize_ranges(x: torch.Tensor, bit_map: torch.Tensor, packed: torch.T
     needs_ws = not ((H * W) % vec == 0 and W % 4 == 0 and W % Wt == 0 and (W // Wt) % 4 == 0)
     ws = torch.empty((7, C, 2), device=x.device, dtype=torch.float32) if needs_ws else None
     if xchg is not None and xchg.world > 1:
-        pws = torch.empty((2 * C,), device=x.device, dtype=torch.float32) if needs_ws else None
+        pws = torch.empty((2 * C,), device=x.device, dtype=torch.float32)
         _call("mcaq_tile_quantize_xchg", x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W, bit_map.data_ptr(),
               Ht, Wt, xchg.local, xchg.world, _ptr(ws), _ptr(pws), _ptr(mask), _stream())
         return y

@@ -348,36 +348,36 @@ def test_cluster_split_is_bit_identical(name, linear, M, W):
 
 # ------------------------------------------------------------------------------ multi-GPU range exchange
 def test_peer_range_exchange_virtual_ranks(M, W):
-    """The in-kernel range exchange (csrc/peer_exchange.cuh) driven by two virtual ranks on one GPU:
-    a batch split in two must quantize exactly like the unsharded batch, over several steps (slot /
-    flag double buffering), and the host-driven publish / merge halves must agree with torch.minimum."""
-    from mcaq_yolo_b200 import constants as K, fused, ops
+    """The in-kernel range exchange (csrc/peer_exchange.cuh) driven by two virtual ranks on one GPU
+    (one stream per rank: each rank's morphology kernel publishes at its start and waits for the other
+    at its end): a batch split in two must quantize exactly like the unsharded batch, over several
+    steps (slot / flag double buffering); the host-driven publish / merge halves must agree with
+    torch.minimum."""
+    from mcaq_yolo_b200 import fused
     from mcaq_yolo_b200.peer import RangeExchange
     c = Case("c4_v8n_smooth")
     a, m, q = M.build_fixture_modules(W, "cuda", grid_size=c.grid)
-    cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_network(m.mapping_network), K.pack_soft_mask(q.soft_mask)
     x = torch.from_numpy(c.x()).cuda()
-    x = torch.cat([x, x * 0.7 + 0.2, x * 1.3 - 0.1, -x], 0).contiguous()        # 4+ images, different ranges
+    x = torch.cat([x, x * 0.7 + 0.2, x * 1.3 - 0.1, -x], 0).contiguous()        # different ranges per shard
     half = x.shape[0] // 2
     shards = [x[:half].contiguous(), x[half:].contiguous()]
     ex = RangeExchange.virtual(c.C, 2)
-    ws = [fused.ScaleWorkspace(c.C, x.device) for _ in range(2)]
+    ws = [None, None]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
     for step in range(3):
         xs = [s * (1.0 + 0.25 * step) for s in shards]
         full = torch.cat(xs, 0)
         with torch.no_grad():
             ref, _ = fused.fused_scale_forward(full, a, m, q, 1.0, None)
-        nets = []
-        for r in range(2):                                    # K1 + K2 of both ranks first ...
-            s_, ab, _ = ops.reduce_planes(xs[r], want_ranges=False)
-            ops._call("mcaq_reduce_planes", xs[r].data_ptr(), ops._dtype_code(xs[r]), xs[r].shape[0], c.C,
-                      xs[r].shape[2], xs[r].shape[3], s_.data_ptr(), ab.data_ptr(), ws[r].keys.data_ptr(), ops._stream())
-            nets.append(ops.morph_fused(s_, ab, c.C, c.grid, cm, mp, sm, 1.0, keys=ws[r].keys, xchg=ex[r]))
-        ys = [ops.tile_quantize_ranges(xs[r], nets[r]["bit_map"], nets[r]["packed"], None, None, nets[r]["mask"],
-                                       xchg=ex[r]) for r in range(2)]     # ... then K3 (waits for both flags)
         torch.cuda.synchronize()
-        assert torch.equal(torch.cat(ys, 0), ref["features_q"]), f"step {step}: sharded != unsharded"
-        assert torch.equal(torch.cat([n["bit_map"] for n in nets], 0), ref["bit_map"])
+        recs = [None, None]
+        for r in range(2):
+            with torch.cuda.stream(streams[r]), torch.no_grad():
+                recs[r], ws[r] = fused.fused_scale_forward(xs[r], a, m, q, 1.0, ws[r], xchg=ex[r])
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat([r_["features_q"] for r_ in recs], 0), ref["features_q"]), \
+            f"step {step}: sharded != unsharded"
+        assert torch.equal(torch.cat([r_["bit_map"] for r_ in recs], 0), ref["bit_map"])
     # host-driven halves
     ex3 = RangeExchange.virtual(8, 3)
     vecs = [torch.randn(16, device="cuda") for _ in range(3)]
