@@ -66,6 +66,17 @@ MCAQ_API int mcaq_ranges_reset(int32_t* keys, int C, void* stream);
 MCAQ_API int mcaq_reduce_planes(const void* x, int dtype, int B, int C, int H, int W,
                        float* sum_plane, float* abs_plane, int32_t* keys, void* stream);
 
+/* channels_last (NHWC memory: B,H,W,C) forms of K1 and K3.  Results are defined to be exactly those
+ * of the NCHW kernels on the same logical tensor (same summation order, same codes).  Covered
+ * geometry: C a multiple of 16 with C / (16 / sizeof(T)) a power of two <= 256 (every YOLOv8
+ * width), 16-byte aligned pointers; otherwise MCAQ_EALIGN (make the tensor NCHW-contiguous). */
+MCAQ_API int mcaq_reduce_planes_nhwc(const void* x, int dtype, int B, int C, int H, int W,
+                                     float* sum_plane, float* abs_plane, int32_t* keys, void* stream);
+MCAQ_API int mcaq_tile_quantize_ranges_nhwc(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                                            const float* bit_map, int Ht, int Wt, const float* packed,
+                                            const float* running_min, const float* running_max,
+                                            const float* mask, void* stream);
+
 /* keys -> packed[0..C) = min, packed[C..2C) = -max  (one MIN all-reduce merges ranks) */
 MCAQ_API int mcaq_ranges_decode(const int32_t* keys, int C, float* packed, void* stream);
 

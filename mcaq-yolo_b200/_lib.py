@@ -20,6 +20,11 @@ PROTOTYPES = {
     "mcaq_ranges_reset": (c_int, [c_void_p, c_int, c_void_p]),
     "mcaq_reduce_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcaq_reduce_planes_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcaq_tile_quantize_ranges_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                               c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p]),
     "mcaq_ranges_decode": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "mcaq_ranges_ema": (c_int, [c_void_p, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "mcaq_build_qtable": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

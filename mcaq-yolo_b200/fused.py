@@ -72,7 +72,7 @@ def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, tempera
     xchg: a peer.RangeExchange when the batch is sharded over the GPUs of a node -- the range merge
     then happens inside K2 / K3 over peer memory instead of a collective between them."""
     B, C, H, W = feat.shape
-    x = feat if feat.is_contiguous() else feat.contiguous()
+    x = ops.as_kernel_layout(feat)            # NCHW-contiguous or channels_last (native NHWC K1 / K3)
     frozen = quantizer._is_frozen() and quantizer.running_min is not None
     sync = (quantizer.sync_ranges and torch.distributed.is_available() and torch.distributed.is_initialized()
             and torch.distributed.get_world_size(quantizer.process_group) > 1)
@@ -81,8 +81,7 @@ def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, tempera
         ws = ScaleWorkspace(C, x.device) if need_ranges else None
     s = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
     a = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
-    ops._call("mcaq_reduce_planes", x.data_ptr(), ops._dtype_code(x), B, C, H, W, s.data_ptr(), a.data_ptr(),
-              ws.keys.data_ptr() if need_ranges else None, ops._stream())
+    ops.reduce_planes_into(x, s, a, ws.keys if need_ranges else None)
     linear = isinstance(mapper, M.LinearBitMapper)
     sm = quantizer.soft_mask if quantizer.smooth_transitions else None
     r = ops.morph_fused(s, a if sm is not None else None, C, analyzer.grid_size,

@@ -61,6 +61,22 @@ def _call(name: str, *args):
         check(rc, name)
 
 
+def is_nhwc(x: torch.Tensor) -> bool:
+    """True when x is a channels_last tensor the NHWC kernels cover (memory (B,H,W,C) dense, C a
+    multiple of 16 with C / (16 / itemsize) a power of two <= 256, 16-byte aligned)."""
+    if x.dim() != 4 or x.is_contiguous() or not x.is_contiguous(memory_format=torch.channels_last):
+        return False
+    C = x.shape[1]
+    vec = 16 // x.element_size()
+    vpp = C // vec
+    return C % 16 == 0 and vpp >= 1 and vpp <= 256 and (vpp & (vpp - 1)) == 0 and x.data_ptr() % 16 == 0
+
+
+def as_kernel_layout(x: torch.Tensor) -> torch.Tensor:
+    """x unchanged if it is NCHW-contiguous or a covered channels_last tensor, else an NCHW copy."""
+    return x if (x.is_contiguous() or is_nhwc(x)) else x.contiguous()
+
+
 def tile_size(H: int, grid_size: int) -> int:
     """morphology.py:359-376."""
     return _lib.load().mcaq_tile_size(int(H), int(grid_size))
@@ -73,7 +89,7 @@ def reduce_planes(x: torch.Tensor, want_ranges: bool = True):
     _need_cuda(x)
     if x.dim() != 4:
         raise ValueError("expected (B,C,H,W)")
-    x = x if x.is_contiguous() else x.contiguous()
+    x = as_kernel_layout(x)
     B, C, H, W = x.shape
     s = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
     a = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
@@ -81,9 +97,15 @@ def reduce_planes(x: torch.Tensor, want_ranges: bool = True):
     if want_ranges:
         keys = torch.empty((2 * C,), device=x.device, dtype=torch.int32)
         _call("mcaq_ranges_reset", keys.data_ptr(), C, _stream())
-    _call("mcaq_reduce_planes", x.data_ptr(), _dtype_code(x), B, C, H, W, s.data_ptr(), a.data_ptr(),
-                                 _ptr(keys), _stream())
+    reduce_planes_into(x, s, a, keys)
     return s, a, keys
+
+
+def reduce_planes_into(x: torch.Tensor, s: torch.Tensor, a: torch.Tensor, keys: torch.Tensor | None):
+    """K1 into caller-owned planes / armed keys; x NCHW-contiguous or covered channels_last."""
+    B, C, H, W = x.shape
+    name = "mcaq_reduce_planes" if x.is_contiguous() else "mcaq_reduce_planes_nhwc"
+    _call(name, x.data_ptr(), _dtype_code(x), B, C, H, W, s.data_ptr(), a.data_ptr(), _ptr(keys), _stream())
 
 
 def ranges_decode(keys: torch.Tensor) -> torch.Tensor:
@@ -317,13 +339,21 @@ def tile_quantize_ranges(x: torch.Tensor, bit_map: torch.Tensor, packed: torch.T
     peer.RangeExchange of world > 1, host-driven use) a one-CTA kernel first merges the ranks'
     published vectors; the fused path passes the already merged `packed` of morph_fused instead."""
     _need_cuda(x, bit_map, packed, running_min, running_max, mask)
-    x = x if x.is_contiguous() else x.contiguous()
+    x = as_kernel_layout(x)
     B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
     bit_map = _f32c(bit_map)
     if packed is None:
         running_min, running_max = _f32c(running_min).reshape(-1), _f32c(running_max).reshape(-1)
     mask = None if mask is None else _f32c(mask)
-    y = torch.empty_like(x) if out is None else out
+    y = torch.empty_like(x) if out is None else out          # empty_like keeps channels_last
+    if not x.is_contiguous():                                 # covered channels_last input: NHWC kernel
+        if xchg is not None and xchg.world > 1:
+            packed = xchg.merged(x.device)
+        if y.stride() != x.stride():
+            raise RuntimeError("channels_last input needs a channels_last output buffer")
+        _call("mcaq_tile_quantize_ranges_nhwc", x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W,
+              bit_map.data_ptr(), Ht, Wt, _ptr(packed), _ptr(running_min), _ptr(running_max), _ptr(mask), _stream())
+        return y
     vec = 4 if x.dtype == torch.float32 else 8
     needs_ws = not ((H * W) % vec == 0 and W % 4 == 0 and W % Wt == 0 and (W // Wt) % 4 == 0)
     ws = torch.empty((7, C, 2), device=x.device, dtype=torch.float32) if needs_ws else None

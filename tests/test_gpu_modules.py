@@ -386,3 +386,34 @@ def test_peer_range_exchange_virtual_ranks(M, W):
     want = torch.minimum(torch.minimum(vecs[0], vecs[1]), vecs[2])
     for e in ex3:
         assert torch.equal(e.merged("cuda"), want)
+
+
+# ------------------------------------------------------------------------------ channels_last (NHWC) inputs
+@pytest.mark.parametrize("name", ["c3_v8n_smooth", "c4_v8n_smooth", "c5_v8n_smooth", "c3_v8s1280_smooth"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_channels_last_matches_nchw(name, dtype, M, W):
+    """channels_last feature maps run through native NHWC forms of K1 and K3 (no layout copy); planes,
+    ranges, bit maps and the quantized map must equal the NCHW path bit for bit, and the output keeps
+    the input's memory format."""
+    from mcaq_yolo_b200 import fused, ops
+    c = Case(name)
+    a, m, q = M.build_fixture_modules(W, "cuda", grid_size=c.grid)
+    x = torch.from_numpy(c.x()).cuda().to(dtype)
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    assert ops.is_nhwc(xcl) and not ops.is_nhwc(x)
+    s0, a0, k0 = ops.reduce_planes(x)
+    s1, a1, k1 = ops.reduce_planes(xcl)
+    assert torch.equal(s0, s1) and torch.equal(a0, a1) and torch.equal(k0, k1)
+    with torch.no_grad():
+        ref, _ = fused.fused_scale_forward(x, a, m, q, 1.0, None)
+        rec, _ = fused.fused_scale_forward(xcl, a, m, q, 1.0, None)
+    assert rec["features_q"].is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(ref["bit_map"], rec["bit_map"]) and torch.equal(ref["complexity"], rec["complexity"])
+    assert torch.equal(ref["features_q"], rec["features_q"])
+    # frozen calibration and no soft mask
+    with torch.no_grad():
+        q(x.float(), ref["bit_map"], training=True)
+        q.freeze_calibration()
+        ref2, _ = fused.fused_scale_forward(x, a, m, q, 1.0, None)
+        rec2, _ = fused.fused_scale_forward(xcl, a, m, q, 1.0, None)
+    assert torch.equal(ref2["features_q"], rec2["features_q"])
