@@ -148,9 +148,14 @@ tile_quantize_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int
                           float sy, float sx, const float* __restrict__ bit_map, NhRanges rg,
                           const float* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* tab = reinterpret_cast<float4*>(smem_raw);         // [7][C] {scale, zero_point, RN(1/scale), -}
+  // {scale, zero_point, RN(1/scale), -} laid out [7][VEC][C / VEC]: for a fixed element index the
+  // lanes of a warp (consecutive vector slots k) read consecutive 16-byte entries -- conflict free
+  float4* tab = reinterpret_cast<float4*>(smem_raw);
+  const int vpp_t = C / VEC;
   for (int i = threadIdx.x; i < 7 * C; i += NH_THREADS) {
-    const int bi = i / C, c = i - bi * C;
+    const int bi = i / C, r = i - bi * C;
+    const int e_ = r / vpp_t, k_ = r - e_ * vpp_t;
+    const int c = k_ * VEC + e_;
     const float mn = rg.packed ? __ldg(rg.packed + c) : __ldg(rg.rmin + c);
     const float mx = rg.packed ? -__ldg(rg.packed + C + c) : __ldg(rg.rmax + c);
     const int half = 1 << (bi + 1);
@@ -188,10 +193,10 @@ tile_quantize_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int
     const uint4 raw = ldg_noalloc(reinterpret_cast<const uint4*>(x) + v);
     float xv[VEC], out[VEC];
     Elem<T>::unpack(raw, xv);
-    const float4* trow = tab + bidx * C + k * VEC;
+    const float4* trow = tab + bidx * C + k;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const float4 p = trow[e];
+      const float4 p = trow[e * vpp];
       const float q = quant_code_fast(xv[e], p.x, p.y, p.z, qmin, qmax);
       float d = dequant(q, p.x, p.y);
       if (HAS_MASK) d = __fmul_rn(d, m);
@@ -248,8 +253,10 @@ static int launch_quant_nhwc(const T* x, T* y, int B, int C, int H, int W, const
                              NhRanges rg, const float* mask, cudaStream_t st) {
   const long long nvec = (long long)B * H * W * (C / VEC);
   const size_t smem = (size_t)7 * C * 16;
-  long long grid = (nvec + NH_THREADS * 8 - 1) / (NH_THREADS * 8);       // ~8 vectors per thread
-  if (grid > (long long)nh_sms() * 16) grid = (long long)nh_sms() * 16;
+  // persistent CTAs (the per-CTA table costs 7*C entries): at least ~16 vectors per thread
+  long long grid = (nvec + NH_THREADS * 16 - 1) / (NH_THREADS * 16);
+  const long long cap = (long long)nh_sms() * (smem > 40 * 1024 ? 3 : 5);
+  if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   const float sy = (float)Ht / (float)H, sx = (float)Wt / (float)W;
   if (mask) {
