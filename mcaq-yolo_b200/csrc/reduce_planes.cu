@@ -92,6 +92,7 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
   const int ngroups = nfull + (tail ? 1 : 0);
   const int npass = (ngroups + G - 1) / G;
   const int nvec = (HW + VEC - 1) / VEC;          // VEC==1 or HW % VEC == 0
+  const long long HWl = HW;
 
   if (RANGES) {
     for (int c = threadIdx.x; c < C; c += NT) { smin[c] = MCAQ_KEY_POS_INF; smax[c] = MCAQ_KEY_NEG_INF; }
@@ -116,13 +117,35 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
       float s[VEC], a[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) { s[e] = 0.f; a[e] = 0.f; }
-      if (gi < ngroups) {
+      if (RMODE != 1 && gi < nfull && __all_sync(0xffffffffu, active)) {
+        // common case (full 16-channel chunk, whole strip inside the image): no predicates, no zero
+        // fill, running pointer
+        typename VecIO<T, VEC>::Raw raw[16];
+        const T* pj = xb + (long long)c0 * HWl;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { raw[j] = VecIO<T, VEC>::load(pj); pj += HWl; }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float d[VEC];
+          VecIO<T, VEC>::unpack(raw[j], d);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            s[e] = __fadd_rn(s[e], d[e]);
+            a[e] = __fadd_rn(a[e], fabsf(d[e]));
+          }
+          if (ACC) mm[j].update(raw[j]);
+        }
+      } else if (gi < ngroups) {
         const int nch = (gi < nfull) ? 16 : tail;
         typename VecIO<T, VEC>::Raw raw[16];
         if (nch == 16) {
+          // running pointer: one 64-bit add per channel instead of re-deriving xb + (c0 + j) * HW
+          const T* pj = xb + (long long)c0 * HWl;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            raw[j] = active ? VecIO<T, VEC>::load(xb + (long long)(c0 + j) * HW) : VecIO<T, VEC>::zero();
+          for (int j = 0; j < 16; ++j) {
+            raw[j] = active ? VecIO<T, VEC>::load(pj) : VecIO<T, VEC>::zero();
+            pj += HWl;
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
