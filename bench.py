@@ -246,9 +246,18 @@ def run_native(args):
     for _slot in range(nslot):
         exchanges = None
         if world > 1 and not args.nccl_ranges and not args.unfused:
-            # batch sharded over the GPUs of the node: ranges merged inside K2 / K3 over peer memory
+            # batch sharded over the GPUs of the node: ranges merged inside K2 over peer memory
             from mcaq_yolo_b200.peer import RangeExchange
-            exchanges = [RangeExchange.create(C) for C, _, _ in shapes]
+            try:
+                exchanges = [RangeExchange.create(C) for C, _, _ in shapes]
+            except RuntimeError as e:        # raised on every rank alike: use the NCCL all-reduce path
+                sys.stderr.write(f"[bench] {e}; falling back to --nccl-ranges\n")
+                args.nccl_ranges = True
+                nslot = 1
+                hots = []
+                exchanges = None
+                hots.append(FusedHotPath(analyzer, mapper, quantizers, temperature=1.0, streams=not args.no_streams))
+                break
         hots.append(FusedHotPath(analyzer, mapper, quantizers, temperature=1.0, streams=not args.no_streams,
                                  exchanges=exchanges, latency=(nslot == 1)))
     hot = hots[0]

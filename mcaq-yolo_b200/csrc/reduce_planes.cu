@@ -65,12 +65,10 @@ struct MinMaxAcc<__nv_bfloat16, 8> {
 // RMODE: 0 no ranges, 1 per-vector warp reduction (any C), 2 per-thread running min / max in
 // registers when the CTA's G warps cover all channel chunks in one pass (a warp then always owns
 // the same 16 channels), reduced across the warp once per CTA
-// four 128-thread CTAs per SM (128 registers) keep more loads in flight than three at 160 registers
-#ifndef K1_MINB
-#define K1_MINB 4
-#endif
+// 512 resident threads per SM at <= 128 registers for every variant (G = 4: four CTAs, G = 8: two,
+// G = 16: one): more CTAs with 16 loads in flight each beat fewer CTAs with more registers
 template <typename T, int VEC, int G, int RMODE>
-__global__ void __launch_bounds__(32 * G, (G == 4 && K1_MINB > 1) ? K1_MINB : 1)
+__global__ void __launch_bounds__(32 * G, (16 / G) > 0 ? (16 / G) : 1)
 reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
                      float* __restrict__ sum_plane, float* __restrict__ abs_plane,
                      int* __restrict__ keys, int strips_per_image, long long total_strips) {

@@ -48,18 +48,30 @@ class RangeExchange:
         _lib.check(lib.mcaq_xchg_export(local, handle), "mcaq_xchg_export")
         handles = [None] * world
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        ptrs, opened = [], []
-        for r, h in enumerate(handles):
-            if r == rank:
-                ptrs.append(local)
-                continue
-            out = ctypes.c_void_p()
-            _lib.check(lib.mcaq_xchg_open(ctypes.create_string_buffer(h, 64), ctypes.byref(out)), "mcaq_xchg_open")
-            ptrs.append(int(out.value))
-            opened.append(int(out.value))
+        ptrs, opened, err = [], [], None
+        try:
+            for r, h in enumerate(handles):
+                if r == rank:
+                    ptrs.append(local)
+                    continue
+                out = ctypes.c_void_p()
+                _lib.check(lib.mcaq_xchg_open(ctypes.create_string_buffer(h, 64), ctypes.byref(out)), "mcaq_xchg_open")
+                ptrs.append(int(out.value))
+                opened.append(int(out.value))
+        except RuntimeError as e:          # no peer access between two GPUs, IPC disabled, ...
+            err = e
+        # agree on the outcome (also the barrier: nobody publishes before every rank has mapped every
+        # buffer); a failure on any rank fails the construction on all of them, so callers can fall back
+        # to the all-reduce path consistently
+        ok = torch.tensor([0 if err else 1], device=torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            for p in opened:
+                lib.mcaq_xchg_close(p)
+            lib.mcaq_xchg_free(local)
+            raise RuntimeError(f"peer range exchange unavailable on this node ({err or 'failed on another rank'})")
         ex = cls(C, rank, world, local, ptrs)
         ex._opened = opened
-        dist.barrier(group)            # nobody publishes before every rank has mapped every buffer
         return ex
 
     @classmethod
