@@ -460,9 +460,32 @@ def run_native(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of the same
+        # workload (profiles/, per launch); None when the capture is absent or is for another shape
+        traffic, traffic_note = None, None
+        cap = os.path.join(ROOT, "profiles", "r01_ncu_full_step_%s_raw.csv" % ("bf16" if dtype_name == "bf16" else "f32"))
+        if args.workload == "yolov8n_640_b64_bf16" and os.path.exists(cap):
+            try:
+                import csv
+                rows = list(csv.reader(open(cap)))
+                hdr, units = rows[0], rows[1]
+                ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+                for r in rows[2:]:
+                    if "tile_quantize_vec_kernel" in r[ik]:          # first K3 launch of the step = C3
+                        scale_r = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(units[ir], 1e6)
+                        scale_w = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(units[iw], 1e6)
+                        traffic = float(r[ir]) * scale_r + float(r[iw]) * scale_w
+                        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of the C3 launch in %s; reads equal the "
+                                        "algorithmic input bytes, the write side is below the %d MB stored because the "
+                                        "profiled launch ends with most of y still dirty in the 126 MB L2"
+                                        % (os.path.basename(cap), dom_bytes // 2 // 1000000))
+                        break
+            except Exception:
+                traffic = None
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "tile_quantize_vec_kernel (K3) on C3 %dx%dx%dx%d %s" % (B, *C3, dtype_name),
+            "traffic": traffic, "traffic_note": traffic_note,
+            "kernel": "tile_quantize_vec_kernel (K3) on C3 %dx%dx%dx%d %s" % (B, *C3, dtype_name),
             "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms, "peak_source": peak_src,
             "how": "CUDA events around a graph replay of %d launches over rotating inputs (cold L2)" % INPUT_SETS,
             "k1_reduce_planes_c3": {"achieved": (esize * B * C3[0] * C3[1] * C3[2]) / (k1_c3 * 1e-3) / 1e9,
