@@ -41,6 +41,7 @@ extern "C" {
 #define MCAQ_EALIGN   (-2)   /* pointer not 16-byte aligned */
 #define MCAQ_ETOOBIG  (-3)   /* plane does not fit the on-chip budget of the morphology kernel */
 #define MCAQ_EDTYPE   (-4)
+#define MCAQ_EGEOM    (-5)   /* geometry / alignment outside the vector path of an entry point that has no scalar form */
 
 /* number of floats in the constant block expected by the morphology kernels, and the
  * packed-parameter block sizes of the three small networks (see mcaq_b200/constants.py) */
@@ -122,6 +123,24 @@ MCAQ_API int mcaq_tile_quantize_train_bwd(const void* grad_y, const void* x, voi
                                  int B, int C, int H, int W,
                                  const float* bit_map, int Ht, int Wt, const float* qtable,
                                  const float* mask, float* dbit, float* dmask, void* stream);
+
+/* Training forward / backward with the feature-level distillation term folded in (SURVEY 8f-3;
+ * train.py:599-610: F.mse_loss(features_q.float(), teacher.float()) per hooked layer):
+ *   forward : *kd_sum += sum (y - teacher)^2  (one fp64 atomic per CTA; caller zeroes it and divides by numel)
+ *   backward: g_t = grad_y + (*kd_coef) * (y - teacher), y recomputed from x, then as the plain backward;
+ *             kd_coef is a DEVICE scalar = dL/d(mse) * 2 / numel, so nothing synchronises.
+ * teacher is fp32 (B,C,H,W) whatever the dtype of x (the reference's teacher runs in fp32).
+ * Vector geometry only (16-byte aligned pointers, H*W % VEC == 0, W % 4 == 0, W % Wt == 0,
+ * (W/Wt) % 4 == 0: every YOLO feature map): otherwise MCAQ_EGEOM and the caller composes the plain
+ * entry points with its own MSE. */
+MCAQ_API int mcaq_tile_quantize_train_fwd_kd(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                                 const float* bit_map, int Ht, int Wt, const float* qtable,
+                                 const float* mask, const float* teacher, double* kd_sum, void* stream);
+MCAQ_API int mcaq_tile_quantize_train_bwd_kd(const void* grad_y, const void* x, void* grad_x, int dtype,
+                                 int B, int C, int H, int W,
+                                 const float* bit_map, int Ht, int Wt, const float* qtable,
+                                 const float* mask, const float* teacher, const float* kd_coef,
+                                 float* dbit, float* dmask, void* stream);
 
 /* The reference's launcher, same argument list (mcaq_kernel.cu:102-111, MCAQPlugin.cpp:15-24).
  * Semantics follow the reference's PyTorch path (round-half-even, IEEE division). */
@@ -218,6 +237,10 @@ MCAQ_API void mcaq_debug_stage_clocks(long long* dev_buf);
 /* debug / tuning: force the number of CTAs (cluster size 1, 2, 4 or 8) an image is split over in
  * the morphology kernel; 0 = automatic */
 MCAQ_API void mcaq_debug_cluster_split(int ns);
+
+/* debug / tests: 1 = route the training forward / backward through the scalar kernels even when the
+ * vector path applies (the two must agree: y and dx bit for bit) */
+MCAQ_API void mcaq_debug_train_scalar(int on);
 
 /* split policy of the morphology kernel: 0 (default) throughput -- one CTA per image unless the batch
  * is too small to fill half the GPU (for callers that keep several launches in flight); 1 latency --

@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libmcaq_b200.so")
 
 MCAQ_F32, MCAQ_BF16 = 0, 1
+MCAQ_EGEOM = -5
 
 # name -> (restype, argtypes): one entry per symbol declared in include/mcaq_b200.h
 PROTOTYPES = {
@@ -41,6 +42,13 @@ PROTOTYPES = {
     "mcaq_tile_quantize_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                              c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p]),
+    "mcaq_tile_quantize_train_fwd_kd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p]),
+    "mcaq_tile_quantize_train_bwd_kd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_void_p, c_void_p]),
+    "mcaq_debug_train_scalar": (None, [c_int]),
     "launch_spatial_quantization": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mcaq_morph_phi": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

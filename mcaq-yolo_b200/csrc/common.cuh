@@ -70,6 +70,7 @@ template <> struct Elem<float> {
                       __float_as_uint(f[2]), __float_as_uint(f[3]));
   }
   __device__ __forceinline__ static float load1(const float* p) { return *p; }
+  __device__ __forceinline__ static float round1(float v) { return v; }      // value as stored
   __device__ __forceinline__ static void store1(float* p, float v) { *p = v; }
 };
 template <> struct Elem<__nv_bfloat16> {
@@ -89,6 +90,7 @@ template <> struct Elem<__nv_bfloat16> {
     return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
   }
   __device__ __forceinline__ static float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  __device__ __forceinline__ static float round1(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
   __device__ __forceinline__ static void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 

@@ -108,6 +108,8 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
     const bool active = v < nvec;
     const T* xb = x + ((long long)b * C) * HW + (long long)v * VEC;
 
+    // CTA-uniform: all of C in one pass of full chunks and the whole strip inside the image
+    const bool fastfold = VEC > 1 && npass == 1 && tail == 0 && nfull == G && (sv + 1) * 32 <= nvec;
     float acc0[NOUT], acc1[NOUT], acc2[NOUT];
 #pragma unroll
     for (int k = 0; k < NOUT; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; acc2[k] = 0.f; }
@@ -190,6 +192,40 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
 #pragma unroll
       for (int e = 0; e < VEC; ++e) { ps[e] = s[e]; pa[e] = a[e]; }
       __syncthreads();
+      if (fastfold) {
+        // every chunk is full, one pass covers C and the strip lies inside the image (every YOLO
+        // width): thread t folds FV consecutive outputs, P_0 + P_1 + ... in chunk order starting
+        // from 0 -- the value of the generic fold below ((0 + acc1) + 0, or 0 + acc2 after 16 chunks)
+        constexpr int NPT = 2 * STRIP / NT;                    // outputs per thread: 2 * VEC / G
+        constexpr int FV = NPT >= 4 ? 4 : (NPT >= 2 ? 2 : 1);
+        constexpr int NIT = NPT >= 4 ? NPT / 4 : 1;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int o = (it * NT + threadIdx.x) * FV;
+          if (o < 2 * STRIP) {
+            const int plane = o / STRIP, q = o - plane * STRIP;
+            float r[FV];
+#pragma unroll
+            for (int e = 0; e < FV; ++e) r[e] = 0.f;
+#pragma unroll
+            for (int w = 0; w < G; ++w) {
+              const float* src = part + (plane * G + w) * STRIP + q;
+              float p[FV];
+              if (FV == 4) *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(src);
+              else if (FV == 2) *reinterpret_cast<float2*>(p) = *reinterpret_cast<const float2*>(src);
+              else p[0] = src[0];
+#pragma unroll
+              for (int e = 0; e < FV; ++e) r[e] = __fadd_rn(r[e], p[e]);
+            }
+            float* dst = (plane ? abs_plane : sum_plane) + (long long)b * HW + (long long)sv * STRIP + q;
+            if (FV == 4) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<float4*>(r);
+            else if (FV == 2) *reinterpret_cast<float2*>(dst) = *reinterpret_cast<float2*>(r);
+            else dst[0] = r[0];
+          }
+        }
+        __syncthreads();
+        break;
+      }
       // fold in chunk order (ATen multi_row_sum, level_step 16)
 #pragma unroll
       for (int k = 0; k < NOUT; ++k) {
@@ -215,7 +251,7 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
 #pragma unroll
     for (int k = 0; k < NOUT; ++k) {
       const int o = threadIdx.x + k * NT;
-      if (o < 2 * STRIP) {
+      if (!fastfold && o < 2 * STRIP) {
         const int plane = o / STRIP, q = o - plane * STRIP;
         const long long pix = (long long)sv * STRIP + q;
         if (pix < HW) {

@@ -11,19 +11,13 @@
 // are 1/C of that and stay in L1/L2.
 #include "common.cuh"
 #include "peer_exchange.cuh"
+#include "tile_quantize.cuh"
 
 namespace mcaq {
 
 constexpr int QCHUNK = 16;   // channels per thread
 constexpr int QUNROLL = 4;   // independent loads in flight per thread
 constexpr int QTHREADS = 128;
-
-struct QGeom {
-  int B, C, H, W, HW, Ht, Wt;
-  float sy, sx;              // (float)Ht/H, (float)Wt/W
-  long long nvec_total;      // B * HW / VEC
-  int nvec;                  // HW / VEC
-};
 
 template <typename T, int VEC>
 __device__ __forceinline__ void load_elems(const T* p, float* f, bool inplace) {
@@ -78,12 +72,6 @@ __device__ __forceinline__ void make_ctx(const QGeom& g, int b, int pix, const f
       for (int e = 0; e < VEC; ++e) ctx.m[e] = __ldg(mp + e);
     }
   }
-}
-
-__device__ __forceinline__ void bit_limits(int bidx, float& qmin, float& qmax) {
-  const int half = 1 << (bidx + 1);            // 2^(bits-1)
-  qmin = -(float)half;
-  qmax = (float)(half - 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -184,11 +172,6 @@ __device__ __forceinline__ float2 qparams_from_ranges(const QRanges& rg, int C, 
   const float zp = __fsub_rn(qmin, __fdiv_rn(mn, scale));
   return make_float2(scale, fminf(fmaxf(zp, qmin), qmax));
 }
-
-constexpr int QV_THREADS = 256;
-constexpr int QV_CHUNK = 16;
-constexpr int QV_UNROLL = 8;
-constexpr int QV_ROW = QV_CHUNK + 1;
 
 template <typename T, int VEC, bool HAS_MASK, bool CODES>
 __global__ void __launch_bounds__(QV_THREADS, K3_MINB)
@@ -297,23 +280,6 @@ tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
 // ---------------------------------------------------------------------------------------------
 // training forward: pre = (1-f)*Q_lo + f*Q_hi ; y = pre*m   (quantization.py:709-727, 742-744)
 // ---------------------------------------------------------------------------------------------
-struct FracCtx {
-  int lo_idx, hi_idx;     // table rows of floor(b) and min(floor(b)+1, 8)
-  float f, omf;           // frac and (1 - frac)
-};
-
-__device__ __forceinline__ FracCtx frac_ctx(float bits) {
-  FracCtx fc;
-  const float bf = floorf(bits);
-  fc.f = __fsub_rn(bits, bf);
-  fc.omf = __fsub_rn(1.f, fc.f);
-  int lo = (int)bf;
-  lo = lo < 2 ? 2 : (lo > 8 ? 8 : lo);
-  fc.lo_idx = lo - 2;
-  fc.hi_idx = (lo + 1 <= 8) ? lo - 1 : lo - 2;   // q_hi = q_lo when floor(b)+1 > 8
-  return fc;
-}
-
 __device__ __forceinline__ void frac_quant(float xv, const float2& plo, const float2& phi, const FracCtx& fc,
                                            float& qlo, float& qhi) {
   float mn, mx;
@@ -412,20 +378,9 @@ tile_quantize_train_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x
     }
     if (HAS_MASK) atomicAdd(dmask + (long long)b * g.HW + pix, acc_m);
   }
-  // d(bit_map): segmented warp reduction over contiguous runs of lanes in the same tile, then one
-  // atomicAdd per run (tile_w >= 4, so at most 8 runs per warp)
-  const int lane = threadIdx.x & 31;
-  const int tile_id = ok ? ty * g.Wt + tx : -1;
-  float v = acc_bit;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const float t = __shfl_down_sync(0xffffffffu, v, off);
-    const int idn = __shfl_down_sync(0xffffffffu, tile_id, off);
-    if (lane + off < 32 && idn == tile_id) v += t;
-  }
-  const int idp = __shfl_up_sync(0xffffffffu, tile_id, 1);
-  const bool head = lane == 0 || idp != tile_id;
-  if (ok && head) atomicAdd(dbit + ((long long)b * g.Ht + ty) * g.Wt + tx, v);
+  // d(bit_map): warp reduction over contiguous runs of lanes in the same tile, then one atomicAdd
+  // per run (tile_w >= 4, so at most 8 runs per warp)
+  run_reduce_atomic(acc_bit, ok ? (b * g.Ht + ty) * g.Wt + tx : -1, dbit);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -469,16 +424,6 @@ spatial_quant_compat_kernel(const float* __restrict__ x, const float* __restrict
     if (HAS_MASK) d = __fmul_rn(d, ctx.m[0]);
     y[base + (long long)c * g.HW] = d;
   }
-}
-
-static QGeom make_geom(int B, int C, int H, int W, int Ht, int Wt, int VEC) {
-  QGeom g;
-  g.B = B; g.C = C; g.H = H; g.W = W; g.HW = H * W; g.Ht = Ht; g.Wt = Wt;
-  g.sy = (float)Ht / (float)H;
-  g.sx = (float)Wt / (float)W;
-  g.nvec = (H * W) / VEC;
-  g.nvec_total = (long long)B * g.nvec;
-  return g;
 }
 
 template <typename T, int VEC>
@@ -541,13 +486,6 @@ static int launch_train_bwd(const T* gy, const T* x, T* gx, int B, int C, int H,
 static bool vec_ok(const void* a, const void* b, int HW, int W, int VEC, const void* mask) {
   return ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)mask & 15) == 0 &&
          HW % VEC == 0 && W % VEC == 0;
-}
-
-// inference vector path: every aligned 4-pixel segment must lie in one row and one tile
-static bool seg_ok(const void* a, const void* b, const void* mask, const void* codes, int HW, int W, int Wt,
-                   int VEC) {
-  return ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)mask & 15) == 0 &&
-         ((uintptr_t)codes & 7) == 0 && HW % VEC == 0 && W % 4 == 0 && W % Wt == 0 && (W / Wt) % 4 == 0;
 }
 
 }  // namespace mcaq
@@ -630,6 +568,9 @@ extern "C" int mcaq_tile_quantize_train_fwd(const void* x, void* y, int dtype, i
   int rc = check_common(x, y, B, C, H, W, bit_map, Ht, Wt, qtable);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if ((dtype == MCAQ_F32 || dtype == MCAQ_BF16) &&
+      train_vec_ok(x, y, nullptr, mask, nullptr, nullptr, dtype, H, W, Wt))
+    return train_fwd_vec(x, y, dtype, B, C, H, W, bit_map, Ht, Wt, qtable, mask, nullptr, nullptr, st);
   if (dtype == MCAQ_F32) {
     if (vec_ok(x, y, H * W, W, 4, nullptr))
       return launch_train_fwd<float, 4>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
@@ -651,6 +592,10 @@ extern "C" int mcaq_tile_quantize_train_bwd(const void* grad_y, const void* x, v
   if (rc) return rc;
   if (!grad_y || !dbit || (mask && !dmask)) return MCAQ_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  if ((dtype == MCAQ_F32 || dtype == MCAQ_BF16) &&
+      train_vec_ok(grad_y, grad_x, x, mask, dmask, nullptr, dtype, H, W, Wt))
+    return train_bwd_vec(grad_y, x, grad_x, dtype, B, C, H, W, bit_map, Ht, Wt, qtable, mask, nullptr, nullptr,
+                         dbit, dmask, st);
   if (dtype == MCAQ_F32)
     return launch_train_bwd<float>((const float*)grad_y, (const float*)x, (float*)grad_x, B, C, H, W, bit_map,
                                    Ht, Wt, qtable, mask, dbit, dmask, st);

@@ -114,21 +114,17 @@ class MorphologicalComplexityAnalyzer(nn.Module):
 
     def bilateral_filter(self, complexity_map: torch.Tensor, sigma_spatial: float = 2.0,
                          sigma_range: float = 0.1, kernel_size: int = 5) -> torch.Tensor:
-        """Differentiable torch bilateral filter for the training path (tiny (B,ht,wt) maps)."""
+        """Differentiable torch bilateral filter for the training path (tiny (B,ht,wt) maps;
+        morphology.py:309-354): all k*k neighbours at once, so a handful of launches per call."""
         B, H, W = complexity_map.shape
         r = kernel_size // 2
-        padded = F.pad(complexity_map.unsqueeze(1), (r, r, r, r), mode="replicate")
+        nb = F.unfold(F.pad(complexity_map.unsqueeze(1), (r, r, r, r), mode="replicate"), kernel_size)
+        centre = complexity_map.reshape(B, 1, H * W)
         ax = torch.arange(kernel_size, device=complexity_map.device, dtype=torch.float32) - r
-        num = torch.zeros_like(complexity_map)
-        den = torch.zeros_like(complexity_map)
-        for ky in range(kernel_size):
-            for kx in range(kernel_size):
-                nb = padded[:, 0, ky:ky + H, kx:kx + W]
-                sw = math.exp(-(float(ax[ky]) ** 2 + float(ax[kx]) ** 2) / (2 * sigma_spatial ** 2))
-                wgt = sw * torch.exp(-((nb - complexity_map) ** 2) / (2 * sigma_range ** 2))
-                num = num + wgt * nb
-                den = den + wgt
-        return num / (den + 1e-8)
+        dist2 = ax.view(-1, 1) ** 2 + ax.view(1, -1) ** 2
+        w_space = torch.exp(-dist2 / (2 * sigma_spatial ** 2)).reshape(1, -1, 1)
+        wgt = w_space * torch.exp(-((nb - centre) ** 2) / (2 * sigma_range ** 2))
+        return ((wgt * nb).sum(dim=1) / (wgt.sum(dim=1) + 1e-8)).reshape(B, H, W)
 
     def score_image(self, features: torch.Tensor) -> torch.Tensor:
         """Deterministic Eq.(8) score per image (morphology.py:923-937)."""
@@ -319,6 +315,32 @@ class _FractionalQuant(torch.autograd.Function):
         return dx, dbit.to(bit_map.dtype), dmask, None
 
 
+class _FractionalQuantKD(torch.autograd.Function):
+    """(y, mse(y, teacher)) in one forward kernel and one backward kernel: the feature-level
+    distillation term of train.py:599-610 folded into the fractional-bit quantiser, so the loss
+    never re-reads y (forward) and its gradient 2 (y - t) / N is formed in registers (backward)."""
+
+    @staticmethod
+    def forward(ctx, x, bit_map, mask, qtable, teacher):
+        m3 = None if mask is None else mask.reshape(mask.shape[0], mask.shape[-2], mask.shape[-1])
+        y, kd_sum = ops.tile_quantize_train_fwd_kd(x, bit_map, qtable, m3, teacher)
+        ctx.save_for_backward(x, bit_map, qtable, teacher, *(() if m3 is None else (m3,)))
+        ctx.has_mask = m3 is not None
+        ctx.mask_shape = None if mask is None else mask.shape
+        return y, (kd_sum / y.numel()).float()
+
+    @staticmethod
+    def backward(ctx, gy, gmse):
+        saved = ctx.saved_tensors
+        x, bit_map, qtable, teacher = saved[:4]
+        m3 = saved[4] if ctx.has_mask else None
+        coef = gmse.float() * (2.0 / x.numel())                 # device scalar: no host round trip
+        dx, dbit, dmask = ops.tile_quantize_train_bwd_kd(gy, x, bit_map, qtable, m3, teacher, coef)
+        if dmask is not None:
+            dmask = dmask.reshape(ctx.mask_shape)
+        return dx, dbit.to(bit_map.dtype), dmask, None, None
+
+
 class SpatialAdaptiveQuantization(nn.Module):
     """Eq.19  X_q(p) = m(p) * Q_{b_T(p)}(X(p))  (quantization.py:242-754), `minmax` calibration,
     per-channel ranges.  `process_group` (optional) all-reduces the per-channel ranges so that a
@@ -347,6 +369,11 @@ class SpatialAdaptiveQuantization(nn.Module):
         self.register_buffer("calibration_histogram", None)
         self.histogram_bins = 2048
         self._frozen_py = None      # host copy of stats_frozen: no device sync on the hot path
+        # feature-level distillation (train.py:599-610), optional: set `kd_teacher` to the teacher's
+        # fp32 feature map of this layer before the student's forward; the training forward then
+        # also leaves mse(features_q, teacher) in `kd_feature_loss` (differentiable)
+        self.kd_teacher = None
+        self.kd_feature_loss = None
 
     # -- state ---------------------------------------------------------------------------------
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
@@ -412,10 +439,19 @@ class SpatialAdaptiveQuantization(nn.Module):
             mask = self.soft_mask(bit_map, x)
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or bit_map.requires_grad or (mask is not None and mask.requires_grad))
+        self.kd_feature_loss = None
         if training or needs_grad:
             # fractional-bit compose; with an integer map it reduces to per-tile STE quantisation
-            y = _FractionalQuant.apply(x if x.is_contiguous() else x.contiguous(),
-                                       bit_map.float(), mask, qtable)
+            xc = x if x.is_contiguous() else x.contiguous()
+            t = self.kd_teacher
+            if t is not None and t.shape == x.shape:
+                if ops.kd_geometry_ok(xc, bit_map):
+                    y, self.kd_feature_loss = _FractionalQuantKD.apply(xc, bit_map.float(), mask, qtable, t.detach())
+                else:       # geometry outside the vector kernels: same loss, composed
+                    y = _FractionalQuant.apply(xc, bit_map.float(), mask, qtable)
+                    self.kd_feature_loss = F.mse_loss(y.float(), t.detach().float())
+            else:
+                y = _FractionalQuant.apply(xc, bit_map.float(), mask, qtable)
         else:
             m3 = None if mask is None else mask.reshape(mask.shape[0], mask.shape[-2], mask.shape[-1])
             y = ops.tile_quantize(x, bit_map, qtable, m3)
@@ -444,7 +480,11 @@ def mcaq_hook_forward(feat: torch.Tensor, analyzer, mapper, quantizer, temperatu
         complexity = ((complexity - lo) / (hi - lo + 1e-8)).clamp(0.0, 1.0)
     bit_map = mapper(complexity, temperature, return_continuous=training)
     feat_q = quantizer(feat, bit_map, training=training or calibrating) if quantize else feat
-    return {"layer": layer, "complexity": complexity, "bit_map": bit_map, "features_q": feat_q}
+    rec = {"layer": layer, "complexity": complexity, "bit_map": bit_map, "features_q": feat_q}
+    kd = getattr(quantizer, "kd_feature_loss", None) if quantize else None
+    if kd is not None:
+        rec["kd_feature_loss"] = kd        # extra key: mse(features_q, quantizer.kd_teacher), fused in K3
+    return rec
 
 
 class _McaqCudaOpsShim:

@@ -185,6 +185,46 @@ def tile_quantize_train_fwd(x, bit_map, qtable, mask=None):
     return y
 
 
+def kd_geometry_ok(x: torch.Tensor, bit_map: torch.Tensor) -> bool:
+    """Whether the distillation-fused entry points cover this geometry (the vector path of K3:
+    every aligned group of 4 pixels inside one row and one tile; every YOLO feature map)."""
+    H, W, Wt = int(x.shape[2]), int(x.shape[3]), int(bit_map.shape[-1])
+    vec = 16 // x.element_size()
+    return (H * W) % vec == 0 and W % 4 == 0 and W % Wt == 0 and (W // Wt) % 4 == 0
+
+
+def _teacher_arg(teacher, x):
+    _need_cuda(teacher)
+    if teacher.shape != x.shape:
+        raise RuntimeError(f"teacher must have the shape of x {tuple(x.shape)}, got {tuple(teacher.shape)}")
+    return _f32c(teacher)
+
+
+def tile_quantize_train_fwd_kd(x, bit_map, qtable, mask, teacher):
+    """Training forward with the feature-distillation term (train.py:599-610) folded in: returns
+    (y, sum((y - teacher)^2) as a 0-dim fp64 tensor).  mse = sum / y.numel()."""
+    _need_cuda(x, bit_map, qtable, mask)
+    x = x if x.is_contiguous() else x.contiguous()
+    B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
+    bit_map = _f32c(bit_map)
+    mask = None if mask is None else _f32c(mask)
+    teacher = _teacher_arg(teacher, x)
+    y = torch.empty_like(x)
+    kd_sum = torch.zeros((), device=x.device, dtype=torch.float64)
+    _call("mcaq_tile_quantize_train_fwd_kd", x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W,
+          bit_map.data_ptr(), Ht, Wt, qtable.data_ptr(), _ptr(mask), teacher.data_ptr(), kd_sum.data_ptr(),
+          _stream())
+    return y, kd_sum
+
+
+def _bwd_outputs(x, bit_map, mask):
+    B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
+    dx = torch.empty_like(x)
+    dbit = torch.zeros((B, Ht, Wt), device=x.device, dtype=torch.float32)
+    dmask = torch.zeros((B, H, W), device=x.device, dtype=torch.float32) if mask is not None else None
+    return dx, dbit, dmask
+
+
 def tile_quantize_train_bwd(grad_y, x, bit_map, qtable, mask=None):
     """Returns (dx, dbit (B,Ht,Wt) fp32, dmask (B,H,W) fp32 or None)."""
     _need_cuda(grad_y, x, bit_map, qtable, mask)
@@ -195,13 +235,31 @@ def tile_quantize_train_bwd(grad_y, x, bit_map, qtable, mask=None):
     B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
     bit_map = _f32c(bit_map)
     mask = None if mask is None else _f32c(mask)
-    dx = torch.empty_like(x)
-    dbit = torch.zeros((B, Ht, Wt), device=x.device, dtype=torch.float32)
-    dmask = torch.zeros((B, H, W), device=x.device, dtype=torch.float32) if mask is not None else None
+    dx, dbit, dmask = _bwd_outputs(x, bit_map, mask)
     _call("mcaq_tile_quantize_train_bwd", grad_y.data_ptr(), x.data_ptr(), dx.data_ptr(),
                                                    _dtype_code(x), B, C, H, W, bit_map.data_ptr(), Ht, Wt,
                                                    qtable.data_ptr(), _ptr(mask), dbit.data_ptr(), _ptr(dmask),
                                                    _stream())
+    return dx, dbit, dmask
+
+
+def tile_quantize_train_bwd_kd(grad_y, x, bit_map, qtable, mask, teacher, kd_coef):
+    """Backward of (y, mse) jointly: g_t = grad_y + kd_coef * (y - teacher) with y recomputed from x.
+    kd_coef: 0-dim / 1-element fp32 CUDA tensor = dL/d(mse) * 2 / numel (stays on the device)."""
+    _need_cuda(grad_y, x, bit_map, qtable, mask, kd_coef)
+    x = x if x.is_contiguous() else x.contiguous()
+    grad_y = grad_y if grad_y.is_contiguous() else grad_y.contiguous()
+    if grad_y.dtype != x.dtype:
+        grad_y = grad_y.to(x.dtype)
+    B, C, H, W, Ht, Wt = _bitmap_args(x, bit_map)
+    bit_map = _f32c(bit_map)
+    mask = None if mask is None else _f32c(mask)
+    teacher = _teacher_arg(teacher, x)
+    kd_coef = _f32c(kd_coef.reshape(1))
+    dx, dbit, dmask = _bwd_outputs(x, bit_map, mask)
+    _call("mcaq_tile_quantize_train_bwd_kd", grad_y.data_ptr(), x.data_ptr(), dx.data_ptr(), _dtype_code(x),
+          B, C, H, W, bit_map.data_ptr(), Ht, Wt, qtable.data_ptr(), _ptr(mask), teacher.data_ptr(),
+          kd_coef.data_ptr(), dbit.data_ptr(), _ptr(dmask), _stream())
     return dx, dbit, dmask
 
 
