@@ -133,4 +133,48 @@ __device__ __forceinline__ float dequant(float q, float scale, float zp) {
   return __fmul_rn(__fsub_rn(q, zp), scale);
 }
 
+// ---- packed fp32 pairs (sm_100: FMUL2 / FADD2 / FFMA2) ---------------------------------------
+// One instruction performs two independent IEEE round-to-nearest fp32 operations on a 64-bit
+// register pair, so results are bit-identical to the scalar forms at half the issue slots.  The
+// compiler does not form these on its own; ptxas maps the {lo, hi} moves onto adjacent registers.
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mul.rn.f32x2 rd, ra, rb;\n"
+      " mov.b64 {%0,%1}, rd;}" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n add.rn.f32x2 rd, ra, rb;\n"
+      " mov.b64 {%0,%1}, rd;}" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mov.b64 rc, {%6,%7};\n"
+      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// a + b where a or b is itself a packed product: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
+// one FFMA2 even under -fmad=false (seen in the SASS: one rounding instead of two; it also folds
+// a * 1 + b back).  Scalar add.rn after a packed multiply is left alone, so these adds stay scalar.
+__device__ __forceinline__ float2 fadd2_sep(float2 a, float2 b) {
+  return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+
+// quant_code_fast for two elements: the same seven roundings per element, issued as pairs
+__device__ __forceinline__ float2 quant_code_fast2(float2 x, float scale, float zp, float rinv, float qmin,
+                                                   float qmax) {
+  const float2 s2 = splat2(scale), r2 = splat2(rinv);
+  const float2 q0 = fmul2(x, r2);
+  const float2 r = ffma2(make_float2(-q0.x, -q0.y), s2, x);
+  const float2 t = fadd2(ffma2(r, r2, q0), splat2(zp));
+  return make_float2(fminf(fmaxf(rintf(t.x), qmin), qmax), fminf(fmaxf(rintf(t.y), qmin), qmax));
+}
+__device__ __forceinline__ float2 dequant2(float2 q, float scale, float zp) {
+  return fmul2(fadd2(q, splat2(-zp)), splat2(scale));
+}
+
 }  // namespace mcaq

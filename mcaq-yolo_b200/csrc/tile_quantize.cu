@@ -232,12 +232,14 @@ tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
       const float4 p = tab[trow[s] + c];
       uint32_t cp = 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float q = quant_code_fast(xv[4 * s + e], p.x, p.y, p.z, qmin[s], qmax[s]);
-        float d = dequant(q, p.x, p.y);
-        if (HAS_MASK) d = __fmul_rn(d, m[4 * s + e]);
-        out[4 * s + e] = d;
-        if (CODES) cp |= ((uint32_t)(int)q & 0xffu) << (8 * e);
+      for (int e = 0; e < 4; e += 2) {
+        const int i = 4 * s + e;
+        const float2 q = quant_code_fast2(make_float2(xv[i], xv[i + 1]), p.x, p.y, p.z, qmin[s], qmax[s]);
+        float2 d = dequant2(q, p.x, p.y);
+        if (HAS_MASK) d = fmul2(d, make_float2(m[i], m[i + 1]));
+        out[i] = d.x;
+        out[i + 1] = d.y;
+        if (CODES) cp |= (((uint32_t)(int)q.x & 0xffu) << (8 * e)) | (((uint32_t)(int)q.y & 0xffu) << (8 * e + 8));
       }
       cpack[s] = cp;
     }

@@ -77,6 +77,13 @@ __device__ __forceinline__ void frac_pair(float xv, const float4& plo, const flo
   qhi = dequant(quant_code_fast(xv, phi.x, phi.y, phi.z, mn_hi, mx_hi), phi.x, phi.y);
 }
 
+// the same for two elements, packed fp32 pairs (identical roundings)
+__device__ __forceinline__ void frac_pair2(float2 xv, const float4& plo, const float4& phi, float mn_lo, float mx_lo,
+                                           float mn_hi, float mx_hi, float2& qlo, float2& qhi) {
+  qlo = dequant2(quant_code_fast2(xv, plo.x, plo.y, plo.z, mn_lo, mx_lo), plo.x, plo.y);
+  qhi = dequant2(quant_code_fast2(xv, phi.x, phi.y, phi.z, mn_hi, mx_hi), phi.x, phi.y);
+}
+
 __device__ __forceinline__ void unpack4(const uint4& v, float* f) {
   f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
   f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
@@ -125,11 +132,15 @@ train_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g, const 
         const float4 plo = tab[ctx.lo_row[s] + c];
         const float4 phi = tab[ctx.hi_row[s] + c];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float qlo, qhi;
-          frac_pair(xv[4 * s + e], plo, phi, ctx.mn_lo[s], ctx.mx_lo[s], ctx.mn_hi[s], ctx.mx_hi[s], qlo, qhi);
-          const float pre = __fadd_rn(__fmul_rn(ctx.omf[s], qlo), __fmul_rn(ctx.f[s], qhi));
-          out[4 * s + e] = HAS_MASK ? __fmul_rn(pre, m[4 * s + e]) : pre;
+        for (int e = 0; e < 4; e += 2) {
+          const int i = 4 * s + e;
+          float2 qlo, qhi;
+          frac_pair2(make_float2(xv[i], xv[i + 1]), plo, phi, ctx.mn_lo[s], ctx.mx_lo[s], ctx.mn_hi[s], ctx.mx_hi[s],
+                     qlo, qhi);
+          float2 pre = fadd2_sep(fmul2(splat2(ctx.omf[s]), qlo), fmul2(splat2(ctx.f[s]), qhi));
+          if (HAS_MASK) pre = fmul2(pre, make_float2(m[i], m[i + 1]));
+          out[i] = pre.x;
+          out[i + 1] = pre.y;
         }
       }
       const uint4 packed = Elem<T>::pack(out);
@@ -241,21 +252,33 @@ train_bwd_vec_kernel(const T* __restrict__ gy, const T* __restrict__ x, T* __res
         float tv[4];
         if (KD) unpack4(trawv[s], tv);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 4; e += 2) {
           const int i = 4 * s + e;
-          float qlo, qhi;
-          frac_pair(xv[i], plo, phi, ctx.mn_lo[s], ctx.mx_lo[s], ctx.mn_hi[s], ctx.mx_hi[s], qlo, qhi);
-          const float pre = __fadd_rn(__fmul_rn(ctx.omf[s], qlo), __fmul_rn(ctx.f[s], qhi));
-          float gt = gvv[i];
+          float2 qlo, qhi;
+          frac_pair2(make_float2(xv[i], xv[i + 1]), plo, phi, ctx.mn_lo[s], ctx.mx_lo[s], ctx.mn_hi[s], ctx.mx_hi[s],
+                     qlo, qhi);
+          const float2 omf2 = splat2(ctx.omf[s]), f2 = splat2(ctx.f[s]);
+          const float2 pre = fadd2_sep(fmul2(omf2, qlo), fmul2(f2, qhi));
+          const float2 m2 = make_float2(m[i], m[i + 1]);
+          float2 gt = make_float2(gvv[i], gvv[i + 1]);
           if (KD) {
-            const float yr = Elem<T>::round1(HAS_MASK ? __fmul_rn(pre, m[i]) : pre);
-            gt = __fadd_rn(gt, __fmul_rn(coef, __fsub_rn(yr, tv[e])));
+            const float2 yv = HAS_MASK ? fmul2(pre, m2) : pre;
+            const float2 yr = make_float2(Elem<T>::round1(yv.x), Elem<T>::round1(yv.y));
+            gt = fadd2_sep(gt, fmul2(splat2(coef), fadd2_sep(yr, make_float2(-tv[e], -tv[e + 1]))));   // yr may be a product
           }
-          const float gm = HAS_MASK ? __fmul_rn(gt, m[i]) : gt;
+          const float2 gm = HAS_MASK ? fmul2(gt, m2) : gt;
           // dx = g*m*(1-f) + g*m*f  (autograd of the two STE branches, quantization.py:725-727)
-          out[i] = __fadd_rn(__fmul_rn(gm, ctx.omf[s]), __fmul_rn(gm, ctx.f[s]));
-          acc_bit[s] = fmaf(gm, __fsub_rn(qhi, qlo), acc_bit[s]);
-          if (HAS_MASK) acc_m[i] = fmaf(gt, pre, acc_m[i]);
+          const float2 dxv = fadd2_sep(fmul2(gm, omf2), fmul2(gm, f2));
+          out[i] = dxv.x;
+          out[i + 1] = dxv.y;
+          const float2 dq = fadd2(qhi, make_float2(-qlo.x, -qlo.y));
+          acc_bit[s] = fmaf(gm.x, dq.x, acc_bit[s]);
+          acc_bit[s] = fmaf(gm.y, dq.y, acc_bit[s]);
+          if (HAS_MASK) {
+            const float2 am = ffma2(gt, pre, make_float2(acc_m[i], acc_m[i + 1]));
+            acc_m[i] = am.x;
+            acc_m[i + 1] = am.y;
+          }
         }
       }
       stg_stream(dst, Elem<T>::pack(out));
