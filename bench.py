@@ -428,7 +428,7 @@ def run_native(args):
             return statistics.mean(ts)
 
         cm = KC.pack_complexity_mlp(analyzer.complexity_mlp)
-        mp_ = KC.pack_mapping_network(mapper.mapping_network)
+        mp_ = KC.pack_mapping_steps(mapper.mapping_network, 1.0, mapper.min_bits, mapper.max_bits)
         kern_ms = {}
         for si, (C, H, Wd) in enumerate(shapes):
             xs_ = [sets[j][si] for j in range(INPUT_SETS)]

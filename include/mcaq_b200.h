@@ -48,6 +48,7 @@ extern "C" {
 #define MCAQ_CONSTS_FLOATS     192
 #define MCAQ_CMLP_FLOATS       2884   /* complexity_mlp 8-64-LN-32-LN-1: W0^T[8][64] b0 g1 be1 W3^T[64][32] b3 g4 be4 W6[32] b6 pad3 */
 #define MCAQ_MAPPER_FLOATS     4612   /* mapping_network, BN folded: W0^T[3][32] (b,alpha,beta)[32] W3^T[32][64] (..)[64] W6^T[64][32] (..)[32] W9[32] b9 pad3 */
+#define MCAQ_MAPPER_STEPS_FLOATS 12   /* step table that may follow the mapper block: 8 steps, valid, temperature, lo, hi */
 #define MCAQ_SOFTMASK_FLOATS   196    /* conv3x3(2->8)+b, conv1x1(8->2)+b, 5x5 smooth, pad1; all three blocks 16-byte aligned */
 
 MCAQ_API int mcaq_abi_version(void);
@@ -167,6 +168,9 @@ MCAQ_API int mcaq_morph_phi(const float* sum_plane, int B, int C, int H, int W, 
 /* K2 fused: everything between the two HBM sweeps of the inference hook in ONE launch
  * (models/mcaq_yolo.py:426-447): phi -> complexity (MLP, bilateral) -> bit map (MLP mapper, or
  * LinearBitMapper when linear_mapper != 0) -> soft mask m (B,H,W) (skipped when softmask NULL).
+ * linear_mapper == 2: `mapper` is the MLP block followed by its step table (mcaq_mapper_steps, built
+ * for the same temperature / min_bits / max_bits); integer (continuous == 0) bit maps are then read off
+ * the staircase instead of re-evaluating the network per tile.
  * If keys != NULL, CTA 0 also decodes K1's range keys into packed_ranges ([min, -max], 2C floats)
  * and re-arms the keys for the next sweep.  phi may be NULL. */
 MCAQ_API int mcaq_morph_fused(const float* sum_plane, const float* abs_plane, int B, int C, int H, int W,
@@ -209,6 +213,15 @@ MCAQ_API int mcaq_morph_fused_xchg(const float* sum_plane, const float* abs_plan
 MCAQ_API int mcaq_tile_quantize_xchg(const void* x, void* y, int dtype, int B, int C, int H, int W,
                                      const float* bit_map, int Ht, int Wt, const void* xchg_local, int world,
                                      float* qtable_ws, float* packed_ws, const float* mask, void* stream);
+
+/* Step table of the MLP bit mapper for integer outputs (bit_allocation.py:218-280 in eval mode): the
+ * mapper is monotone in the scalar complexity c (Eq.18), so its rounded output is a staircase.
+ * steps[k], k < 8 = smallest c in [0,1] with bits(c) >= min_bits + 1 + k (0 always, +inf never), found by
+ * bisection with the mapper kernel itself; steps[8] = 1 if the table is monotone (else the fused kernel
+ * evaluates the network), steps[9..11] = temperature, min_bits, max_bits it was built for.
+ * One small launch; rebuild when the weights, the temperature or the bit range change. */
+MCAQ_API int mcaq_mapper_steps(const float* mapper, float temperature, int use_temperature, float min_bits,
+                               float max_bits, float* steps /* MCAQ_MAPPER_STEPS_FLOATS */, void* stream);
 
 /* phi -> complexity (MLP + LayerNorm + sigmoid, 5x5 bilateral, clamp)  morphology.py:959-968 */
 MCAQ_API int mcaq_complexity(const float* phi, int B, int ht, int wt, const float* cmlp, const float* consts,

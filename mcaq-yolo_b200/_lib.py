@@ -57,6 +57,7 @@ PROTOTYPES = {
                                 c_void_p]),
     "mcaq_bit_mapper": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_int, c_int,
                                 c_float, c_float, c_float, c_void_p, c_void_p]),
+    "mcaq_mapper_steps": (c_int, [c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p]),
     "mcaq_xchg_bytes": (c_longlong, [c_int, c_int]),
     "mcaq_xchg_alloc": (c_int, [c_longlong, POINTER(c_void_p)]),
     "mcaq_xchg_free": (c_int, [c_void_p]),

@@ -121,6 +121,32 @@ def pack_mapping_network(seq) -> torch.Tensor:
     return _cached(seq, "mapper", ts, build)
 
 
+MAPPER_STEPS_FLOATS = 12
+
+
+def pack_mapping_steps(seq, temperature, min_bits: float, max_bits: float) -> torch.Tensor:
+    """The mapper block followed by its step table (include/mcaq_b200.h: mcaq_mapper_steps) for this
+    temperature and bit range: eval-mode integer bit maps of the fused kernel are read off the
+    staircase of the (monotone) mapper instead of evaluating 4.2k FMAs per tile.  One tiny launch per
+    (weights version, temperature, range), cached on the module like the block itself."""
+    from . import ops
+    base = pack_mapping_network(seq)
+    use_t = temperature is not None
+    t = max(float(temperature), 0.1) if use_t else 1.0
+    cache = seq.__dict__.setdefault("_mcaq_steps_cache", {})
+    if cache.get("base") is not base:
+        cache.clear()
+        cache["base"] = base
+    key = (t, use_t, float(min_bits), float(max_bits))
+    ext = cache.get(key)
+    if ext is None:
+        ext = torch.empty(MAPPER_FLOATS + MAPPER_STEPS_FLOATS, device=base.device, dtype=torch.float32)
+        ext[:MAPPER_FLOATS].copy_(base)
+        ops.mapper_steps(ext, t, use_t, min_bits, max_bits)
+        cache[key] = ext
+    return ext
+
+
 def pack_soft_mask(soft_mask) -> torch.Tensor:
     """LearnedSoftMask: net[0] conv3x3(2->8), net[2] conv1x1(8->2), smooth_kernel (1,1,5,5)."""
     ts = [soft_mask.net[0].weight, soft_mask.net[0].bias, soft_mask.net[2].weight,

@@ -63,6 +63,7 @@ struct FusedArgs {
   XchgPeers px;                // world > 1: CTA 0 also publishes `packed` to every rank (peer_exchange.cuh)
   const float* cmlp;           // NULL: stop after phi
   const float* mapper;         // packed MLP mapper, or NULL with linear_mapper != 0
+  const float* steps;          // step table of the MLP mapper (tile_nets.cuh), or NULL
   const float* softmask;
   int run_mapper, linear_mapper, use_t, continuous;
   float temperature, lo, hi, eps_spread;
@@ -933,6 +934,9 @@ morph_fused_kernel(const FusedArgs A) {
     if (ns > 1) { publish(cfin); cl.sync(); }
     mapper_linear_range(cfin, nt, red, t_lo, t_hi, A.temperature, A.use_t, A.continuous, A.lo, A.hi, A.eps_spread,
                         bits_s, bout);
+  } else if (A.steps && __ldg(A.steps + MAPPER_STEPS) == 1.f) {
+    mapper_steps_range(cfin, t_lo, t_hi, A.steps, A.lo, bits_s, bout);     // staircase of the same network
+    __syncthreads();
   } else {
     mapper_mlp_warps(cfin, t_lo, t_hi, w_map, scratch, A.temperature, A.use_t, A.continuous, A.lo, A.hi, bits_s, bout);
     __syncthreads();
@@ -1150,6 +1154,9 @@ extern "C" int mcaq_morph_fused_xchg(const float* sum_plane, const float* abs_pl
     A.px.world = xchg_world;
   }
   A.cmlp = cmlp; A.mapper = mapper; A.softmask = softmask;
+  // linear_mapper == 2: MLP mapper whose block is followed by its step table (mcaq_mapper_steps)
+  A.steps = (linear_mapper == 2 && mapper && !continuous) ? mapper + MAPPER_SMEM_FLOATS : nullptr;
+  if (linear_mapper == 2) linear_mapper = 0;
   A.run_mapper = 1; A.linear_mapper = linear_mapper; A.use_t = use_temperature; A.continuous = continuous;
   A.temperature = temperature; A.lo = min_bits; A.hi = max_bits; A.eps_spread = eps_spread;
   A.phi = phi; A.complexity = complexity; A.bit_map = bit_map; A.mask = mask;

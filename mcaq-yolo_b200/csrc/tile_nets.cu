@@ -34,6 +34,62 @@ mapper_mlp_kernel(const float* __restrict__ cmap, int ntiles, const float* __res
                    bits_s, out + (long long)b * ntiles);
 }
 
+// Builds the step table of mapper_steps_range by bisection on the fp32 bit pattern of c in [0, 1],
+// evaluating the mapper with mapper_mlp_warps itself (all 8 steps advance together, 31 rounds).
+__global__ void __launch_bounds__(TN_THREADS)
+mapper_steps_kernel(const float* __restrict__ mp, float temperature, int use_t, float lo, float hi,
+                    float* __restrict__ steps) {
+  extern __shared__ __align__(16) float sm[];
+  float* scratch = sm;                                  // TN_WARPS * NET_WARP_SCRATCH
+  float* cand = scratch + TN_WARPS * NET_WARP_SCRATCH;  // [8]
+  float* bits = cand + 8;                               // [8]
+  __shared__ unsigned L[MAPPER_STEPS], R[MAPPER_STEPS];
+  __shared__ int mode[MAPPER_STEPS];                    // 0 bisect, 1 always, 2 never
+  const int tid = threadIdx.x;
+  const int nsteps = (int)__fsub_rn(hi, lo);
+  if (tid < 8) cand[tid] = tid == 0 ? 0.f : 1.f;
+  __syncthreads();
+  mapper_mlp_warps(cand, 0, 8, mp, scratch, temperature, use_t, 0, lo, hi, bits, nullptr);
+  __syncthreads();
+  if (tid < MAPPER_STEPS) {
+    const float target = __fadd_rn(lo, (float)(tid + 1));
+    const float b0 = bits[0], b1 = bits[1];
+    mode[tid] = (tid >= nsteps || !(b1 >= target)) ? 2 : (b0 >= target ? 1 : 0);
+    L[tid] = 0u;                                        // bits(L) <  target
+    R[tid] = 0x3f800000u;                               // bits(R) >= target
+  }
+  __syncthreads();
+  for (int it = 0; it < 31; ++it) {
+    if (tid < MAPPER_STEPS) cand[tid] = __uint_as_float((L[tid] + R[tid]) >> 1);
+    __syncthreads();
+    mapper_mlp_warps(cand, 0, 8, mp, scratch, temperature, use_t, 0, lo, hi, bits, nullptr);
+    __syncthreads();
+    if (tid < MAPPER_STEPS && mode[tid] == 0) {
+      const unsigned mid = (L[tid] + R[tid]) >> 1;
+      if (mid != L[tid]) {
+        if (bits[tid] >= __fadd_rn(lo, (float)(tid + 1))) R[tid] = mid; else L[tid] = mid;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < MAPPER_STEPS)
+    steps[tid] = mode[tid] == 1 ? 0.f : (mode[tid] == 2 ? INFINITY : __uint_as_float(R[tid]));
+  __syncthreads();
+  if (tid == 0) {
+    bool ok = nsteps >= 1 && nsteps <= MAPPER_STEPS;
+    float prev = 0.f;
+    for (int k = 0; k < MAPPER_STEPS; ++k) {
+      const float v = mode[k] == 1 ? 0.f : (mode[k] == 2 ? INFINITY : __uint_as_float(R[k]));
+      if (v < prev) ok = false;
+      prev = v;
+    }
+    steps[8] = ok ? 1.f : 0.f;
+    steps[9] = use_t ? temperature : 0.f;
+    steps[10] = lo;
+    steps[11] = hi;
+  }
+}
+
 __global__ void __launch_bounds__(TN_THREADS)
 mapper_linear_kernel(const float* __restrict__ cmap, int ntiles, float temperature, int use_t,
                      int continuous, float lo, float hi, float eps_spread, float* __restrict__ out) {
@@ -88,6 +144,17 @@ extern "C" int mcaq_complexity(const float* phi, int B, int ht, int wt, const fl
   if (smem > 200 * 1024) return MCAQ_ETOOBIG;
   if (smem > 48 * 1024) cudaFuncSetAttribute(complexity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   complexity_kernel<<<B, TN_THREADS, smem, (cudaStream_t)stream>>>(phi, ht, wt, cmlp, complexity_raw, complexity);
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcaq_mapper_steps(const float* mapper, float temperature, int use_temperature, float min_bits,
+                                 float max_bits, float* steps, void* stream) {
+  if (!mapper || !steps || !(max_bits > min_bits)) return MCAQ_EINVAL;
+  if (((uintptr_t)mapper | (uintptr_t)steps) & 15) return MCAQ_EALIGN;
+  const size_t smem = (size_t)(TN_WARPS * NET_WARP_SCRATCH + 16) * sizeof(float);
+  mapper_steps_kernel<<<1, TN_THREADS, smem, (cudaStream_t)stream>>>(mapper, temperature, use_temperature,
+                                                                      min_bits, max_bits, steps);
   MCAQ_LAUNCH_CHECK();
   return 0;
 }

@@ -318,6 +318,32 @@ __device__ __forceinline__ void mapper_mlp_warps(const float* cmap, int t_lo, in
   }
 }
 
+// Step table of the MLP mapper (eval, integer output).  With non-negative weights (Eq.18) and folded
+// BN scales the network is monotone in c, so bits(c) = lo + #{k : c >= steps[k]} where steps[k] is the
+// smallest c in [0, 1] (by fp32 bit pattern) at which mapper_mlp_warps itself returns >= lo + 1 + k
+// (0: always, +inf: never).  The table is built by bisection WITH mapper_mlp_warps
+// (tile_nets.cu: mapper_steps_kernel), so both agree everywhere except possibly within a few ulps of a
+// step, where the continuous bit value sits on a .5 rounding boundary (SURVEY 7.3 ambiguity set).
+// steps[8] == 1 marks a valid (monotone) table.
+constexpr int MAPPER_STEPS = 8;
+constexpr int MAPPER_STEPS_FLOATS = 12;                       // 8 steps | valid | temperature | lo | hi
+__device__ __forceinline__ void mapper_steps_range(const float* cmap, int t_lo, int t_hi,
+                                                   const float* __restrict__ steps, float lo, float* bits_s,
+                                                   float* __restrict__ out) {
+  float st[MAPPER_STEPS];
+#pragma unroll
+  for (int k = 0; k < MAPPER_STEPS; ++k) st[k] = __ldg(steps + k);
+  for (int t = t_lo + threadIdx.x; t < t_hi; t += blockDim.x) {
+    const float c = fminf(fmaxf(cmap[t], 0.f), 1.f);
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < MAPPER_STEPS; ++k) n += (c >= st[k]) ? 1 : 0;
+    const float b = __fadd_rn(lo, (float)n);
+    bits_s[t] = b;
+    if (out) out[t] = b;
+  }
+}
+
 // torch.quantile(q, 'linear'): fp32 rank, torch.lerp formula on the two neighbouring order statistics
 __device__ __forceinline__ void quantile_ranks(int n, float q, int& lo, int& hi, float& w) {
   const float rank = __fmul_rn(q, (float)(n - 1));

@@ -86,7 +86,8 @@ def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, tempera
     sm = quantizer.soft_mask if quantizer.smooth_transitions else None
     r = ops.morph_fused(s, a if sm is not None else None, C, analyzer.grid_size,
                         K.pack_complexity_mlp(analyzer.complexity_mlp),
-                        None if linear else K.pack_mapping_network(mapper.mapping_network),
+                        None if linear else K.pack_mapping_steps(mapper.mapping_network, temperature,
+                                                                 mapper.min_bits, mapper.max_bits),
                         None if sm is None else K.pack_soft_mask(sm),
                         temperature, False, ws.keys if need_ranges else None,
                         mapper.min_bits, mapper.max_bits, getattr(mapper, "eps_spread", 1e-3),
@@ -273,7 +274,8 @@ class ShardedHotPath:
             sm = q.soft_mask if q.smooth_transitions else None
             return ops.morph_fused(s, a if sm is not None else None, x.shape[1], self.analyzer.grid_size,
                                    K.pack_complexity_mlp(self.analyzer.complexity_mlp),
-                                   None if linear else K.pack_mapping_network(self.mapper.mapping_network),
+                                   None if linear else K.pack_mapping_steps(self.mapper.mapping_network, self.temperature,
+                                                                            self.mapper.min_bits, self.mapper.max_bits),
                                    None if sm is None else K.pack_soft_mask(sm), self.temperature, False, None,
                                    self.mapper.min_bits, self.mapper.max_bits,
                                    getattr(self.mapper, "eps_spread", 1e-3))

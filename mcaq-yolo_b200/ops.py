@@ -342,6 +342,21 @@ def bit_mapper(cmap: torch.Tensor, mapper: torch.Tensor | None, temperature, con
     return out
 
 
+MAPPER_FLOATS = 4612
+MAPPER_STEPS_FLOATS = 12
+
+
+def mapper_steps(ext_block: torch.Tensor, t: float, use_t: bool, min_bits: float, max_bits: float) -> torch.Tensor:
+    """Fill the step table behind the mapper block in `ext_block` (MAPPER_FLOATS + MAPPER_STEPS_FLOATS
+    floats) in place: mcaq_mapper_steps, bisection with the mapper kernel itself."""
+    _need_cuda(ext_block)
+    if ext_block.numel() != MAPPER_FLOATS + MAPPER_STEPS_FLOATS or ext_block.dtype != torch.float32:
+        raise RuntimeError("extended mapper block must hold MAPPER_FLOATS + MAPPER_STEPS_FLOATS fp32 values")
+    _call("mcaq_mapper_steps", ext_block.data_ptr(), float(t), int(use_t), float(min_bits), float(max_bits),
+          ext_block.data_ptr() + 4 * MAPPER_FLOATS, _stream())
+    return ext_block
+
+
 def soft_mask(bit_map: torch.Tensor, abs_plane: torch.Tensor, C: int, softmask: torch.Tensor,
               want_tiles: bool = False):
     """m (B,H,W) (quantization.py:213-239) from the bit map and the sum_c|x| plane."""
@@ -377,8 +392,10 @@ def morph_fused(sum_plane: torch.Tensor, abs_plane: torch.Tensor | None, C: int,
     packed = torch.empty((2 * C,), device=dev, dtype=torch.float32) if keys is not None else None
     use_t = temperature is not None
     t = max(float(temperature), 0.1) if use_t else 1.0
+    # mapper kind: 1 linear (quantile) mapper, 0 MLP block, 2 MLP block + step table (constants.pack_mapping_steps)
+    kind = 1 if mapper is None else (2 if mapper.numel() == MAPPER_FLOATS + MAPPER_STEPS_FLOATS else 0)
     args = (sum_plane.data_ptr(), _ptr(abs_plane), B, int(C), H, W, int(grid_size), _ptr(keys),
-            _ptr(packed), cmlp.data_ptr(), _ptr(mapper), int(mapper is None), _ptr(softmask), t, int(use_t),
+            _ptr(packed), cmlp.data_ptr(), _ptr(mapper), kind, _ptr(softmask), t, int(use_t),
             int(continuous), float(min_bits), float(max_bits), float(eps_spread), _ptr(phi), cpx.data_ptr(),
             bits.data_ptr(), _ptr(mask))
     if xchg is not None and xchg.world > 1:
