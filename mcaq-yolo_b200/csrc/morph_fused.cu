@@ -921,8 +921,12 @@ morph_fused_kernel(const FusedArgs A) {
   // ---- N1: complexity MLP (own tiles) -> all-gather -> bilateral (own tiles) -------------------------
   float* scratch = S;                        // the float planes are dead from here on
   const int nt = g.ntiles;
-  complexity_mlp_warps(phi8, t_lo, t_hi, w_cmlp, scratch, craw_s,
-                       A.complexity_raw ? A.complexity_raw + (long long)b * nt : nullptr);
+  float* w_cmlp_s = S + (MORPH_MAX_THREADS / 32) * NET_WARP_SCRATCH;   // staged behind the per-warp scratch
+  copy_params(w_cmlp, w_cmlp_s, CMLP_SMEM_FLOATS);
+  __syncthreads();
+  complexity_mlp_warps(phi8, t_lo, t_hi, w_cmlp_s, scratch, craw_s,
+                       A.complexity_raw ? A.complexity_raw + (long long)b * nt : nullptr,
+                       (clk && rank == 0) ? clk + (long long)b * 16 : nullptr);
   if (ns > 1) { __syncthreads(); publish(craw_s); cl.sync(); } else __syncthreads();
   STAGE_CLOCK(9);
   bilateral_range(craw_s, g.ht, g.wt, t_lo, t_hi, scratch, cfin, A.complexity ? A.complexity + (long long)b * nt : nullptr);
@@ -1024,7 +1028,7 @@ static long long layout(MorphGeom& g) {
   const long long wG = (long long)(g.band_max + 10) * g.gs;      // also holds MAG ((band+2) * Wc) after T1
   const long long wBL = (long long)(g.band_max + 4) * g.bs + 8LL * g.gs;
   // the same region later holds the per-warp net scratch, bilateral weights, mask classes
-  const long long nets = max_i((MORPH_MAX_THREADS / 32) * NET_WARP_SCRATCH, 2 * g.ntiles + 25 * g.max_own);
+  const long long nets = max_i((MORPH_MAX_THREADS / 32) * NET_WARP_SCRATCH + CMLP_SMEM_FLOATS, 2 * g.ntiles + 25 * g.max_own);
   g.off_bl = (int)((wG + 3) & ~3LL);
   g.off_mag = 0;
   long long bits0 = (g.off_bl + wBL + 3) & ~3LL;

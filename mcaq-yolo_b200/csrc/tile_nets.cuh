@@ -48,8 +48,10 @@ constexpr int MAPPER_SMEM_FLOATS = 96 + 96 + 2048 + 192 + 2048 + 96 + 36;   // 4
 // soft mask: W0[8][2][3][3] | b0[8] | W2[2][8] | b2[2] | smooth[5][5] | pad1
 constexpr int SOFTMASK_SMEM_FLOATS = 196;                                   // == MCAQ_SOFTMASK_FLOATS
 
-constexpr int NET_TT = 4;                                    // tiles a warp carries through a net at once
-constexpr int NET_WARP_SCRATCH = NET_TT * (64 + 32 + 32 + 4);   // floats of scratch per warp (528)
+constexpr int NET_TT = 4;                                    // tiles a warp carries through the mapper at once
+constexpr int CM_TT = 8;                                     // ... and through the complexity MLP (packed pairs)
+// floats of scratch per warp: mapper NET_TT * (64 + 32 + 32 + 4) = 528, complexity MLP CM_TT * (64 + 32) = 768
+constexpr int NET_WARP_SCRATCH = CM_TT * (64 + 32);
 
 // plain cooperative copy global -> shared (n % 4 == 0, both 16-byte aligned)
 __device__ __forceinline__ void copy_params(const float* __restrict__ src, float* dst, int n) {
@@ -84,6 +86,71 @@ __device__ __forceinline__ float ln32_relu(float a0, float g, float be) {
   return fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(d0, rstd), g), be), 0.f);
 }
 
+// The same LayerNorm + ReLU for N tiles at once: the N butterflies run as independent shuffle chains and
+// the 1 / sqrt(var + eps) of tile j (an IEEE division and square root: slow-path calls) is evaluated once
+// by lane j for all tiles in parallel, then broadcast.  Per tile exactly the operations of ln64_relu /
+// ln32_relu, so the values are bit-identical.
+template <int N>
+__device__ __forceinline__ void warp_tree_sum_n(float (&v)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = __fadd_rn(v[j], __shfl_xor_sync(0xffffffffu, v[j], o));
+  }
+}
+template <int N>
+__device__ __forceinline__ void rstd_n(const float (&var)[N], float (&rstd)[N]) {
+  static_assert(N <= 32, "one lane per tile");
+  const int lane = threadIdx.x & 31;
+  float mine = var[0];
+#pragma unroll
+  for (int j = 1; j < N; ++j) mine = (lane == j) ? var[j] : mine;
+  const float r = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mine, 1e-5f)));
+#pragma unroll
+  for (int j = 0; j < N; ++j) rstd[j] = __shfl_sync(0xffffffffu, r, j);
+}
+template <int N>
+__device__ __forceinline__ void ln64_relu_n(float2 (&a)[N], float g0, float g1, float be0, float be1) {
+  float s[N], rstd[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) s[j] = __fadd_rn(a[j].x, a[j].y);
+  warp_tree_sum_n<N>(s);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float mean = __fmul_rn(s[j], 0.015625f);
+    a[j].x = __fsub_rn(a[j].x, mean);
+    a[j].y = __fsub_rn(a[j].y, mean);
+    s[j] = __fadd_rn(__fmul_rn(a[j].x, a[j].x), __fmul_rn(a[j].y, a[j].y));
+  }
+  warp_tree_sum_n<N>(s);
+#pragma unroll
+  for (int j = 0; j < N; ++j) s[j] = __fmul_rn(s[j], 0.015625f);
+  rstd_n<N>(s, rstd);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    a[j].x = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(a[j].x, rstd[j]), g0), be0), 0.f);
+    a[j].y = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(a[j].y, rstd[j]), g1), be1), 0.f);
+  }
+}
+template <int N>
+__device__ __forceinline__ void ln32_relu_n(float (&a)[N], float g, float be) {
+  float s[N], rstd[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) s[j] = a[j];
+  warp_tree_sum_n<N>(s);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    a[j] = __fsub_rn(a[j], __fmul_rn(s[j], 0.03125f));
+    s[j] = __fmul_rn(a[j], a[j]);
+  }
+  warp_tree_sum_n<N>(s);
+#pragma unroll
+  for (int j = 0; j < N; ++j) s[j] = __fmul_rn(s[j], 0.03125f);
+  rstd_n<N>(s, rstd);
+#pragma unroll
+  for (int j = 0; j < N; ++j) a[j] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(a[j], rstd[j]), g), be), 0.f);
+}
+
 // out[j] (+)= sum_k act[j][k] * Wt[k][unit]: FMA chain over k from 0 for NET_TT tiles at once.
 // act rows are 16-byte aligned shared memory (broadcast LDS.128), Wt column reads are conflict-free.
 template <int K_IN, int N_OUT>
@@ -109,14 +176,16 @@ __device__ __forceinline__ void dense_warp(const float* act, int act_stride, con
 // ---------------------------------------------------------------------------------------------
 // complexity MLP 8 -> 64 (LN, ReLU) -> 32 (LN, ReLU) -> 1, sigmoid  (morphology.py:81-97)
 // craw[t] for t in [t_lo, t_hi).  phi: [ntiles][8] floats, 16-byte aligned rows (shared or global);
-// w: CMLP block in GLOBAL memory (read through L1, shared by every CTA); scratch: NET_WARP_SCRATCH
-// floats of shared memory per warp.  Warp-level only: the
+// w: CMLP block, global or shared memory (plain loads; the fused kernel stages it into shared memory:
+// L1 starts cold in every launch and layer 2 would walk the block in 16 dependent L2 round trips);
+// scratch: NET_WARP_SCRATCH floats of shared memory per warp.  Warp-level only: the
 // caller synchronises the CTA before anyone reads craw.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo, int t_hi,
                                                      const float* __restrict__ w, float* scratch_all, float* craw,
-                                                     float* __restrict__ raw_out) {
+                                                     float* __restrict__ raw_out, long long* dbg = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#define CM_DBG(k) do { if (dbg && threadIdx.x == 0 && tg == t_lo) dbg[k] = clock64(); } while (0)
   const float* W0t = w;
   const float* b0 = w + 512;
   const float* g1 = w + 576;
@@ -126,59 +195,96 @@ __device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo,
   const float* g4 = w + 2784;
   const float* be4 = w + 2816;
   const float* W6 = w + 2848;
-  const float b6 = __ldg(w + 2880);
-  float* h1 = scratch_all + warp * NET_WARP_SCRATCH;      // [TT][64]
-  float* h2 = h1 + NET_TT * 64;                           // [TT][32]
-  for (int tg = t_lo + warp * NET_TT; tg < t_hi; tg += nwarps * NET_TT) {
-    float a0[NET_TT], a1[NET_TT];
+  const float b6 = *(w + 2880);
+  // a warp carries CM_TT = 8 tiles; activations of layer 1 are parked as h1[k][tile] so that one
+  // LDS.128 yields two (tile, tile + 1) pairs for the packed FMAs of layer 2
+  float* h1 = scratch_all + warp * NET_WARP_SCRATCH;      // [64][CM_TT]
+  float* h2 = h1 + 64 * CM_TT;                            // [CM_TT][32]
+  for (int tg = t_lo + warp * CM_TT; tg < t_hi; tg += nwarps * CM_TT) {
+    // layer 1 (8 -> 64): lane owns units lane and lane + 32 = one packed accumulator per tile
+    float2 a[CM_TT];
+    {
+      float2 w01[8];
 #pragma unroll
-    for (int j = 0; j < NET_TT; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
-    float4 pa[NET_TT], pb[NET_TT];
+      for (int k = 0; k < 8; ++k) w01[k] = make_float2(*(W0t + k * 64 + lane), *(W0t + k * 64 + 32 + lane));
 #pragma unroll
-    for (int j = 0; j < NET_TT; ++j) {
-      const float4* pr = reinterpret_cast<const float4*>(phi + min(tg + j, t_hi - 1) * 8);
-      pa[j] = pr[0];
-      pb[j] = pr[1];
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float w0 = __ldg(W0t + k * 64 + lane), w1 = __ldg(W0t + k * 64 + 32 + lane);
-#pragma unroll
-      for (int j = 0; j < NET_TT; ++j) {
-        const float p = k == 0 ? pa[j].x : k == 1 ? pa[j].y : k == 2 ? pa[j].z : k == 3 ? pa[j].w
-                      : k == 4 ? pb[j].x : k == 5 ? pb[j].y : k == 6 ? pb[j].z : pb[j].w;
-        a0[j] = fmaf(p, w0, a0[j]);
-        a1[j] = fmaf(p, w1, a1[j]);
+      for (int j = 0; j < CM_TT; ++j) {
+        const float4* pr = reinterpret_cast<const float4*>(phi + min(tg + j, t_hi - 1) * 8);
+        const float4 pa = pr[0], pb = pr[1];
+        float2 acc = make_float2(0.f, 0.f);
+        acc = ffma2(splat2(pa.x), w01[0], acc);
+        acc = ffma2(splat2(pa.y), w01[1], acc);
+        acc = ffma2(splat2(pa.z), w01[2], acc);
+        acc = ffma2(splat2(pa.w), w01[3], acc);
+        acc = ffma2(splat2(pb.x), w01[4], acc);
+        acc = ffma2(splat2(pb.y), w01[5], acc);
+        acc = ffma2(splat2(pb.z), w01[6], acc);
+        acc = ffma2(splat2(pb.w), w01[7], acc);
+        a[j] = acc;
       }
     }
+    CM_DBG(13);
     {
-      const float bb0 = __ldg(b0 + lane), bb1 = __ldg(b0 + lane + 32);
-      const float gg0 = __ldg(g1 + lane), gg1 = __ldg(g1 + lane + 32), ee0 = __ldg(be1 + lane), ee1 = __ldg(be1 + lane + 32);
+      const float bb0 = *(b0 + lane), bb1 = *(b0 + lane + 32);
+      const float gg0 = *(g1 + lane), gg1 = *(g1 + lane + 32), ee0 = *(be1 + lane), ee1 = *(be1 + lane + 32);
 #pragma unroll
-      for (int j = 0; j < NET_TT; ++j) {
-        a0[j] = __fadd_rn(a0[j], bb0);
-        a1[j] = __fadd_rn(a1[j], bb1);
-        ln64_relu(a0[j], a1[j], gg0, gg1, ee0, ee1);
-        h1[j * 64 + lane] = a0[j];
-        h1[j * 64 + 32 + lane] = a1[j];
+      for (int j = 0; j < CM_TT; ++j) a[j] = make_float2(__fadd_rn(a[j].x, bb0), __fadd_rn(a[j].y, bb1));
+      ln64_relu_n<CM_TT>(a, gg0, gg1, ee0, ee1);
+      float4* r0 = reinterpret_cast<float4*>(h1 + lane * CM_TT);
+      float4* r1 = reinterpret_cast<float4*>(h1 + (lane + 32) * CM_TT);
+      r0[0] = make_float4(a[0].x, a[1].x, a[2].x, a[3].x);
+      r0[1] = make_float4(a[4].x, a[5].x, a[6].x, a[7].x);
+      r1[0] = make_float4(a[0].y, a[1].y, a[2].y, a[3].y);
+      r1[1] = make_float4(a[4].y, a[5].y, a[6].y, a[7].y);
+    }
+    __syncwarp();
+    CM_DBG(14);
+    // layer 2 (64 -> 32): lane = unit, packed accumulators over tile pairs, weights one block ahead
+    float2 acc[CM_TT / 2];
+#pragma unroll
+    for (int p = 0; p < CM_TT / 2; ++p) acc[p] = make_float2(0.f, 0.f);
+    float wc[4], wn[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wc[q] = *(W3t + q * 32 + lane);
+#pragma unroll 1
+    for (int k4 = 0; k4 < 16; ++k4) {
+      const int kn = k4 < 15 ? k4 + 1 : k4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wn[q] = *(W3t + (4 * kn + q) * 32 + lane);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4* hr = reinterpret_cast<const float4*>(h1 + (4 * k4 + q) * CM_TT);
+        const float4 ha = hr[0], hb = hr[1];
+        const float2 ws = splat2(wc[q]);
+        acc[0] = ffma2(make_float2(ha.x, ha.y), ws, acc[0]);
+        acc[1] = ffma2(make_float2(ha.z, ha.w), ws, acc[1]);
+        acc[2] = ffma2(make_float2(hb.x, hb.y), ws, acc[2]);
+        acc[3] = ffma2(make_float2(hb.z, hb.w), ws, acc[3]);
       }
-    }
-    __syncwarp();
-    float acc[NET_TT];
-    dense_warp<64, 32>(h1, 64, W3t, lane, acc);
-    {
-      const float bb = __ldg(b3 + lane), gg = __ldg(g4 + lane), ee = __ldg(be4 + lane);
 #pragma unroll
-      for (int j = 0; j < NET_TT; ++j) h2[j * 32 + lane] = ln32_relu(__fadd_rn(acc[j], bb), gg, ee);
+      for (int q = 0; q < 4; ++q) wc[q] = wn[q];
+    }
+    CM_DBG(15);
+    {
+      const float bb = *(b3 + lane), gg = *(g4 + lane), ee = *(be4 + lane);
+      float v[CM_TT];
+#pragma unroll
+      for (int p = 0; p < CM_TT / 2; ++p) {
+        v[2 * p] = __fadd_rn(acc[p].x, bb);
+        v[2 * p + 1] = __fadd_rn(acc[p].y, bb);
+      }
+      ln32_relu_n<CM_TT>(v, gg, ee);
+#pragma unroll
+      for (int j = 0; j < CM_TT; ++j) h2[j * 32 + lane] = v[j];
     }
     __syncwarp();
-    if (lane < NET_TT && tg + lane < t_hi) {               // layer 3: 32 -> 1 and sigmoid, one lane per tile
+    if (lane < CM_TT && tg + lane < t_hi) {                // layer 3: 32 -> 1 and sigmoid, one lane per tile
       float z = 0.f;
 #pragma unroll
       for (int k4 = 0; k4 < 8; ++k4) {
-        const float4 a = *reinterpret_cast<const float4*>(h2 + lane * 32 + 4 * k4);
-        const float4 ww = __ldg(reinterpret_cast<const float4*>(W6 + 4 * k4));
-        z = fmaf(a.x, ww.x, z); z = fmaf(a.y, ww.y, z); z = fmaf(a.z, ww.z, z); z = fmaf(a.w, ww.w, z);
+        const float4 av = *reinterpret_cast<const float4*>(h2 + lane * 32 + 4 * k4);
+        const float4 ww = *reinterpret_cast<const float4*>(W6 + 4 * k4);
+        z = fmaf(av.x, ww.x, z); z = fmaf(av.y, ww.y, z); z = fmaf(av.z, ww.z, z); z = fmaf(av.w, ww.w, z);
       }
       const float c = sigmoid_exact(__fadd_rn(z, b6));
       craw[tg + lane] = c;

@@ -29,3 +29,6 @@ for (C, H) in ((64, 80), (128, 40), (256, 20), (128, 160)):
     print(f"C={C} H={H}: total {tot:.0f} cycles = {tot / 1.965e3:.1f} us @1.965GHz")
     for i in range(12):
         print(f"   {names[i]:24s} {d[i]:9.0f} cyc  {100 * d[i] / tot:5.1f}%")
+    if (c[:, 13:16] > 0).all():       # inside N1 (first tile group of warp 0): layer 1 | LN64 + park | layer 2 | rest
+        n1 = [(c[:, 13] - c[:, 8]).mean(), (c[:, 14] - c[:, 13]).mean(), (c[:, 15] - c[:, 14]).mean(), (c[:, 9] - c[:, 15]).mean()]
+        print("   N1 detail: layer1 %.0f | LN64+park %.0f | layer2 %.0f | LN32+layer3+later rounds+sync %.0f" % tuple(n1))
