@@ -191,36 +191,60 @@ __device__ __forceinline__ void task_blur(const Ctx& c, int r0, int rend, int k,
 
 // ---- T1b: adaptive threshold, 11x11 Gaussian mean of 255*G with replicate borders, rows [r0, r0+RT)
 //      (morphology.py:550-573) -> BIN words (own plane and every peer's).
+// The reference's value is the 121-tap FMA chain in row-major order; only the SIGN of
+// 255 g - (mean - 2) is kept.  The 2-D kernel is the fp32 outer product of an 11-tap vector, so a
+// separable evaluation (11 + 11 FMAs) differs from the chain by at most
+//   121 u 255 (chain) + 22 u 255 (separable) + 3 u 255 (scalings)  <  2.3e-3      (u = 2^-24, g in [0,1]),
+// and decides every pixel whose margin exceeds 4e-3; the few pixels inside the guard band (about one
+// in a thousand) take the literal chain, so the bit plane is exactly the reference's.
+__device__ constexpr float ADAPT1[11] = {0x1.20c256p-7f, 0x1.bcb868p-6f, 0x1.0ab508p-4f, 0x1.f2464cp-4f, 0x1.6a7e1cp-3f,
+                              0x1.9ac20ap-3f, 0x1.6a7e1cp-3f, 0x1.f2464cp-4f, 0x1.0ab508p-4f, 0x1.bcb868p-6f,
+                              0x1.20c256p-7f};
+constexpr float ADAPT_GUARD = 4e-3f;
+
+// literal reference arithmetic for one pixel (not inlined: rare)
+static __device__ __noinline__ bool adaptive_exact(const float* Gp, int gs, int Hc, int Wc, int r, int x) {
+  float acc = 0.f;
+#pragma unroll 1
+  for (int ky = 0; ky < 11; ++ky) {
+    const float* row = Gp + clampi(r - 5 + ky, 0, Hc - 1) * gs;
+#pragma unroll
+    for (int kx = 0; kx < 11; ++kx)
+      acc = fmaf(__fmul_rn(row[clampi(x + kx - 5, 0, Wc - 1)], 255.f), __fmul_rn(ADAPT1[ky], ADAPT1[kx]), acc);
+  }
+  return __fmul_rn(Gp[r * gs + x], 255.f) > __fsub_rn(acc, 2.0f);
+}
+
 template <int RT>
 __device__ __forceinline__ void task_adaptive(const Ctx& c, cg::cluster_group& cl, int r0, int k, int lane) {
   const int x = 32 * k + lane;
   const bool valid = x < c.Wc;
+  const int xq = valid ? x : c.Wc - 1;
   int xc[11];
 #pragma unroll
-  for (int j = 0; j < 11; ++j) xc[j] = clampi(x + j - 5, 0, c.Wc - 1);
+  for (int j = 0; j < 11; ++j) xc[j] = clampi(xq + j - 5, 0, c.Wc - 1);
   float acc[RT], ctr[RT];
 #pragma unroll
   for (int j = 0; j < RT; ++j) acc[j] = 0.f;
 #pragma unroll
   for (int rr = 0; rr < RT + 10; ++rr) {
     const float* row = c.Gp + clampi(r0 - 5 + rr, 0, c.Hc - 1) * c.gs;
-    float v[11];
+    float h = 0.f;                                          // horizontal pass on g
 #pragma unroll
-    for (int kx = 0; kx < 11; ++kx) v[kx] = __fmul_rn(row[xc[kx]], 255.f);
-    if (rr >= 5 && rr < RT + 5) ctr[rr - 5] = v[5];
+    for (int kx = 0; kx < 11; ++kx) h = fmaf(row[xc[kx]], ADAPT1[kx], h);
+    if (rr >= 5 && rr < RT + 5) ctr[rr - 5] = __fmul_rn(row[xc[5]], 255.f);
 #pragma unroll
     for (int j = 0; j < RT; ++j) {
       const int ky = rr - j;
-      if (ky >= 0 && ky < 11) {
-#pragma unroll
-        for (int kx = 0; kx < 11; ++kx) acc[j] = fmaf(v[kx], kc::ADAPT[ky * 11 + kx], acc[j]);
-      }
+      if (ky >= 0 && ky < 11) acc[j] = fmaf(h, ADAPT1[ky], acc[j]);
     }
   }
 #pragma unroll
   for (int j = 0; j < RT; ++j) {
-    const bool bit = valid && (ctr[j] > __fsub_rn(acc[j], 2.0f));
-    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+    const float d = __fsub_rn(ctr[j], __fsub_rn(__fmul_rn(acc[j], 255.f), 2.0f));
+    bool bit = d > 0.f;
+    if (fabsf(d) <= ADAPT_GUARD) bit = adaptive_exact(c.Gp, c.gs, c.Hc, c.Wc, r0 + j, xq);
+    const uint32_t word = __ballot_sync(0xffffffffu, bit && valid);
     if (lane < c.ns) {
       uint32_t* dst = lane == 0 ? c.BIN : cl.map_shared_rank(c.BIN, (c.rank + lane) % c.ns);
       dst[(r0 + j) * c.WW + k] = word;
@@ -708,7 +732,14 @@ morph_fused_kernel(const FusedArgs A) {
     const int nact = fast_act ? nlbp : 0;
     const int ntask = nadapt + nblur + nlbp + nact;
     const float* ap = A.abs_plane ? A.abs_plane + (long long)b * g.H * g.W : nullptr;
+#ifdef MCAQ_T1_PROF
+    long long t1p[4] = {0, 0, 0, 0};
+#endif
     for (int task = warp; task < ntask; task += nwarps) {
+#ifdef MCAQ_T1_PROF
+      const long long t1s = clock64();
+      const int t1k = task < nadapt ? 0 : (task < nadapt + nblur ? 1 : (task < nadapt + nblur + nlbp ? 2 : 3));
+#endif
       if (task < nadapt) {
         const int rg = task / WW, k = task - rg * WW;
         task_adaptive<4>(c, cl, r_lo + rg * 4, k, lane);
@@ -726,7 +757,16 @@ morph_fused_kernel(const FusedArgs A) {
         const int tyl = q / WW, k = q - tyl * WW;
         task_act(c, ap, g.W, fC, rC, cpow2, tr0 + tyl, k, lane, act_s);
       }
+#ifdef MCAQ_T1_PROF
+      t1p[t1k] += clock64() - t1s;
+#endif
     }
+#ifdef MCAQ_T1_PROF
+    if (clk && tid == 0 && rank == 0) {                 // warp 0's cycles per task type (debug build only)
+      clk[(long long)b * 16 + 13] = t1p[0]; clk[(long long)b * 16 + 14] = t1p[1];
+      clk[(long long)b * 16 + 15] = t1p[2] * 1000000LL + t1p[3];
+    }
+#endif
     if (A.softmask && A.abs_plane && !g.aligned)
       softmask_act_generic(ap, g.C, g.H, g.W, g.ht, g.wt, tr0, tr1, act_s);
   }
@@ -926,7 +966,11 @@ morph_fused_kernel(const FusedArgs A) {
   __syncthreads();
   complexity_mlp_warps(phi8, t_lo, t_hi, w_cmlp_s, scratch, craw_s,
                        A.complexity_raw ? A.complexity_raw + (long long)b * nt : nullptr,
+#ifdef MCAQ_T1_PROF
+                       nullptr);
+#else
                        (clk && rank == 0) ? clk + (long long)b * 16 : nullptr);
+#endif
   if (ns > 1) { __syncthreads(); publish(craw_s); cl.sync(); } else __syncthreads();
   STAGE_CLOCK(9);
   bilateral_range(craw_s, g.ht, g.wt, t_lo, t_hi, scratch, cfin, A.complexity ? A.complexity + (long long)b * nt : nullptr);
