@@ -16,7 +16,7 @@ lib = _lib.load()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 splits = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 4]
 a, m, q = M.build_fixture_modules(weights(), "cuda")
-cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_network(m.mapping_network), K.pack_soft_mask(q.soft_mask)
+cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_steps(m.mapping_network, 1.0, m.min_bits, m.max_bits), K.pack_soft_mask(q.soft_mask)
 for (C, H) in ((64, 80), (128, 40), (256, 20), (128, 160), (256, 80), (512, 40)):
     Bh = B if H < 160 else max(1, B // 2)
     x = torch.nn.functional.interpolate(torch.randn(Bh, C, H // 8, H // 8, device="cuda"), size=(H, H), mode="bicubic")

@@ -56,7 +56,7 @@ rows = []
 for model, (B, shapes) in SETS.items():
     for grid in (4, 8, 16):
         an, mp_, q = M.build_fixture_modules(W, device=dev, grid_size=grid)
-        cm, mpk, smk = K.pack_complexity_mlp(an.complexity_mlp), K.pack_mapping_network(mp_.mapping_network), K.pack_soft_mask(q.soft_mask)
+        cm, mpk, smk = K.pack_complexity_mlp(an.complexity_mlp), K.pack_mapping_steps(mp_.mapping_network, 1.0, mp_.min_bits, mp_.max_bits), K.pack_soft_mask(q.soft_mask)
         for (C, H) in shapes:
             for dt in (torch.bfloat16, torch.float32):
                 for layout in ("nchw", "nhwc"):

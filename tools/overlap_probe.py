@@ -17,7 +17,7 @@ B = 64
 dev = torch.device("cuda")
 W = weights()
 a, m, q = M.build_fixture_modules(W, device=dev)
-cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_network(m.mapping_network), K.pack_soft_mask(q.soft_mask)
+cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_steps(m.mapping_network, 1.0, m.min_bits, m.max_bits), K.pack_soft_mask(q.soft_mask)
 shapes = [(64, 80, 80), (128, 40, 40), (256, 20, 20)]
 g = torch.Generator(device=dev)
 g.manual_seed(1)

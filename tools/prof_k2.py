@@ -10,7 +10,7 @@ from golden_util import weights
 C, H = int(sys.argv[1]), int(sys.argv[2])
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 a, m, q = M.build_fixture_modules(weights(), "cuda")
-cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_network(m.mapping_network), K.pack_soft_mask(q.soft_mask)
+cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_steps(m.mapping_network, 1.0, m.min_bits, m.max_bits), K.pack_soft_mask(q.soft_mask)
 coarse = torch.randn(B, C, H // 8 + 2, H // 8 + 2, device="cuda")
 x = (torch.nn.functional.interpolate(coarse, size=(H, H), mode="bilinear") * 1.6 + 0.1 * torch.randn(B, C, H, H, device="cuda")).to(torch.bfloat16)
 s, ab, k = ops.reduce_planes(x)

@@ -12,7 +12,7 @@ names = ["L load+minmax", "N normalise", "T1 blur|adapt|lbp|act", "T2 mag+sync",
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 lib.mcaq_debug_cluster_split(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 a, m, q = M.build_fixture_modules(weights(), "cuda")
-cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_network(m.mapping_network), K.pack_soft_mask(q.soft_mask)
+cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_steps(m.mapping_network, 1.0, m.min_bits, m.max_bits), K.pack_soft_mask(q.soft_mask)
 for (C, H) in ((64, 80), (128, 40), (256, 20), (128, 160)):
     x = torch.nn.functional.interpolate(torch.randn(B, C, H // 8, H // 8, device="cuda"), size=(H, H), mode="bicubic")
     x = (x + 0.1 * torch.randn_like(x)).to(torch.bfloat16)

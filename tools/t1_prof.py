@@ -9,7 +9,7 @@ from mcaq_yolo_b200 import ops, _lib, constants as K, modules as M
 from golden_util import weights
 lib = _lib.load()
 a, m, q = M.build_fixture_modules(weights(), "cuda")
-cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_network(m.mapping_network), K.pack_soft_mask(q.soft_mask)
+cm, mp, sm = K.pack_complexity_mlp(a.complexity_mlp), K.pack_mapping_steps(m.mapping_network, 1.0, m.min_bits, m.max_bits), K.pack_soft_mask(q.soft_mask)
 B = 64
 for (C, H) in ((64, 80), (128, 40)):
     x = torch.nn.functional.interpolate(torch.randn(B, C, H // 8, H // 8, device="cuda"), size=(H, H), mode="bicubic")
