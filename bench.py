@@ -57,6 +57,11 @@ def parse():
                          "workspace), so the latency-bound morphology kernel of one step overlaps the HBM sweeps of "
                          "its neighbours; 1 = strictly serial steps")
     ap.add_argument("--input-sets", type=int, default=0, help="rotating input sets (default 4, or --inflight if larger)")
+    ap.add_argument("--frozen-ranges", action="store_true",
+                    help="calibrate once on the first input set, then freeze the per-channel ranges (the paper's "
+                         "deployment mode, quantization.py:647-649): K1 skips the range reduction and no exchange "
+                         "between ranks is needed; the default is the reference's un-calibrated eval mode "
+                         "(ranges of the current batch)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -237,6 +242,12 @@ def run_native(args):
         return x.to(tdtype).contiguous()
 
     sets = [[synth(*s) for s in shapes] for _ in range(INPUT_SETS)]
+    if args.frozen_ranges:
+        # MCAQYOLO.calibrate (models/mcaq_yolo.py:475-508): EMA statistics from calibration batches, then freeze
+        with torch.no_grad():
+            for x, q in zip(sets[0], quantizers):
+                q.update_running_stats(x)
+                q.freeze_calibration()
     elems = sum(C * H * Wd for C, H, Wd in shapes)
     alg_bytes_step = 3 * esize * elems * B            # K1 read + K3 read + K3 write
 
@@ -245,7 +256,7 @@ def run_native(args):
     hots = []
     for _slot in range(nslot):
         exchanges = None
-        if world > 1 and not args.nccl_ranges and not args.unfused:
+        if world > 1 and not args.nccl_ranges and not args.unfused and not args.frozen_ranges:
             # batch sharded over the GPUs of the node: ranges merged inside K2 over peer memory
             from mcaq_yolo_b200.peer import RangeExchange
             try:
@@ -559,7 +570,8 @@ def run_native(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 arithmetic on %s feature maps" % dtype_name, "data": "synthetic",
         "config": {"workload": args.workload, "per_gpu_batch": B, "shapes_CHW": shapes, "grid": grid, "bits": "2-8",
-                   "mapper": "MLP (fixture weights)", "soft_mask": True, "ranges": "dynamic per batch"
+                   "mapper": "MLP (fixture weights)", "soft_mask": True,
+                   "ranges": "frozen after calibration (no exchange between ranks)" if args.frozen_ranges else "dynamic per batch"
                    + ("" if world == 1 else (" (all-reduced MIN over ranks, NCCL)" if sharded is not None else
                                              " (min over ranks inside K2 through NVLink peer memory, no collective launch)")),
                    "l2": "%d rotating input sets (%.0f MB) > 126 MB L2, no flush" % (INPUT_SETS, INPUT_SETS * esize * elems * B / 1e6),

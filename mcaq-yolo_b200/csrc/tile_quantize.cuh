@@ -19,7 +19,10 @@ __device__ __forceinline__ void bit_limits(int bidx, float& qmin, float& qmax) {
 
 constexpr int QV_THREADS = 256;
 constexpr int QV_CHUNK = 16;
-constexpr int QV_UNROLL = 8;
+#ifndef K3_UNROLL
+#define K3_UNROLL 8
+#endif
+constexpr int QV_UNROLL = K3_UNROLL;
 constexpr int QV_ROW = QV_CHUNK + 1;
 
 
