@@ -215,24 +215,31 @@ static __device__ __noinline__ bool adaptive_exact(const float* Gp, int gs, int 
   return __fmul_rn(Gp[r * gs + x], 255.f) > __fsub_rn(acc, 2.0f);
 }
 
+// Rows [r0, min(r0 + RT, r1)) of the columns of word k: per input row one horizontal 11-tap pass (two
+// interleaved partial chains), fed into the RT independent vertical accumulators of the run's outputs.
+// RT + 10 input rows per RT output rows.
 template <int RT>
-__device__ __forceinline__ void task_adaptive(const Ctx& c, cg::cluster_group& cl, int r0, int k, int lane) {
+__device__ __forceinline__ void task_adaptive(const Ctx& c, cg::cluster_group& cl, int r0, int r1, int k, int lane) {
   const int x = 32 * k + lane;
   const bool valid = x < c.Wc;
   const int xq = valid ? x : c.Wc - 1;
   int xc[11];
 #pragma unroll
   for (int j = 0; j < 11; ++j) xc[j] = clampi(xq + j - 5, 0, c.Wc - 1);
-  float acc[RT], ctr[RT];
+  float acc[RT];
 #pragma unroll
   for (int j = 0; j < RT; ++j) acc[j] = 0.f;
 #pragma unroll
   for (int rr = 0; rr < RT + 10; ++rr) {
     const float* row = c.Gp + clampi(r0 - 5 + rr, 0, c.Hc - 1) * c.gs;
-    float h = 0.f;                                          // horizontal pass on g
+    float h0 = 0.f, h1 = 0.f;                               // horizontal pass on g (any order: filter path)
 #pragma unroll
-    for (int kx = 0; kx < 11; ++kx) h = fmaf(row[xc[kx]], ADAPT1[kx], h);
-    if (rr >= 5 && rr < RT + 5) ctr[rr - 5] = __fmul_rn(row[xc[5]], 255.f);
+    for (int kx = 0; kx < 10; kx += 2) {
+      h0 = fmaf(row[xc[kx]], ADAPT1[kx], h0);
+      h1 = fmaf(row[xc[kx + 1]], ADAPT1[kx + 1], h1);
+    }
+    h0 = fmaf(row[xc[10]], ADAPT1[10], h0);
+    const float h = __fadd_rn(h0, h1);
 #pragma unroll
     for (int j = 0; j < RT; ++j) {
       const int ky = rr - j;
@@ -241,13 +248,17 @@ __device__ __forceinline__ void task_adaptive(const Ctx& c, cg::cluster_group& c
   }
 #pragma unroll
   for (int j = 0; j < RT; ++j) {
-    const float d = __fsub_rn(ctr[j], __fsub_rn(__fmul_rn(acc[j], 255.f), 2.0f));
-    bool bit = d > 0.f;
-    if (fabsf(d) <= ADAPT_GUARD) bit = adaptive_exact(c.Gp, c.gs, c.Hc, c.Wc, r0 + j, xq);
-    const uint32_t word = __ballot_sync(0xffffffffu, bit && valid);
-    if (lane < c.ns) {
-      uint32_t* dst = lane == 0 ? c.BIN : cl.map_shared_rank(c.BIN, (c.rank + lane) % c.ns);
-      dst[(r0 + j) * c.WW + k] = word;
+    const int r = r0 + j;
+    if (r < r1) {                                           // warp-uniform
+      const float ctr = __fmul_rn(c.Gp[r * c.gs + xq], 255.f);
+      const float d = __fsub_rn(ctr, __fsub_rn(__fmul_rn(acc[j], 255.f), 2.0f));
+      bool bit = d > 0.f;
+      if (fabsf(d) <= ADAPT_GUARD) bit = adaptive_exact(c.Gp, c.gs, c.Hc, c.Wc, r, xq);
+      const uint32_t word = __ballot_sync(0xffffffffu, bit && valid);
+      if (lane < c.ns) {
+        uint32_t* dst = lane == 0 ? c.BIN : cl.map_shared_rank(c.BIN, (c.rank + lane) % c.ns);
+        dst[r * c.WW + k] = word;
+      }
     }
   }
 }
@@ -724,9 +735,11 @@ morph_fused_kernel(const FusedArgs A) {
   {
     const int b_lo = max(r_lo - 2, 0), b_hi = min(r_hi + 2, Hc);          // blur rows
     const int nblur = ((b_hi - b_lo + 7) >> 3) * WW;
-    const int RTa = 4;                 // 4-row runs: the unrolled 11x11 body (15 KB) stays resident in the
-                                       // instruction cache and is re-used by every run of every warp
-    const int nadapt = ((r_hi - r_lo) / RTa) * WW;
+#ifndef MCAQ_ADAPT_RT
+#define MCAQ_ADAPT_RT 8
+#endif
+    constexpr int RTa = MCAQ_ADAPT_RT;   // output rows per task: RTa + 10 rows are filtered for RTa outputs
+    const int nadapt = ((r_hi - r_lo + RTa - 1) / RTa) * WW;
     const int nlbp = (tr1 - tr0) * WW;
     const bool fast_act = A.softmask && A.abs_plane && g.aligned;
     const int nact = fast_act ? nlbp : 0;
@@ -742,7 +755,7 @@ morph_fused_kernel(const FusedArgs A) {
 #endif
       if (task < nadapt) {
         const int rg = task / WW, k = task - rg * WW;
-        task_adaptive<4>(c, cl, r_lo + rg * 4, k, lane);
+        task_adaptive<RTa>(c, cl, r_lo + rg * RTa, r_hi, k, lane);
       } else if (task < nadapt + nblur) {
         const int q = task - nadapt;
         const int rg = q / WW, k = q - rg * WW;
