@@ -184,6 +184,7 @@ __device__ __forceinline__ void dense_warp(const float* act, int act_stride, con
 __device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo, int t_hi,
                                                      const float* __restrict__ w, float* scratch_all, float* craw,
                                                      float* __restrict__ raw_out, long long* dbg = nullptr) {
+  // dbg (tools/stage_clocks.py): clock64() after layer 1 / LayerNorm + park / layer 2 of warp 0's first group
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #define CM_DBG(k) do { if (dbg && threadIdx.x == 0 && tg == t_lo) dbg[k] = clock64(); } while (0)
   const float* W0t = w;
@@ -293,6 +294,7 @@ __device__ __forceinline__ void complexity_mlp_warps(const float* phi, int t_lo,
     __syncwarp();
   }
 }
+#undef CM_DBG
 
 // 5x5 bilateral filter with replicate padding (morphology.py:309-354) and clamp, for tiles
 // [t_lo, t_hi); craw must hold ALL tiles of the image.  wgt: 25*(t_hi-t_lo) floats of scratch.

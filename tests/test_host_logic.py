@@ -169,3 +169,35 @@ def test_range_merge_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_kd_geometry_rule_matches_vector_path_contract():
+    """ops.kd_geometry_ok mirrors the C-side test of the training vector path (include/mcaq_b200.h:
+    H*W % VEC == 0, W % 4 == 0, W % Wt == 0, (W / Wt) % 4 == 0)."""
+    import torch
+    from mcaq_yolo_b200 import ops
+
+    def ok(shape, wt, dtype=torch.float32):
+        return ops.kd_geometry_ok(torch.empty(shape, dtype=dtype), torch.empty(shape[0], wt, wt))
+
+    assert ok((2, 64, 80, 80), 10) and ok((2, 128, 40, 40), 10) and ok((2, 256, 20, 20), 5)
+    assert ok((2, 256, 20, 20), 5, torch.bfloat16) and ok((1, 128, 160, 160), 10, torch.bfloat16)
+    assert not ok((1, 3, 7, 9), 2) and not ok((2, 8, 50, 50), 12)
+    assert not ok((1, 8, 12, 12), 6)                    # tile width 2: segments would straddle tiles
+    assert ok((1, 8, 5, 12), 3) and not ok((1, 8, 5, 12), 3, torch.bfloat16)     # 60 pixels: multiple of 4, not of 8
+
+
+def test_mlp_mapper_is_a_staircase_in_the_oracle():
+    """The step table of the fused kernel (mcaq_mapper_steps) relies on the monotonic mapper of Eq.18
+    giving a non-decreasing integer bit width in the scalar complexity: check it on the oracle's
+    restatement of the reference mapper with the fixture weights, over a dense sorted sample."""
+    import mcaq_oracle as o
+    from golden_util import weights
+    W = weights()
+    rng = np.random.default_rng(11)
+    c = np.sort(np.concatenate([rng.random(20000, dtype=np.float32), np.linspace(0, 1, 2049, dtype=np.float32)]))
+    for t in (1.0, 0.7, 1.3):
+        bits = o.mlp_bit_mapper(c.reshape(1, 1, -1), W["mapper"], temperature=t, continuous=False).reshape(-1)
+        assert np.all(np.diff(bits) >= 0), "mapper output must be non-decreasing in complexity"
+        assert set(np.unique(bits)) <= set(np.arange(2, 9, dtype=np.float32))
+    assert np.unique(o.mlp_bit_mapper(c.reshape(1, 1, -1), W["mapper"], temperature=1.0, continuous=False)).size >= 4
