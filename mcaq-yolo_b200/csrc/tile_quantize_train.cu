@@ -271,7 +271,7 @@ train_bwd_vec_kernel(const T* __restrict__ gy, const T* __restrict__ x, T* __res
           const float2 dxv = fadd2_sep(fmul2(gm, omf2), fmul2(gm, f2));
           out[i] = dxv.x;
           out[i + 1] = dxv.y;
-          const float2 dq = fadd2(qhi, make_float2(-qlo.x, -qlo.y));
+          const float2 dq = fadd2_sep(qhi, make_float2(-qlo.x, -qlo.y));      // q_hi, q_lo are packed products
           acc_bit[s] = fmaf(gm.x, dq.x, acc_bit[s]);
           acc_bit[s] = fmaf(gm.y, dq.y, acc_bit[s]);
           if (HAS_MASK) {
