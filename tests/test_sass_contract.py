@@ -72,3 +72,37 @@ def test_ffma2_count_is_exactly_the_source(sass, pattern, pairs, quants, extra):
 def test_packed_instructions_present(sass):
     for pattern in (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb1ELb0E", r"train_fwd_vec_kernelIfLi4ELb1ELb0E"):
         assert count(sass, pattern, "FMUL2") > 0 and count(sass, pattern, "FADD2") > 0
+
+
+# ---- occupancy contract: the register caps the design relies on -------------------
+def _res_usage(obj):
+    txt = subprocess.run(["cuobjdump", "-res-usage", os.path.join(LIBDIR, obj)], capture_output=True, text=True).stdout
+    out = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", txt):
+        out[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    return out
+
+
+def test_register_caps_of_the_hot_kernels(sass):
+    """K1: <= 128 registers (512 resident threads per SM), K2: <= 64 (four 256-thread CTAs), K3: <= 80
+    (three 256-thread CTAs), training forms: <= 128 (two CTAs); stack (spill) frames stay small."""
+    k1 = {n: v for n, v in _res_usage("reduce_planes.o").items() if "reduce_planes_kernel" in n}
+    assert k1 and all(r <= 128 for r, _ in k1.values())
+    assert all(st == 0 for n, (r, st) in k1.items() if re.search(r"Li8ELi(4|8|16)ELi2E|IfLi4ELi(4|8|16)ELi2E", n)), "no spills in the YOLO-width K1 variants"
+    k2 = _res_usage("morph_fused.o")
+    (r2, st2), = [v for n, v in k2.items() if "morph_fused_kernel" in n]
+    assert r2 <= 64 and st2 <= 128
+    k3 = {n: v for n, v in _res_usage("tile_quantize.o").items() if "tile_quantize_vec_kernel" in n}
+    assert k3 and all(r <= 80 for r, _ in k3.values())
+    # spill frames: the product variants (no int8 code output) stay under 160 bytes, the code-emitting test variants 256
+    assert all(st <= (256 if re.search(r"Lb[01]ELb1EEEv", n) else 160) for n, (_, st) in k3.items())
+    kt = {n: v for n, v in _res_usage("tile_quantize_train.o").items() if "_vec_kernel" in n}
+    assert kt and all(r <= 128 and st <= 64 for r, st in kt.values())
+
+
+def test_bandwidth_kernels_use_128_bit_accesses(sass):
+    txt = subprocess.run(["cuobjdump", "-sass", os.path.join(LIBDIR, "reduce_planes.o")], capture_output=True, text=True).stdout
+    assert re.search(r"LDG\.E(\.\w+)*\.128", txt), "K1 loads 16-byte vectors"
+    for pattern in (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb1ELb0E", r"train_bwd_vec_kernelIfLi4ELb1ELb0E"):
+        name, = [n for n in sass if re.search(pattern, n)]
+        assert re.search(r"LD(G)?\.E(\.\w+)*\.128", sass[name]) and re.search(r"STG\.E(\.\w+)*\.128", sass[name]), pattern
