@@ -569,9 +569,9 @@ morph_fused_kernel(const FusedArgs A) {
   float* mmx = red + 64;                                       // [16] per-rank min / max
   float* lutn = mmx + 16;                                      // [260] log(N + 1)
   float* lutp = lutn + 260;                                    // [tile^2 + 1 (+pad)] log2(k / tile^2 + 1e-10)
-  // the three parameter blocks (31 KB) are read through L1 (__ldg-style coalesced loads) where they
-  // are used: every CTA of every image shares the same lines, and shared memory stays free for a
-  // second resident CTA
+  // parameter blocks: the complexity-MLP block (11.5 KB) is staged into the dead plane area right before
+  // N1 (L1 starts cold in every launch), the soft-mask block over the dead LUT; the mapper block is only
+  // read (through L1) when its step table is absent or invalid
   const float* w_cmlp = A.cmlp;
   const float* w_map = A.mapper;
   float* w_sm = lutn;                                          // soft-mask block (196 floats) staged over the dead LUT
