@@ -1,9 +1,8 @@
-"""Import alias: the package lives in the directory `mcaq-yolo_b200/` (not a valid Python
-identifier), this shim makes it importable as `mcaq_yolo_b200`."""
-import os as _os
+"""mcaq_yolo_b200: B200-native (sm_100a) implementation of MCAQ-YOLO's data-parallel hot path.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "mcaq-yolo_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
-del _os, _f, _real
+Host side mirrors the reference's interface for that path (same class names, constructor
+arguments, call signatures and state_dict keys as mcaq_yolo/core/*.py) on top of the C-ABI
+library libmcaq_b200.so (include/mcaq_b200.h).  There is no CPU fallback: every op raises
+if the CUDA library or a CUDA device is missing.
+"""
+__version__ = "0.1.0"

@@ -5,7 +5,7 @@ This file is a numpy restatement of the reference's algorithm for the path
 `complexity analyzer -> bit mapper -> soft mask -> tile-wise quantize`
 (SURVEY.md section 8a).  Only `tests/`, `__graft_entry__.smoke()` and the
 `cpu_baseline` / `--impl reference` legs of `bench.py` may import it; the
-product path (`mcaq-yolo_b200/`) never does and fails loudly when the CUDA
+product path (`mcaq_yolo_b200/`) never does and fails loudly when the CUDA
 library is missing.
 
 Parity pin: every function below is checked against outputs of the real
@@ -108,7 +108,7 @@ def rint32(x):
 
 # ----------------------------------------------------------------------------
 # fixed constants (shared bit-for-bit with the CUDA side, see
-# mcaq-yolo_b200/constants.py which recomputes them the same way)
+# mcaq_yolo_b200/constants.py which recomputes them the same way)
 # ----------------------------------------------------------------------------
 
 def gaussian_kernel2d(k: int, sigma: float) -> np.ndarray:

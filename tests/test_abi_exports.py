@@ -56,7 +56,7 @@ def test_library_is_sm100a_only(lib_path):
 def test_no_cpu_fallback_in_product():
     """The product never imports the oracle and refuses CPU tensors."""
     import torch
-    pkg = os.path.join(ROOT, "mcaq-yolo_b200")
+    pkg = os.path.join(ROOT, "mcaq_yolo_b200")
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()

@@ -114,7 +114,7 @@ def test_constant_block_and_packers_match_oracle():
 
 def test_generated_consts_header_is_current():
     import gen_consts_header
-    path = os.path.join(ROOT, "mcaq-yolo_b200", "csrc", "mcaq_consts.cuh")
+    path = os.path.join(ROOT, "mcaq_yolo_b200", "csrc", "mcaq_consts.cuh")
     assert open(path).read() == gen_consts_header.generate(), "run tools/gen_consts_header.py"
 
 

@@ -13,7 +13,7 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIBDIR = os.path.join(ROOT, "mcaq-yolo_b200", "lib")
+LIBDIR = os.path.join(ROOT, "mcaq_yolo_b200", "lib")
 
 
 @pytest.fixture(scope="module")

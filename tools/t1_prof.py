@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Cycles warp 0 spends per T1 task type (adaptive / blur / LBP / activity) in the morphology kernel.
-Needs a profiling build: MCAQ_NVCC_EXTRA="-DMCAQ_T1_PROF" python mcaq-yolo_b200/build.py --force"""
+Needs a profiling build: MCAQ_NVCC_EXTRA="-DMCAQ_T1_PROF" python mcaq_yolo_b200/build.py --force"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
