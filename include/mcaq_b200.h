@@ -197,6 +197,12 @@ MCAQ_API int mcaq_xchg_free(void* p);
 MCAQ_API int mcaq_xchg_export(void* p, void* handle64);              /* cudaIpcGetMemHandle */
 MCAQ_API int mcaq_xchg_open(const void* handle64, void** out);       /* cudaIpcOpenMemHandle */
 MCAQ_API int mcaq_xchg_close(void* p);
+/* Waits are bounded (default 2 s per wait): a peer that died or ran a different sequence of exchange
+ * steps makes the waiting launch keep THIS rank's own ranges and record the step in the buffer's error
+ * word instead of spinning forever.  mcaq_xchg_error synchronises, returns the first such step (0 = none)
+ * in *step and clears the word. */
+MCAQ_API void mcaq_xchg_set_timeout_ms(int ms);
+MCAQ_API int mcaq_xchg_error(void* local, int* step);
 /* stand-alone halves of the protocol (tests, host-driven use): publish `packed` as this rank's
  * next step / wait for all ranks and write the merged vector */
 MCAQ_API int mcaq_xchg_publish(void* const* peers, int rank, int world, const float* packed, int C, void* stream);
@@ -250,6 +256,9 @@ MCAQ_API void mcaq_debug_stage_clocks(long long* dev_buf);
 /* debug / tuning: force the number of CTAs (cluster size 1, 2, 4 or 8) an image is split over in
  * the morphology kernel; 0 = automatic */
 MCAQ_API void mcaq_debug_cluster_split(int ns);
+
+/* debug / tuning: force the CTA size (threads, multiple of 32, 64..512) of the morphology kernel; 0 = automatic */
+MCAQ_API void mcaq_debug_morph_threads(int n);
 
 /* debug / tests: 1 = route the training forward / backward through the scalar kernels even when the
  * vector path applies (the two must agree: y and dx bit for bit) */

@@ -18,6 +18,7 @@ PROTOTYPES = {
     "mcaq_debug_stage_clocks": (None, [c_void_p]),
     "mcaq_debug_cluster_split": (None, [c_int]),
     "mcaq_morph_policy": (None, [c_int]),
+    "mcaq_debug_morph_threads": (None, [c_int]),
     "mcaq_ranges_reset": (c_int, [c_void_p, c_int, c_void_p]),
     "mcaq_reduce_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -64,6 +65,8 @@ PROTOTYPES = {
     "mcaq_xchg_export": (c_int, [c_void_p, c_void_p]),
     "mcaq_xchg_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "mcaq_xchg_close": (c_int, [c_void_p]),
+    "mcaq_xchg_set_timeout_ms": (None, [c_int]),
+    "mcaq_xchg_error": (c_int, [c_void_p, POINTER(c_int)]),
     "mcaq_xchg_publish": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mcaq_xchg_merge": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mcaq_morph_fused_xchg": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -96,6 +99,8 @@ def load():
             fn = getattr(lib, name)          # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("MCAQ_K2_THREADS"):      # tuning aid: force the morphology kernel's CTA size
+            lib.mcaq_debug_morph_threads(int(os.environ["MCAQ_K2_THREADS"]))
         if os.environ.get("MCAQ_K2_SPLIT"):        # tuning aid: force the morphology kernel's cluster split
             lib.mcaq_debug_cluster_split(int(os.environ["MCAQ_K2_SPLIT"]))
         _lib = lib

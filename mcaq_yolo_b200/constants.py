@@ -124,6 +124,23 @@ def pack_mapping_network(seq) -> torch.Tensor:
 MAPPER_STEPS_FLOATS = 12
 
 
+def mapping_is_monotone(mapper) -> bool:
+    """True when bits(c) of the MLP mapper is provably non-decreasing in c, the condition under which its
+    eval output may be read off a step table: Eq.18's constraint is declared (`enforce_monotonicity`) AND
+    actually holds -- every Linear weight and every BatchNorm gamma (the sign of the folded eval scale)
+    is >= 0.  A checkpoint saved before `enforce_weight_constraints()` ran, or a mapper built with
+    enforce_monotonicity=False, fails this and is evaluated as the network it is.  One device->host read
+    per weights version (cached like the packed blocks)."""
+    if not getattr(mapper, "enforce_monotonicity", False):
+        return False
+    seq = mapper.mapping_network
+    ts = [seq[i].weight for i in (0, 1, 3, 4, 6, 7, 9)]
+
+    def build():
+        return bool(torch.stack([t.detach().min() for t in ts]).min().item() >= 0.0)
+    return _cached(seq, "monotone", ts, build)
+
+
 def pack_mapping_steps(seq, temperature, min_bits: float, max_bits: float) -> torch.Tensor:
     """The mapper block followed by its step table (include/mcaq_b200.h: mcaq_mapper_steps) for this
     temperature and bit range: eval-mode integer bit maps of the fused kernel are read off the

@@ -41,7 +41,10 @@ namespace cg = cooperative_groups;
 
 namespace mcaq {
 
-constexpr int MORPH_MAX_THREADS = 256;
+#ifndef MCAQ_MORPH_MAX_THREADS
+#define MCAQ_MORPH_MAX_THREADS 512
+#endif
+constexpr int MORPH_MAX_THREADS = MCAQ_MORPH_MAX_THREADS;
 
 struct MorphGeom {
   int B, C, H, W, tile, ht, wt, Hc, Wc, WW, ntiles, S;
@@ -50,8 +53,10 @@ struct MorphGeom {
   int gs, bs;         // row strides of G (Wc + 4) and BL (Wc + 2)
   int aligned;        // H == Hc && W == Wc: soft-mask windows are the analyzer's tiles
   // shared-memory layout, offsets in 4-byte words
-  int off_bl, off_mag, off_bits, off_tiles, off_w, words;
+  int off_bl, off_mag, off_h, off_bits, off_tiles, off_w, words;
+  int hs;             // row stride of the horizontally filtered plane (Wc + 1: odd)
   int max_own;        // most tiles a CTA owns
+  int threads;        // CTA size (fixes the per-warp scratch of the tile networks)
 };
 
 struct FusedArgs {
@@ -135,6 +140,7 @@ struct Ctx {
   const float* Gp; int gs;
   float* BLp; int bs;
   float* MAGp;
+  float* Hp; int hs;       // horizontally filtered gray (adaptive threshold), biased like Gp without pad columns
   uint32_t *BIN, *DIR0, *DIR1, *STRONG, *WEAK, *EDGE;
   int Hc, Wc, WW, tile, tshift, wt;
   int r_lo, r_hi;
@@ -215,31 +221,42 @@ static __device__ __noinline__ bool adaptive_exact(const float* Gp, int gs, int 
   return __fmul_rn(Gp[r * gs + x], 255.f) > __fsub_rn(acc, 2.0f);
 }
 
-// Rows [r0, min(r0 + RT, r1)) of the columns of word k: per input row one horizontal 11-tap pass (two
-// interleaved partial chains), fed into the RT independent vertical accumulators of the run's outputs.
-// RT + 10 input rows per RT output rows.
+// Horizontal 11-tap pass (replicate borders) of image rows lr0 + lane (< r_end) for columns [x0, x1), x1 - x0 a
+// multiple of 8: a thread owns a row and produces 8 consecutive outputs from 18 inputs held in registers.
+// The column clamps are warp-uniform, rows of G have an odd stride (conflict-free for lane = row).
+__device__ __forceinline__ void task_adapt_h(const Ctx& c, int r_begin, int r_end, int x0, int x1, int lane) {
+  const int r = min(r_begin + lane, r_end - 1);
+  const bool ok = r_begin + lane < r_end;
+  const float* row = c.Gp + r * c.gs;
+  float* out = c.Hp + r * c.hs;
+#pragma unroll 1
+  for (int xb = x0; xb < x1; xb += 8) {
+    float v[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) v[j] = row[clampi(xb + j - 5, 0, c.Wc - 1)];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float acc = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < 11; ++kx) acc = fmaf(v[o + kx], ADAPT1[kx], acc);
+      if (ok && xb + o < c.Wc) out[xb + o] = acc;
+    }
+  }
+}
+
+// Rows [r0, min(r0 + RT, r1)) of the columns of word k: the vertical 11-tap pass over the horizontally
+// filtered plane (RT + 10 input rows per RT output rows, RT independent accumulators), then the sign.
 template <int RT>
 __device__ __forceinline__ void task_adaptive(const Ctx& c, cg::cluster_group& cl, int r0, int r1, int k, int lane) {
   const int x = 32 * k + lane;
   const bool valid = x < c.Wc;
   const int xq = valid ? x : c.Wc - 1;
-  int xc[11];
-#pragma unroll
-  for (int j = 0; j < 11; ++j) xc[j] = clampi(xq + j - 5, 0, c.Wc - 1);
   float acc[RT];
 #pragma unroll
   for (int j = 0; j < RT; ++j) acc[j] = 0.f;
 #pragma unroll
   for (int rr = 0; rr < RT + 10; ++rr) {
-    const float* row = c.Gp + clampi(r0 - 5 + rr, 0, c.Hc - 1) * c.gs;
-    float h0 = 0.f, h1 = 0.f;                               // horizontal pass on g (any order: filter path)
-#pragma unroll
-    for (int kx = 0; kx < 10; kx += 2) {
-      h0 = fmaf(row[xc[kx]], ADAPT1[kx], h0);
-      h1 = fmaf(row[xc[kx + 1]], ADAPT1[kx + 1], h1);
-    }
-    h0 = fmaf(row[xc[10]], ADAPT1[10], h0);
-    const float h = __fadd_rn(h0, h1);
+    const float h = c.Hp[clampi(r0 - 5 + rr, 0, c.Hc - 1) * c.hs + xq];
 #pragma unroll
     for (int j = 0; j < RT; ++j) {
       const int ky = rr - j;
@@ -540,7 +557,7 @@ __device__ __forceinline__ void task_hysteresis(const Ctx& c, int R0, int lane) 
 // 64 registers per thread (4 CTAs of 256 threads fit the register file): the kernel is issue / latency
 // bound, so resident CTAs of other images, scales and steps -- and the HBM-bound K1 / K3 CTAs --
 // fill its idle issue slots
-__global__ void __launch_bounds__(MORPH_MAX_THREADS, 4)
+__global__ void __launch_bounds__(MORPH_MAX_THREADS, 1024 / MORPH_MAX_THREADS)
 morph_fused_kernel(const FusedArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const MorphGeom& g = A.g;
@@ -641,8 +658,8 @@ morph_fused_kernel(const FusedArgs A) {
     if (xstep == 0) return;
     const float* local = A.px.base[A.px.rank];
     __syncthreads();
-    xchg_wait(local, A.px.world, xstep, tid);
-    __syncthreads();
+    const bool ok = xchg_wait(local, A.px.world, xstep, tid, A.px.timeout_ns);
+    if (!__syncthreads_and(ok)) return;     // timed out: `packed` keeps this rank's ranges, error word set
     for (int i = tid; i < 2 * g.C; i += NT) A.packed[i] = xchg_min(local, A.px.world, 2 * g.C, xstep, i);
   };
 
@@ -651,10 +668,10 @@ morph_fused_kernel(const FusedArgs A) {
   c.Gp = G + (5 - r_lo) * g.gs + 2;
   c.BLp = BL + (2 - r_lo) * g.bs + 1;
   c.MAGp = MAG + (1 - r_lo) * Wc;
+  c.Hp = S + g.off_h + (5 - r_lo) * g.hs; c.hs = g.hs;
   c.BIN = BIN; c.DIR0 = DIR0; c.DIR1 = DIR1; c.STRONG = STRONG; c.WEAK = WEAK; c.EDGE = EDGE;
   c.Hc = Hc; c.Wc = Wc; c.WW = WW; c.tile = tile; c.tshift = tshift; c.wt = wt;
   c.r_lo = r_lo; c.r_hi = r_hi; c.ns = ns; c.rank = rank;
-  float* Gw = G + (5 - r_lo) * g.gs + 2;                   // writable alias of c.Gp
 
   // ---- L: gray = sum / C for rows [r_lo-5, r_hi+5) (zero outside the image and in the pad
   //      columns), min / max over the band; BL and the histograms start as zeros -------------------
@@ -668,28 +685,25 @@ morph_fused_kernel(const FusedArgs A) {
     const int nbl = (r_hi - r_lo + 4) * g.bs;
     for (int i = tid; i < nbl; i += NT) BL[i] = 0.f;
   }
-  {
-    const int nrows = r_hi - r_lo + 10;
-    for (int lr0 = warp * 4; lr0 < nrows; lr0 += nwarps * 4) {
-      for (int c0 = lane; c0 < g.gs; c0 += 32) {
-        const int x = c0 - 2;
-        const bool xok = x >= 0 && x < Wc;
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = r_lo - 5 + lr0 + u;
-          v[u] = (xok && lr0 + u < nrows && r >= 0 && r < Hc) ? __ldg(sp + r * g.W + x) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = r_lo - 5 + lr0 + u;
-          if (lr0 + u < nrows) {
-            const bool in = xok && r >= 0 && r < Hc;
-            const float q = in ? div_channels(v[u], fC, rC, cpow2) : 0.f;
-            G[(lr0 + u) * g.gs + c0] = q;
-            if (in && r >= r_lo && r < r_hi) { lmin = fminf(lmin, q); lmax = fmaxf(lmax, q); }
-          }
-        }
+  // band min / max of gray = sum / C straight from global memory (the plane is L2 resident: K1 just
+  // wrote it); the values are formed again, identically, when G is filled below
+  const bool vec4 = (g.W & 3) == 0 && (reinterpret_cast<uintptr_t>(sp) & 15) == 0;
+  if (vec4 && g.W == Wc) {                                        // band rows are one contiguous run
+    const float4* p4 = reinterpret_cast<const float4*>(sp + (long long)r_lo * g.W);
+    const int n4 = ((r_hi - r_lo) * Wc) >> 2;
+    for (int i = tid; i < n4; i += NT) {
+      const float4 v = __ldg(p4 + i);
+      const float q0 = div_channels(v.x, fC, rC, cpow2), q1 = div_channels(v.y, fC, rC, cpow2);
+      const float q2 = div_channels(v.z, fC, rC, cpow2), q3 = div_channels(v.w, fC, rC, cpow2);
+      lmin = fminf(fminf(lmin, fminf(q0, q1)), fminf(q2, q3));
+      lmax = fmaxf(fmaxf(lmax, fmaxf(q0, q1)), fmaxf(q2, q3));
+    }
+  } else {
+    for (int r = r_lo + warp; r < r_hi; r += nwarps) {
+      for (int x = lane; x < Wc; x += 32) {
+        const float q = div_channels(__ldg(sp + (long long)r * g.W + x), fC, rC, cpow2);
+        lmin = fminf(lmin, q);
+        lmax = fmaxf(lmax, q);
       }
     }
   }
@@ -714,74 +728,103 @@ morph_fused_kernel(const FusedArgs A) {
     for (int pr = 1; pr < ns; ++pr) { gmin = fminf(gmin, mmx[2 * pr]); gmax = fmaxf(gmax, mmx[2 * pr + 1]); }
   }
   STAGE_CLOCK(1);
-  // ---- N: normalise in place (morphology.py:378-383); rows outside the image stay zero ---------
+  // ---- N: G = normalised gray (morphology.py:378-383) for rows [r_lo-5, r_hi+5): zero rows outside the
+  //      image, zero pad columns -------------------------------------------------------------------
   {
     const float den = __fadd_rn(__fsub_rn(gmax, gmin), 1e-8f);
     const float rden = __frcp_rn(den);
-    const int ra = max(r_lo - 5, 0), rb = min(r_hi + 5, Hc);
-    for (int r = ra + warp; r < rb; r += nwarps) {
-      float* row = Gw + r * g.gs;
-      for (int x = lane; x < Wc; x += 32) {
-        const float v = div_exact(__fsub_rn(row[x], gmin), den, rden);
-        row[x] = v;
-        if (A.gray_dbg && r >= r_lo && r < r_hi) A.gray_dbg[(long long)b * Hc * Wc + r * Wc + x] = v;
+    const int nrows = r_hi - r_lo + 10;
+    const int npad = g.gs - Wc;
+    for (int i = tid; i < nrows * npad; i += NT) {                // pad columns: 2 left, the rest right
+      const int lr = i / npad, k = i - lr * npad;
+      G[lr * g.gs + (k < 2 ? k : Wc + k)] = 0.f;
+    }
+    if (vec4) {
+      const int W4 = Wc >> 2;
+      const uint32_t m4 = div_magic(W4);
+      for (int i = tid; i < nrows * W4; i += NT) {
+        const int lr = fast_div(i, m4), x = (i - lr * W4) << 2;
+        const int r = r_lo - 5 + lr;
+        float* dst = G + lr * g.gs + 2 + x;
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r >= 0 && r < Hc) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(sp + (long long)r * g.W + x));
+          o[0] = div_exact(__fsub_rn(div_channels(v.x, fC, rC, cpow2), gmin), den, rden);
+          o[1] = div_exact(__fsub_rn(div_channels(v.y, fC, rC, cpow2), gmin), den, rden);
+          o[2] = div_exact(__fsub_rn(div_channels(v.z, fC, rC, cpow2), gmin), den, rden);
+          o[3] = div_exact(__fsub_rn(div_channels(v.w, fC, rC, cpow2), gmin), den, rden);
+          if (A.gray_dbg && r >= r_lo && r < r_hi)
+            *reinterpret_cast<float4*>(A.gray_dbg + (long long)b * Hc * Wc + r * Wc + x) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3];
+      }
+    } else {
+      for (int lr = warp; lr < nrows; lr += nwarps) {
+        const int r = r_lo - 5 + lr;
+        const bool rin = r >= 0 && r < Hc;
+        float* row = G + lr * g.gs + 2;
+        for (int x = lane; x < Wc; x += 32) {
+          float v = 0.f;
+          if (rin) {
+            v = div_exact(__fsub_rn(div_channels(__ldg(sp + (long long)r * g.W + x), fC, rC, cpow2), gmin), den, rden);
+            if (A.gray_dbg && r >= r_lo && r < r_hi) A.gray_dbg[(long long)b * Hc * Wc + r * Wc + x] = v;
+          }
+          row[x] = v;
+        }
       }
     }
   }
   __syncthreads();
   STAGE_CLOCK(2);
 
-  // ---- T1: independent warp tasks on G ----------------------------------------------------------
+  // ---- T1: independent warp tasks on G, two phases (the vertical half of the adaptive threshold needs
+  //      the horizontally filtered plane) ------------------------------------------------------------
   {
     const int b_lo = max(r_lo - 2, 0), b_hi = min(r_hi + 2, Hc);          // blur rows
     const int nblur = ((b_hi - b_lo + 7) >> 3) * WW;
 #ifndef MCAQ_ADAPT_RT
 #define MCAQ_ADAPT_RT 8
 #endif
-    constexpr int RTa = MCAQ_ADAPT_RT;   // output rows per task: RTa + 10 rows are filtered for RTa outputs
+    constexpr int RTa = MCAQ_ADAPT_RT;   // output rows per vertical task: RTa + 10 input rows for RTa outputs
     const int nadapt = ((r_hi - r_lo + RTa - 1) / RTa) * WW;
+    const int h_lo = max(r_lo - 5, 0), h_hi = min(r_hi + 5, Hc);          // rows of the horizontal pass
+    constexpr int HSEG = 40;                                              // columns per horizontal task
+    const int nhseg = (Wc + HSEG - 1) / HSEG;
+    const int nhor = ((h_hi - h_lo + 31) >> 5) * nhseg;
     const int nlbp = (tr1 - tr0) * WW;
     const bool fast_act = A.softmask && A.abs_plane && g.aligned;
     const int nact = fast_act ? nlbp : 0;
-    const int ntask = nadapt + nblur + nlbp + nact;
     const float* ap = A.abs_plane ? A.abs_plane + (long long)b * g.H * g.W : nullptr;
-#ifdef MCAQ_T1_PROF
-    long long t1p[4] = {0, 0, 0, 0};
-#endif
-    for (int task = warp; task < ntask; task += nwarps) {
-#ifdef MCAQ_T1_PROF
-      const long long t1s = clock64();
-      const int t1k = task < nadapt ? 0 : (task < nadapt + nblur ? 1 : (task < nadapt + nblur + nlbp ? 2 : 3));
-#endif
-      if (task < nadapt) {
-        const int rg = task / WW, k = task - rg * WW;
-        task_adaptive<RTa>(c, cl, r_lo + rg * RTa, r_hi, k, lane);
-      } else if (task < nadapt + nblur) {
-        const int q = task - nadapt;
-        const int rg = q / WW, k = q - rg * WW;
-        task_blur<8>(c, b_lo + rg * 8, b_hi, k, lane, hloc);
-      } else if (task < nadapt + nblur + nlbp) {
-        const int q = task - nadapt - nblur;
+    // phase a: horizontal pass | LBP + gradient variance | tile activity
+    for (int task = warp; task < nhor + nlbp + nact; task += nwarps) {
+      if (task < nhor) {
+        const int rg = task / nhseg, sg = task - rg * nhseg;
+        task_adapt_h(c, h_lo + 32 * rg, h_hi, sg * HSEG, min((sg + 1) * HSEG, Wc), lane);
+      } else if (task < nhor + nlbp) {
+        const int q = task - nhor;
         const int tyl = q / WW, k = q - tyl * WW;
         task_lbp_var(c, tr0 + tyl, k, lane, lutp, phis,
                      A.lbp_dbg ? A.lbp_dbg + (long long)b * g.ntiles * 10 : nullptr);
       } else {
-        const int q = task - nadapt - nblur - nlbp;
+        const int q = task - nhor - nlbp;
         const int tyl = q / WW, k = q - tyl * WW;
         task_act(c, ap, g.W, fC, rC, cpow2, tr0 + tyl, k, lane, act_s);
       }
-#ifdef MCAQ_T1_PROF
-      t1p[t1k] += clock64() - t1s;
-#endif
     }
-#ifdef MCAQ_T1_PROF
-    if (clk && tid == 0 && rank == 0) {                 // warp 0's cycles per task type (debug build only)
-      clk[(long long)b * 16 + 13] = t1p[0]; clk[(long long)b * 16 + 14] = t1p[1];
-      clk[(long long)b * 16 + 15] = t1p[2] * 1000000LL + t1p[3];
-    }
-#endif
     if (A.softmask && A.abs_plane && !g.aligned)
       softmask_act_generic(ap, g.C, g.H, g.W, g.ht, g.wt, tr0, tr1, act_s);
+    __syncthreads();
+    // phase b: vertical pass + sign -> BIN | 5x5 blur -> BL + histogram
+    for (int task = warp; task < nadapt + nblur; task += nwarps) {
+      if (task < nadapt) {
+        const int rg = task / WW, k = task - rg * WW;
+        task_adaptive<RTa>(c, cl, r_lo + rg * RTa, r_hi, k, lane);
+      } else {
+        const int q = task - nadapt;
+        const int rg = q / WW, k = q - rg * WW;
+        task_blur<8>(c, b_lo + rg * 8, b_hi, k, lane, hloc);
+      }
+    }
   }
   __syncthreads();
   for (int pr = 0; pr < ns; ++pr) {                               // integer counts: order-free, exact
@@ -974,7 +1017,7 @@ morph_fused_kernel(const FusedArgs A) {
   // ---- N1: complexity MLP (own tiles) -> all-gather -> bilateral (own tiles) -------------------------
   float* scratch = S;                        // the float planes are dead from here on
   const int nt = g.ntiles;
-  float* w_cmlp_s = S + (MORPH_MAX_THREADS / 32) * NET_WARP_SCRATCH;   // staged behind the per-warp scratch
+  float* w_cmlp_s = S + nwarps * NET_WARP_SCRATCH;   // staged behind the per-warp scratch
   copy_params(w_cmlp, w_cmlp_s, CMLP_SMEM_FLOATS);
   __syncthreads();
   complexity_mlp_warps(phi8, t_lo, t_hi, w_cmlp_s, scratch, craw_s,
@@ -1076,19 +1119,32 @@ static int pick_split(int B, int ht, int tile) {
   return ns < 1 ? 1 : ns;
 }
 
+static int g_force_threads = 0;
+// debug / tuning: force the CTA size of the morphology kernel (0 = automatic)
+extern "C" void mcaq_debug_morph_threads(int n) { g_force_threads = n; }
+
+static int pick_threads(const MorphGeom& g) {
+  if (g_force_threads >= 64 && g_force_threads <= MORPH_MAX_THREADS && g_force_threads % 32 == 0) return g_force_threads;
+  const long long band = (long long)g.band_max * g.Wc;
+  return band <= 512 ? 128 : 256;
+}
+
 // shared-memory layout for a given split; returns bytes of dynamic smem
 static long long layout(MorphGeom& g) {
   g.band_max = ((g.ht + g.ns - 1) / g.ns) * g.tile;
+  g.threads = pick_threads(g);
   g.max_own = ((g.ht + g.ns - 1) / g.ns) * g.wt;
   // float planes; a partial 8-row run of a stencil task reads at most 7 rows past its plane (results
   // discarded), which stays inside the following plane / the margin after BL
   const long long wG = (long long)(g.band_max + 10) * g.gs;      // also holds MAG ((band+2) * Wc) after T1
   const long long wBL = (long long)(g.band_max + 4) * g.bs + 8LL * g.gs;
   // the same region later holds the per-warp net scratch, bilateral weights, mask classes
-  const long long nets = max_i((MORPH_MAX_THREADS / 32) * NET_WARP_SCRATCH + CMLP_SMEM_FLOATS, 2 * g.ntiles + 25 * g.max_own);
+  const long long nets = max_i((g.threads / 32) * NET_WARP_SCRATCH + CMLP_SMEM_FLOATS, 2 * g.ntiles + 25 * g.max_own);
   g.off_bl = (int)((wG + 3) & ~3LL);
   g.off_mag = 0;
-  long long bits0 = (g.off_bl + wBL + 3) & ~3LL;
+  g.off_h = (int)((g.off_bl + wBL + 3) & ~3LL);
+  const long long wH = (long long)(g.band_max + 10) * g.hs;      // rows [r_lo-5, r_hi+5) of the horizontal pass
+  long long bits0 = (g.off_h + wH + 3) & ~3LL;
   if (bits0 < ((nets + 3) & ~3LL)) bits0 = (nets + 3) & ~3LL;
   g.off_bits = (int)bits0;
   const long long tiles0 = (bits0 + 6LL * g.Hc * g.WW + 3) & ~3LL;
@@ -1113,7 +1169,8 @@ static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size) {
   g.S = 0;
   for (int s = 2; s <= g.tile; s <<= 1) g.S++;
   g.aligned = (H == g.Hc && W == g.Wc) ? 1 : 0;
-  g.gs = g.Wc + 4;
+  g.gs = g.Wc + 5;          // two zero columns each side; odd, so lane = row accesses are conflict-free
+  g.hs = g.Wc + 1;
   g.bs = g.Wc + 2;
   g.ns = pick_split(B, g.ht, g.tile);
   long long bytes = layout(g);
@@ -1127,11 +1184,6 @@ static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size) {
 }
 
 // threads per CTA from the pixels of the largest band
-static int pick_threads(const MorphGeom& g) {
-  const long long band = (long long)g.band_max * g.Wc;
-  return band <= 512 ? 128 : MORPH_MAX_THREADS;
-}
-
 static int launch_fused(FusedArgs& A, long long smem, int threads, cudaStream_t st) {
   if (smem > 227 * 1024) return MCAQ_ETOOBIG;
   static bool attr_set = false;
@@ -1166,7 +1218,7 @@ extern "C" int mcaq_morph_phi(const float* sum_plane, int B, int C, int H, int W
   FusedArgs A = {};
   const long long smem = plan(A.g, B, C, H, W, grid_size);
   if (smem < 0) return (int)smem;
-  const int threads = pick_threads(A.g);
+  const int threads = A.g.threads;
   A.sum_plane = sum_plane;
   A.phi = phi;
   A.gray_dbg = gray_dbg; A.edge_dbg = edge_bits_dbg; A.bin_dbg = bin_bits_dbg;
@@ -1201,7 +1253,7 @@ extern "C" int mcaq_morph_fused_xchg(const float* sum_plane, const float* abs_pl
   FusedArgs A = {};
   const long long smem = plan(A.g, B, C, H, W, grid_size);
   if (smem < 0) return (int)smem;
-  const int threads = pick_threads(A.g);
+  const int threads = A.g.threads;
   A.sum_plane = sum_plane; A.abs_plane = abs_plane;
   A.keys = keys; A.packed = packed_ranges;
   if (xchg_world > 1) {
@@ -1213,6 +1265,7 @@ extern "C" int mcaq_morph_fused_xchg(const float* sum_plane, const float* abs_pl
     }
     A.px.rank = xchg_rank;
     A.px.world = xchg_world;
+    A.px.timeout_ns = xchg_timeout_ns();
   }
   A.cmlp = cmlp; A.mapper = mapper; A.softmask = softmask;
   // linear_mapper == 2: MLP mapper whose block is followed by its step table (mcaq_mapper_steps)

@@ -4,10 +4,15 @@
 
 namespace mcaq {
 
-__global__ void xchg_merge_kernel(const float* local, int world, int C, float* packed) {
+static long long g_timeout_ns = 2000000000LL;
+long long xchg_timeout_ns() { return g_timeout_ns; }
+
+// on a timeout `packed` is left untouched (callers pre-fill it with this rank's own ranges when they
+// want a defined fallback) and the error word carries the step
+__global__ void xchg_merge_kernel(const float* local, int world, int C, float* packed, long long budget_ns) {
   const int e = xchg_step(local);
-  xchg_wait(local, world, e, threadIdx.x);
-  __syncthreads();
+  const bool ok = xchg_wait(local, world, e, threadIdx.x, budget_ns);
+  if (!__syncthreads_and(ok)) return;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) packed[i] = xchg_min(local, world, 2 * C, e, i);
 }
 
@@ -65,6 +70,19 @@ extern "C" int mcaq_xchg_open(const void* handle64, void** out) {
   return (int)cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
 }
 
+extern "C" void mcaq_xchg_set_timeout_ms(int ms) { g_timeout_ns = ms > 0 ? (long long)ms * 1000000LL : 2000000000LL; }
+
+// Synchronising read of the buffer's error word: *step = 0 when every wait so far was satisfied, else the
+// first exchange step whose wait timed out (that launch kept this rank's own ranges).  Clears the word.
+extern "C" int mcaq_xchg_error(void* local, int* step) {
+  if (!local || !step) return MCAQ_EINVAL;
+  int* w = reinterpret_cast<int*>(local) + XCHG_ERROR;
+  cudaError_t e = cudaMemcpy(step, w, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return (int)e;
+  if (*step != 0) e = cudaMemset(w, 0, sizeof(int));
+  return (int)e;
+}
+
 extern "C" int mcaq_xchg_close(void* p) { return p ? (int)cudaIpcCloseMemHandle(p) : 0; }
 
 static int fill_peers(XchgPeers& px, void* const* peers, int rank, int world) {
@@ -74,6 +92,7 @@ static int fill_peers(XchgPeers& px, void* const* peers, int rank, int world) {
     if (!px.base[i]) return MCAQ_EINVAL;
   px.rank = rank;
   px.world = world;
+  px.timeout_ns = g_timeout_ns;
   return 0;
 }
 
@@ -89,7 +108,8 @@ extern "C" int mcaq_xchg_publish(void* const* peers, int rank, int world, const 
 
 extern "C" int mcaq_xchg_merge(const void* local, int world, int C, float* packed, void* stream) {
   if (!local || !packed || C <= 0 || world <= 0 || world > XCHG_MAX_RANKS) return MCAQ_EINVAL;
-  xchg_merge_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(local), world, C, packed);
+  xchg_merge_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(local), world, C, packed,
+                                                         g_timeout_ns);
   MCAQ_LAUNCH_CHECK();
   return 0;
 }

@@ -16,7 +16,15 @@
 // peer (its next merge waits for the peer's next publish), so a slot is never overwritten while it
 // can still be read.  No host involvement, no extra launch, capturable in a CUDA graph.
 //
-// Buffer layout (4-byte words):  [0] step counter of the owning rank   [16 + 8*par + q] flag of
+// A wait is BOUNDED: a peer that died, or ranks that issued different numbers of launches (uneven last
+// batch, rank-0-only validation), would otherwise leave the waiting CTA spinning until the process is
+// killed.  After `timeout_ns` (default 2 s, mcaq_xchg_set_timeout_ms) the waiter records the step in the
+// buffer's error word, the launch keeps THIS rank's own ranges (no merge) and finishes; the host reads the
+// error word with mcaq_xchg_error (peer.RangeExchange.check raises).  Every rank must run the same
+// sequence of exchange steps.
+//
+// Buffer layout (4-byte words):  [0] step counter of the owning rank   [1] error word (0, or the first
+// step whose wait timed out)   [16 + 8*par + q] flag of
 // rank q   [32 + ((par*R + q) * 2C) ...] slot of rank q, par = step & 1.
 #pragma once
 #include "common.cuh"
@@ -26,11 +34,21 @@ namespace mcaq {
 constexpr int XCHG_MAX_RANKS = 8;
 constexpr int XCHG_FLAGS = 16;
 constexpr int XCHG_SLOTS = 32;
+constexpr int XCHG_ERROR = 1;
 
 struct XchgPeers {
   float* base[XCHG_MAX_RANKS];   // exchange buffer of every rank (own entry = local memory)
   int rank, world;
+  long long timeout_ns;          // budget of one wait (<= 0: library default)
 };
+
+long long xchg_timeout_ns();     // host: current budget (peer_exchange.cu)
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   int v;
@@ -46,12 +64,21 @@ __device__ __forceinline__ int xchg_step(const float* local) {
   return *reinterpret_cast<const volatile int*>(local);
 }
 
-// thread q < world spins until rank q has published step e in the local buffer
-__device__ __forceinline__ void xchg_wait(const float* local, int world, int e, int q) {
+// thread q < world spins until rank q has published step e in the local buffer, for at most budget_ns;
+// returns false (and records e in the error word) on a timeout.  Callers combine the per-thread results
+// with __syncthreads_and and skip the merge when any wait failed.
+__device__ __forceinline__ bool xchg_wait(const float* local, int world, int e, int q, long long budget_ns) {
+  bool ok = true;
   if (q < world) {
     const int* f = reinterpret_cast<const int*>(local) + XCHG_FLAGS + 8 * (e & 1) + q;
-    while (ld_acquire_sys(f) != e) __nanosleep(64);
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) != e) {
+      __nanosleep(64);
+      if ((long long)(global_ns() - t0) > budget_ns) { ok = false; break; }
+    }
+    if (!ok) atomicCAS(reinterpret_cast<int*>(const_cast<float*>(local)) + XCHG_ERROR, 0, e);
   }
+  return ok;
 }
 
 // min over ranks of element idx (< 2C) of the step-e slots of the local buffer

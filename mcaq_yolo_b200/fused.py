@@ -66,6 +66,15 @@ class ScaleWorkspace:
         ops._call("mcaq_ranges_reset", self.keys.data_ptr(), C, ops._stream())
 
 
+def mapper_block(mapper, temperature) -> torch.Tensor:
+    """Parameter block of the MLP mapper for K2: with its step table when the network is monotone in c
+    (constants.mapping_is_monotone), the plain block -- K2 then evaluates the network per tile -- when it
+    is not (enforce_monotonicity=False, or negative weights before enforce_weight_constraints())."""
+    if K.mapping_is_monotone(mapper):
+        return K.pack_mapping_steps(mapper.mapping_network, temperature, mapper.min_bits, mapper.max_bits)
+    return K.pack_mapping_network(mapper.mapping_network)
+
+
 def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, temperature, ws: ScaleWorkspace | None,
                         layer: int = -1, xchg=None) -> dict:
     """Eval-mode hook body for one scale in three launches.  Returns the aux record.
@@ -86,8 +95,7 @@ def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, tempera
     sm = quantizer.soft_mask if quantizer.smooth_transitions else None
     r = ops.morph_fused(s, a if sm is not None else None, C, analyzer.grid_size,
                         K.pack_complexity_mlp(analyzer.complexity_mlp),
-                        None if linear else K.pack_mapping_steps(mapper.mapping_network, temperature,
-                                                                 mapper.min_bits, mapper.max_bits),
+                        None if linear else mapper_block(mapper, temperature),
                         None if sm is None else K.pack_soft_mask(sm),
                         temperature, False, ws.keys if need_ranges else None,
                         mapper.min_bits, mapper.max_bits, getattr(mapper, "eps_spread", 1e-3),
@@ -274,8 +282,7 @@ class ShardedHotPath:
             sm = q.soft_mask if q.smooth_transitions else None
             return ops.morph_fused(s, a if sm is not None else None, x.shape[1], self.analyzer.grid_size,
                                    K.pack_complexity_mlp(self.analyzer.complexity_mlp),
-                                   None if linear else K.pack_mapping_steps(self.mapper.mapping_network, self.temperature,
-                                                                            self.mapper.min_bits, self.mapper.max_bits),
+                                   None if linear else mapper_block(self.mapper, self.temperature),
                                    None if sm is None else K.pack_soft_mask(sm), self.temperature, False, None,
                                    self.mapper.min_bits, self.mapper.max_bits,
                                    getattr(self.mapper, "eps_spread", 1e-3))

@@ -343,12 +343,14 @@ class _FractionalQuantKD(torch.autograd.Function):
 
 class SpatialAdaptiveQuantization(nn.Module):
     """Eq.19  X_q(p) = m(p) * Q_{b_T(p)}(X(p))  (quantization.py:242-754), `minmax` calibration,
-    per-channel ranges.  `process_group` (optional) all-reduces the per-channel ranges so that a
-    batch sharded over ranks quantises exactly like the unsharded reference batch."""
+    per-channel ranges.  `sync_ranges=True` (opt-in; the reference has no collective, so the default
+    keeps a forward hook free of one) all-reduces the per-channel ranges over `process_group` so that a
+    batch sharded over ranks quantises exactly like the unsharded reference batch; every rank must then
+    run the same number of forwards."""
 
     def __init__(self, calibration_mode: str = "minmax", smooth_transitions: bool = True,
                  per_channel: bool = True, learned_rounding: bool = False, momentum: float = 0.99,
-                 process_group=None, sync_ranges: bool = True):
+                 process_group=None, sync_ranges: bool = False):
         super().__init__()
         if calibration_mode != "minmax" or not per_channel or learned_rounding:
             raise NotImplementedError(
@@ -419,7 +421,10 @@ class SpatialAdaptiveQuantization(nn.Module):
         self.num_batches_tracked += 1
 
     def _qtable(self, x: torch.Tensor, training: bool) -> torch.Tensor:
-        use_running = self.running_min is not None and (training or self._is_frozen())
+        # the reference decides on the MODULE flag, not on the call argument (quantization.py:415-417):
+        # in MCAQYOLO.calibrate() the model is in eval mode and the hook passes training=True, so the EMA
+        # is updated but the calibration pass itself quantises with the current batch's min / max
+        use_running = self.running_min is not None and (self.training or self._is_frozen())
         if use_running:
             return ops.build_qtable(None, self.running_min, self.running_max)
         return ops.build_qtable(self._batch_ranges(x))

@@ -25,6 +25,7 @@ class RangeExchange:
         self.peers = (ctypes.c_void_p * MAX_RANKS)(*([int(p) for p in peer_ptrs] + [None] * (MAX_RANKS - world)))
         self._owner = owner            # keeps shared state (virtual ranks) alive
         self._opened = []
+        self._owns_local = owner is None
 
     # ------------------------------------------------------------------ construction
     @staticmethod
@@ -43,9 +44,26 @@ class RangeExchange:
         import torch.distributed as dist
         lib = _lib.load()
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        local = cls._alloc(C, world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def agree(err):
+            """All ranks learn whether any of them failed (also a barrier): construction then fails
+            on every rank alike, so callers can fall back to the all-reduce path consistently."""
+            ok = torch.tensor([0 if err else 1], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            return int(ok.item()) == 1
+
+        local, err = None, None
         handle = ctypes.create_string_buffer(64)
-        _lib.check(lib.mcaq_xchg_export(local, handle), "mcaq_xchg_export")
+        try:
+            local = cls._alloc(C, world)
+            _lib.check(lib.mcaq_xchg_export(local, handle), "mcaq_xchg_export")
+        except (RuntimeError, ValueError) as e:      # allocation / IPC export failed on this rank
+            err = e
+        if not agree(err):                           # before all_gather_object: nobody is left waiting in it
+            if local is not None:
+                lib.mcaq_xchg_free(local)
+            raise RuntimeError(f"peer range exchange unavailable on this node ({err or 'failed on another rank'})")
         handles = [None] * world
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
         ptrs, opened, err = [], [], None
@@ -60,12 +78,8 @@ class RangeExchange:
                 opened.append(int(out.value))
         except RuntimeError as e:          # no peer access between two GPUs, IPC disabled, ...
             err = e
-        # agree on the outcome (also the barrier: nobody publishes before every rank has mapped every
-        # buffer); a failure on any rank fails the construction on all of them, so callers can fall back
-        # to the all-reduce path consistently
-        ok = torch.tensor([0 if err else 1], device=torch.device("cuda", torch.cuda.current_device()))
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 0:
+        # nobody publishes before every rank has mapped every buffer
+        if not agree(err):
             for p in opened:
                 lib.mcaq_xchg_close(p)
             lib.mcaq_xchg_free(local)
@@ -93,8 +107,29 @@ class RangeExchange:
         ops._call("mcaq_xchg_merge", self.local, self.world, self.C, out.data_ptr(), ops._stream())
         return out
 
+    def check(self):
+        """Synchronise and raise if a wait of this exchange timed out (a peer died, or the ranks did not
+        run the same number of exchange steps); the affected launch used this rank's own ranges."""
+        step = ctypes.c_int(0)
+        _lib.check(_lib.load().mcaq_xchg_error(self.local, ctypes.byref(step)), "mcaq_xchg_error")
+        if step.value:
+            raise RuntimeError(f"peer range exchange: wait for step {step.value} timed out on rank {self.rank} "
+                               "(peer not running the same step sequence?); that launch used local ranges")
+
     def close(self):
+        """Unmap the peers' buffers and free the local one (peers must have closed their mappings or be
+        gone: call after a barrier)."""
         lib = _lib.load()
         for p in self._opened:
             lib.mcaq_xchg_close(p)
         self._opened = []
+        if self._owns_local and self.local:
+            lib.mcaq_xchg_free(self.local)
+            self.local = 0
+        # virtual ranks (tests) share their buffers through `_owner`: those few KB are not freed
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
