@@ -35,6 +35,7 @@ extern "C" {
 /* element type of feature maps */
 #define MCAQ_F32  0
 #define MCAQ_BF16 1
+#define MCAQ_F16  2   /* IEEE half: what the hooked backbone outputs are under torch.autocast (train.py:192, 582, 748) */
 
 /* error codes (negative) */
 #define MCAQ_EINVAL   (-1)   /* bad size / null pointer */
@@ -143,13 +144,25 @@ MCAQ_API int mcaq_tile_quantize_train_bwd_kd(const void* grad_y, const void* x, 
                                  const float* mask, const float* teacher, const float* kd_coef,
                                  float* dbit, float* dmask, void* stream);
 
-/* The reference's launcher, same argument list (mcaq_kernel.cu:102-111, MCAQPlugin.cpp:15-24).
- * Semantics follow the reference's PyTorch path (round-half-even, IEEE division). */
+/* Level 0: the reference's launcher, same symbol and argument list (ops/src/mcaq_kernel.cu:102-111,
+ * engine/MCAQPlugin.cpp:15-24).  It returns void there; here the outcome of a thread's last call is
+ * kept in mcaq_level0_status() (0 / cudaError_t / negative MCAQ_E*), and mcaq_spatial_quantization is the
+ * same call returning that code.  When the tile grid divides the map (tile_h * n_tiles_h == H, same for W)
+ * and the geometry is 16-byte friendly -- every YOLO feature map -- this IS the vector kernel of the fused
+ * path (K3, ranges given directly); other geometries take a scalar kernel with the entry point's own tile
+ * rule min(h / tile_h, n_tiles_h - 1).  Rounding follows the reference's PyTorch path (half-to-even, IEEE
+ * division), not its kernel's roundf. */
 MCAQ_API void launch_spatial_quantization(const float* input, const float* bit_map,
                                  const float* min_vals, const float* max_vals,
                                  const float* mask, float* output,
                                  int N, int C, int H, int W, int tile_h, int tile_w,
                                  int n_tiles_h, int n_tiles_w, void* stream);
+MCAQ_API int mcaq_spatial_quantization(const float* input, const float* bit_map,
+                                 const float* min_vals, const float* max_vals,
+                                 const float* mask, float* output,
+                                 int N, int C, int H, int W, int tile_h, int tile_w,
+                                 int n_tiles_h, int n_tiles_w, void* stream);
+MCAQ_API int mcaq_level0_status(void);
 
 /* ------------------------------------------------------------------------------------------
  * K2  per-image morphology on the on-chip gray plane (one CTA per image).

@@ -6,7 +6,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_ui
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libmcaq_b200.so")
 
-MCAQ_F32, MCAQ_BF16 = 0, 1
+MCAQ_F32, MCAQ_BF16, MCAQ_F16 = 0, 1, 2
 MCAQ_EGEOM = -5
 
 # name -> (restype, argtypes): one entry per symbol declared in include/mcaq_b200.h
@@ -52,6 +52,9 @@ PROTOTYPES = {
     "mcaq_debug_train_scalar": (None, [c_int]),
     "launch_spatial_quantization": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mcaq_spatial_quantization": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mcaq_level0_status": (c_int, []),
     "mcaq_morph_phi": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcaq_complexity": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -10,7 +10,7 @@ extern "C" const char* mcaq_error_string(int code) {
     case MCAQ_EINVAL: return "mcaq: invalid argument (null pointer or non-positive size)";
     case MCAQ_EALIGN: return "mcaq: pointer is not 16-byte aligned";
     case MCAQ_ETOOBIG: return "mcaq: feature plane exceeds the on-chip budget of the morphology kernel";
-    case MCAQ_EDTYPE: return "mcaq: unsupported dtype (expected MCAQ_F32 or MCAQ_BF16)";
+    case MCAQ_EDTYPE: return "mcaq: unsupported dtype (expected MCAQ_F32, MCAQ_BF16 or MCAQ_F16)";
     case MCAQ_EGEOM: return "mcaq: geometry or alignment outside the vector path (no scalar form of this entry point)";
     default: return "mcaq: unknown error";
   }

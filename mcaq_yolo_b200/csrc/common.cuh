@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "mcaq_b200.h"
@@ -93,6 +94,35 @@ template <> struct Elem<__nv_bfloat16> {
   __device__ __forceinline__ static float round1(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
   __device__ __forceinline__ static void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
+
+template <> struct Elem<__half> {
+  static constexpr int VEC = 8;
+  // fp16 -> fp32 is exact (one HADD2.F32 per pair)
+  __device__ __forceinline__ static void unpack(const uint4& v, float* f) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
+    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+  __device__ __forceinline__ static uint32_t pack2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);              // round-to-nearest-even
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __device__ __forceinline__ static uint4 pack(const float* f) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+  __device__ __forceinline__ static float load1(const __half* p) { return __half2float(*p); }
+  __device__ __forceinline__ static float round1(float v) { return __half2float(__float2half_rn(v)); }
+  __device__ __forceinline__ static void store1(__half* p, float v) { *p = __float2half_rn(v); }
+};
+
+// element type of a dtype code with 16-bit storage (MCAQ_BF16 / MCAQ_F16): dispatch helper
+#define MCAQ_DISPATCH_16(dtype, T16, ...)                              \
+  do {                                                                 \
+    if ((dtype) == MCAQ_BF16) { typedef __nv_bfloat16 T16; __VA_ARGS__; } \
+    else { typedef __half T16; __VA_ARGS__; }                          \
+  } while (0)
 
 // ---- F.interpolate(mode='nearest') source index: min(floor(dst * (float)in/out), in-1) -----
 __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {

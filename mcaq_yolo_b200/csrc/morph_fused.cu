@@ -55,6 +55,7 @@ struct MorphGeom {
   // shared-memory layout, offsets in 4-byte words
   int off_bl, off_mag, off_h, off_bits, off_tiles, off_w, words;
   int hs;             // row stride of the horizontally filtered plane (Wc + 1: odd)
+  unsigned m_ww, m_hseg;   // 2^32 / d + 1 for d = WW and the horizontal tasks per row group (fast_div)
   int max_own;        // most tiles a CTA owns
   int threads;        // CTA size (fixes the per-warp scratch of the tile networks)
 };
@@ -232,8 +233,13 @@ __device__ __forceinline__ void task_adapt_h(const Ctx& c, int r_begin, int r_en
 #pragma unroll 1
   for (int xb = x0; xb < x1; xb += 8) {
     float v[18];
+    if (xb >= 5 && xb + 12 < c.Wc) {                      // interior block (warp-uniform): immediate offsets
 #pragma unroll
-    for (int j = 0; j < 18; ++j) v[j] = row[clampi(xb + j - 5, 0, c.Wc - 1)];
+      for (int j = 0; j < 18; ++j) v[j] = row[xb + j - 5];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 18; ++j) v[j] = row[clampi(xb + j - 5, 0, c.Wc - 1)];
+    }
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
       float acc = 0.f;
@@ -283,6 +289,7 @@ __device__ __forceinline__ void task_adaptive(const Ctx& c, cg::cluster_group& c
 // ---- T1c: uniform-LBP histogram (morphology.py:623-652) and Sobel(G) statistics (654-670) of the
 //      tiles of tile row ty under word k -> phi2, phi3.
 __device__ __forceinline__ void task_lbp_var(const Ctx& c, int ty, int k, int lane, const float* lutp, float* phis,
+                                             const unsigned long long* __restrict__ lbp_inc,
                                              int* __restrict__ lbp_dbg) {
   const int x = 32 * k + lane;
   const bool valid = x < c.Wc;
@@ -300,21 +307,19 @@ __device__ __forceinline__ void task_lbp_var(const Ctx& c, int ty, int k, int la
   const bool top = r0 == 0, bot = r0 + tile == c.Hc;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   unsigned long long cnt = 0ull;                          // ten 6-bit counters (a column has <= 32 pixels)
-  for (int j = 0; j < tile; ++j) {
+  // one pixel of the column: LBP label through the 256-entry table of counter increments
+  // (1 << 6 * label), Sobel statistics, window shift.  rt / rb: replicate padding in y.
+  auto step = [&](bool rt, bool rb) {
     p += c.gs;
     const float bL = p[-1], bC = p[0], bR = p[1];
     const float bLr = x0 ? bC : bL, bRr = xN ? bC : bR;
-    // replicate padding in y: the row above row 0 is row 0, the row below the last row is the last row
-    const bool rt = top && j == 0, rb = bot && j == tile - 1;
     const float uL = rt ? mLr : aLr, uC = rt ? mC : aC, uR = rt ? mRr : aRr;
     const float dL = rb ? mLr : bLr, dC = rb ? mC : bC, dR = rb ? mRr : bRr;
     // neighbour order (-1,-1),(-1,0),(-1,1),(0,1),(1,1),(1,0),(1,-1),(0,-1)  (morphology.py:634)
     const uint32_t code = (uint32_t)(uL >= mC) | ((uint32_t)(uC >= mC) << 1) | ((uint32_t)(uR >= mC) << 2) |
                           ((uint32_t)(mRr >= mC) << 3) | ((uint32_t)(dR >= mC) << 4) | ((uint32_t)(dC >= mC) << 5) |
                           ((uint32_t)(dL >= mC) << 6) | ((uint32_t)(mLr >= mC) << 7);
-    const uint32_t rot = ((code << 1) | (code >> 7)) & 0xffu;
-    const int label = __popc(code ^ rot) <= 2 ? __popc(code) : 9;
-    cnt += 1ull << (6 * label);
+    cnt += lbp_inc[code];
     float gx, gy;
     sobel3(aL, aC, aR, mL, mR, bL, bC, bR, gx, gy);
     s0 = __fadd_rn(s0, gx);
@@ -323,6 +328,13 @@ __device__ __forceinline__ void task_lbp_var(const Ctx& c, int ty, int k, int la
     s3 = __fadd_rn(s3, __fmul_rn(gy, gy));
     aL = mL; aC = mC; aR = mR; aLr = mLr; aRr = mRr;
     mL = bL; mC = bC; mR = bR; mLr = bLr; mRr = bRr;
+  };
+  // tiles are 4, 8, 16 or 32 rows: chunks of four unrolled rows, border handling only in the first / last
+  for (int j = 0; j < tile; j += 4) {
+    step(top && j == 0, false);
+    step(false, false);
+    step(false, false);
+    step(false, bot && j + 4 == tile);
   }
   // column sums left-to-right over the tile's lanes (leader = first lane of the tile)
   const float q0 = s0, q1 = s1, q2 = s2, q3 = s3;
@@ -586,6 +598,7 @@ morph_fused_kernel(const FusedArgs A) {
   float* mmx = red + 64;                                       // [16] per-rank min / max
   float* lutn = mmx + 16;                                      // [260] log(N + 1)
   float* lutp = lutn + 260;                                    // [tile^2 + 1 (+pad)] log2(k / tile^2 + 1e-10)
+  unsigned long long* lbp_inc = reinterpret_cast<unsigned long long*>(S + g.off_w);   // [256] LBP code -> 1 << 6 * label
   // parameter blocks: the complexity-MLP block (11.5 KB) is staged into the dead plane area right before
   // N1 (L1 starts cold in every launch), the soft-mask block over the dead LUT; the mapper block is only
   // read (through L1) when its step table is absent or invalid
@@ -614,6 +627,11 @@ morph_fused_kernel(const FusedArgs A) {
     const float* src = tile == 4 ? kc::LOG2P_4 : (tile == 8 ? kc::LOG2P_8 : (tile == 16 ? kc::LOG2P_16 : kc::LOG2P_32));
     for (int i = tid; i < 257; i += NT) lutn[i] = __ldg(kc::LOGN1 + i);
     for (int i = tid; i <= tile * tile; i += NT) lutp[i] = __ldg(src + i);
+    for (int code = tid; code < 256; code += NT) {              // uniform LBP label (morphology.py:640-650)
+      const uint32_t rot = (((uint32_t)code << 1) | ((uint32_t)code >> 7)) & 0xffu;
+      const int label = __popc((uint32_t)code ^ rot) <= 2 ? __popc((uint32_t)code) : 9;
+      lbp_inc[code] = 1ull << (6 * label);
+    }
   }
   // K1 -> K3 hand-off of the per-channel ranges: decode the atomics' integer keys to floats and
   // re-arm the keys for the next sweep (stream order: K1 done, K3 not started)
@@ -798,16 +816,16 @@ morph_fused_kernel(const FusedArgs A) {
     // phase a: horizontal pass | LBP + gradient variance | tile activity
     for (int task = warp; task < nhor + nlbp + nact; task += nwarps) {
       if (task < nhor) {
-        const int rg = task / nhseg, sg = task - rg * nhseg;
+        const int rg = fast_div(task, g.m_hseg), sg = task - rg * nhseg;
         task_adapt_h(c, h_lo + 32 * rg, h_hi, sg * HSEG, min((sg + 1) * HSEG, Wc), lane);
       } else if (task < nhor + nlbp) {
         const int q = task - nhor;
-        const int tyl = q / WW, k = q - tyl * WW;
-        task_lbp_var(c, tr0 + tyl, k, lane, lutp, phis,
+        const int tyl = fast_div(q, g.m_ww), k = q - tyl * WW;
+        task_lbp_var(c, tr0 + tyl, k, lane, lutp, phis, lbp_inc,
                      A.lbp_dbg ? A.lbp_dbg + (long long)b * g.ntiles * 10 : nullptr);
       } else {
         const int q = task - nhor - nlbp;
-        const int tyl = q / WW, k = q - tyl * WW;
+        const int tyl = fast_div(q, g.m_ww), k = q - tyl * WW;
         task_act(c, ap, g.W, fC, rC, cpow2, tr0 + tyl, k, lane, act_s);
       }
     }
@@ -817,11 +835,11 @@ morph_fused_kernel(const FusedArgs A) {
     // phase b: vertical pass + sign -> BIN | 5x5 blur -> BL + histogram
     for (int task = warp; task < nadapt + nblur; task += nwarps) {
       if (task < nadapt) {
-        const int rg = task / WW, k = task - rg * WW;
+        const int rg = fast_div(task, g.m_ww), k = task - rg * WW;
         task_adaptive<RTa>(c, cl, r_lo + rg * RTa, r_hi, k, lane);
       } else {
         const int q = task - nadapt;
-        const int rg = q / WW, k = q - rg * WW;
+        const int rg = fast_div(q, g.m_ww), k = q - rg * WW;
         task_blur<8>(c, b_lo + rg * 8, b_hi, k, lane, hloc);
       }
     }
@@ -839,7 +857,7 @@ morph_fused_kernel(const FusedArgs A) {
     const int m_lo = max(r_lo - 1, 0), m_hi = min(r_hi + 1, Hc);
     const int nmag = ((m_hi - m_lo + 7) >> 3) * WW;
     for (int task = warp; task < nmag; task += nwarps) {
-      const int rg = task / WW, k = task - rg * WW;
+      const int rg = fast_div(task, g.m_ww), k = task - rg * WW;
       task_mag<8>(c, m_lo + rg * 8, m_hi, k, lane);
     }
   }
@@ -855,7 +873,7 @@ morph_fused_kernel(const FusedArgs A) {
     const int RTn = tile >= 8 ? 8 : 4;
     const int nnms = ((r_hi - r_lo) / RTn) * WW;
     for (int task = warp; task < nnms; task += nwarps) {
-      const int rg = task / WW, k = task - rg * WW;
+      const int rg = fast_div(task, g.m_ww), k = task - rg * WW;
       if (RTn == 8) task_nms<8>(c, cl, r_lo + rg * 8, k, lane, thr255, thr_lo);
       else task_nms<4>(c, cl, r_lo + rg * 4, k, lane, thr255, thr_lo);
     }
@@ -878,7 +896,7 @@ morph_fused_kernel(const FusedArgs A) {
   const uint32_t segmask = tile == 32 ? 0xffffffffu : ((1u << tile) - 1u);
   for (int i = r_lo * WW + tid; i < r_hi * WW; i += NT) {
     {
-      const int r = i / WW, k = i - r * WW;
+      const int r = fast_div(i, g.m_ww), k = i - r * WW;
       const int nbits = min(32, Wc - 32 * k);
       const uint32_t vmask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
       const uint32_t e = EDGE[i];
@@ -1151,8 +1169,8 @@ static long long layout(MorphGeom& g) {
   g.off_tiles = (int)tiles0;
   const long long tw = (long long)g.ntiles * (2 + 8 + 5 + 9) + 512 + 64 + 16 + 260 + g.tile * g.tile + 4;
   const long long w0 = (tiles0 + tw + 3) & ~3LL;
-  g.off_w = (int)w0;
-  g.words = (int)w0;
+  g.off_w = (int)w0;                                   // 256 x 8-byte LBP increment table
+  g.words = (int)(w0 + 512);
   return (long long)g.words * 4;
 }
 
@@ -1169,6 +1187,8 @@ static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size) {
   g.S = 0;
   for (int s = 2; s <= g.tile; s <<= 1) g.S++;
   g.aligned = (H == g.Hc && W == g.Wc) ? 1 : 0;
+  g.m_ww = 0xffffffffu / (unsigned)g.WW + 1u;
+  g.m_hseg = 0xffffffffu / (unsigned)((g.Wc + 39) / 40) + 1u;
   g.gs = g.Wc + 5;          // two zero columns each side; odd, so lane = row accesses are conflict-free
   g.hs = g.Wc + 1;
   g.bs = g.Wc + 2;

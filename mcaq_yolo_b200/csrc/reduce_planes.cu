@@ -62,6 +62,20 @@ struct MinMaxAcc<__nv_bfloat16, 8> {
   __device__ __forceinline__ float vmax() const { return fmaxf(__low2float(hi), __high2float(hi)); }
 };
 
+template <>
+struct MinMaxAcc<__half, 8> {
+  __half2 lo, hi;
+  __device__ __forceinline__ static __half2 as2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
+  __device__ __forceinline__ void init() { lo = as2(0x7c007c00u); hi = as2(0xfc00fc00u); }
+  __device__ __forceinline__ void update(const uint4& r) {
+    const __half2 a = as2(r.x), b = as2(r.y), c = as2(r.z), d = as2(r.w);
+    lo = __hmin2(lo, __hmin2(__hmin2(a, b), __hmin2(c, d)));
+    hi = __hmax2(hi, __hmax2(__hmax2(a, b), __hmax2(c, d)));
+  }
+  __device__ __forceinline__ float vmin() const { return fminf(__low2float(lo), __high2float(lo)); }
+  __device__ __forceinline__ float vmax() const { return fmaxf(__low2float(hi), __high2float(hi)); }
+};
+
 // RMODE: 0 no ranges, 1 per-vector warp reduction (any C), 2 per-thread running min / max in
 // registers when the CTA's G warps cover all channel chunks in one pass (a warp then always owns
 // the same 16 channels), reduced across the warp once per CTA
@@ -401,6 +415,10 @@ extern "C" int mcaq_reduce_planes(const void* x, int dtype, int B, int C, int H,
     const __nv_bfloat16* p = (const __nv_bfloat16*)x;
     if (aligned && HW % 8 == 0) return dispatch_groups<__nv_bfloat16, 8>(p, B, C, HW, sum_plane, abs_plane, keys, st);
     return dispatch_groups<__nv_bfloat16, 1>(p, B, C, HW, sum_plane, abs_plane, keys, st);
+  } else if (dtype == MCAQ_F16) {
+    const __half* p = (const __half*)x;
+    if (aligned && HW % 8 == 0) return dispatch_groups<__half, 8>(p, B, C, HW, sum_plane, abs_plane, keys, st);
+    return dispatch_groups<__half, 1>(p, B, C, HW, sum_plane, abs_plane, keys, st);
   }
   return MCAQ_EDTYPE;
 }

@@ -21,7 +21,31 @@ namespace mcaq {
 // fp64 transcendentals rounded once to fp32 (the oracle's contract).  Deliberately NOT inlined: each
 // expansion is ~1.5 KB of straight-line code used once per call site, and the per-image kernel is
 // instruction-fetch bound.
-static __device__ __noinline__ float exp_f64(float x) { return (float)exp((double)x); }
+// exp: k = rint(x log2 e), r = x - k ln2 (two-part ln2, exact products), exp(r) by the degree-13 Taylor
+// polynomial (|r| <= 0.347: truncation 4e-18), scaled by 2^k -- about 1 ulp in fp64 like the library exp at
+// a fifth of its instructions (the bilateral filter evaluates 25 per tile).
+static __device__ __noinline__ float exp_f64(float xf) {
+  const double x = (double)xf;
+  if (!(fabs(x) < 700.0)) return (float)exp(x);            // inf / nan / beyond the scaling range: library
+  const int k = __double2int_rn(x * 1.4426950408889634074);
+  const double kd = (double)k;
+  const double r = fma(-kd, 1.90821492927058770002e-10, fma(-kd, 6.93147180369123816490e-01, x));
+  double p = 1.6059043836821613e-10;                        // 1 / 13!
+  p = fma(p, r, 2.08767569878681e-09);                      // 1 / 12!
+  p = fma(p, r, 2.505210838544172e-08);                     // 1 / 11!
+  p = fma(p, r, 2.755731922398589e-07);                     // 1 / 10!
+  p = fma(p, r, 2.7557319223985893e-06);                    // 1 / 9!
+  p = fma(p, r, 2.48015873015873e-05);                      // 1 / 8!
+  p = fma(p, r, 1.984126984126984e-04);                     // 1 / 7!
+  p = fma(p, r, 1.388888888888889e-03);                     // 1 / 6!
+  p = fma(p, r, 8.333333333333333e-03);                     // 1 / 5!
+  p = fma(p, r, 4.1666666666666664e-02);                    // 1 / 4!
+  p = fma(p, r, 1.6666666666666666e-01);                    // 1 / 3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return (float)(p * __hiloint2double((k + 1023) << 20, 0));
+}
 static __device__ __noinline__ float log1p_f64(float x) { return (float)log1p((double)x); }
 
 __device__ __forceinline__ float sigmoid_exact(float z) {
@@ -311,7 +335,10 @@ __device__ __forceinline__ void bilateral_range(const float* craw, int ht, int w
     const int ky = tap / 5, kx = tap - ky * 5;
     const int yy = min(max(y + ky - 2, 0), ht - 1), xx = min(max(x + kx - 2, 0), wt - 1);
     const float d = __fsub_rn(craw[yy * wt + xx], craw[t]);
-    const float arg = __fdiv_rn(-__fmul_rn(d, d), kc::BILAT_DEN);
+    // -(d^2) / (2 sigma_r^2): Markstein's correction with the constant's reciprocal equals div.rn in the
+    // normal range (tests/test_gpu_division.py); zero / tiny numerators take the division
+    const float nd = -__fmul_rn(d, d);
+    const float arg = (nd <= -1e-30f) ? div_markstein(nd, kc::BILAT_DEN, 50.0f) : __fdiv_rn(nd, kc::BILAT_DEN);
     wgt[o] = __fmul_rn(kc::BILAT[tap], exp_f64(arg));
   }
   __syncthreads();

@@ -386,14 +386,16 @@ tile_quantize_train_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------------
-// reference-compatible launcher: builds {scale, zp} per (bit, channel) on the fly from
-// min/max (no workspace in that signature), one CTA-level table in shared memory.
+// reference-compatible launcher, odd geometries: builds {scale, zp} per (bit, channel) on the fly from
+// min/max (no workspace in that signature), one CTA-level table in shared memory; the tile of a pixel is
+// min(h / tile_h, n_tiles_h - 1) x min(w / tile_w, n_tiles_w - 1), the rule of the entry point it replaces
+// (ops/src/mcaq_kernel.cu:48-51).  Geometries the vector kernel covers never come here.
 // ---------------------------------------------------------------------------------------------
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(256)
 spatial_quant_compat_kernel(const float* __restrict__ x, const float* __restrict__ bit_map,
                             const float* __restrict__ mn, const float* __restrict__ mx,
-                            const float* __restrict__ mask, float* __restrict__ y, QGeom g) {
+                            const float* __restrict__ mask, float* __restrict__ y, QGeom g, int tile_h, int tile_w) {
   extern __shared__ float2 tab[];                      // [7][cchunk]
   const int cchunk = QCHUNK;
   const int c_begin = blockIdx.y * cchunk;
@@ -414,16 +416,20 @@ spatial_quant_compat_kernel(const float* __restrict__ x, const float* __restrict
   if (gp >= (long long)g.B * g.HW) return;
   const int b = (int)(gp / g.HW);
   const int pix = (int)(gp - (long long)b * g.HW);
-  PixCtx<1> ctx;
-  make_ctx<1, HAS_MASK>(g, b, pix, bit_map, mask, ctx);
+  const int h = pix / g.W, w = pix - h * g.W;
+  const int ty = min(h / tile_h, g.Ht - 1), tx = min(w / tile_w, g.Wt - 1);
+  float bf = rintf(__ldg(bit_map + ((long long)b * g.Ht + ty) * g.Wt + tx));
+  bf = fminf(fmaxf(bf, 2.f), 8.f);
+  const int bidx = (int)bf - 2;
+  const float m = HAS_MASK ? __ldg(mask + (long long)b * g.HW + pix) : 1.f;
   float qmin, qmax;
-  bit_limits(ctx.bidx[0], qmin, qmax);
+  bit_limits(bidx, qmin, qmax);
   const long long base = ((long long)b * g.C) * g.HW + pix;
   for (int c = c_begin; c < c_end; ++c) {
-    const float2 p = tab[ctx.bidx[0] * cchunk + (c - c_begin)];
+    const float2 p = tab[bidx * cchunk + (c - c_begin)];
     const float q = quant_code(__ldg(x + base + (long long)c * g.HW), p.x, p.y, qmin, qmax);
     float d = dequant(q, p.x, p.y);
-    if (HAS_MASK) d = __fmul_rn(d, ctx.m[0]);
+    if (HAS_MASK) d = __fmul_rn(d, m);
     y[base + (long long)c * g.HW] = d;
   }
 }
@@ -512,11 +518,11 @@ extern "C" int mcaq_tile_quantize(const void* x, void* y, int dtype, int B, int 
     if (seg_ok(x, y, mask, codes, H * W, W, Wt, 4))
       return launch_quant<float, 4>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
     return launch_quant<float, 1>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
-  } else if (dtype == MCAQ_BF16) {
-    typedef __nv_bfloat16 bf;
-    if (seg_ok(x, y, mask, codes, H * W, W, Wt, 8))
-      return launch_quant<bf, 8>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
-    return launch_quant<bf, 1>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
+  } else if (dtype == MCAQ_BF16 || dtype == MCAQ_F16) {
+    const bool v8 = seg_ok(x, y, mask, codes, H * W, W, Wt, 8);
+    MCAQ_DISPATCH_16(dtype, h16,
+      if (v8) return launch_quant<h16, 8>((const h16*)x, (h16*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st);
+      return launch_quant<h16, 1>((const h16*)x, (h16*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, codes, st));
   }
   return MCAQ_EDTYPE;
 }
@@ -531,15 +537,15 @@ extern "C" int mcaq_tile_quantize_ranges(const void* x, void* y, int dtype, int 
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   QRanges rg{packed, running_min, running_max};
+  if (dtype != MCAQ_F32 && dtype != MCAQ_BF16 && dtype != MCAQ_F16) return MCAQ_EDTYPE;
   const bool vec = dtype == MCAQ_F32 ? seg_ok(x, y, mask, nullptr, H * W, W, Wt, 4)
                                      : seg_ok(x, y, mask, nullptr, H * W, W, Wt, 8);
   if (vec) {
     if (dtype == MCAQ_F32)
       return launch_quant<float, 4>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, nullptr, mask, nullptr, st, rg);
-    if (dtype == MCAQ_BF16) {
-      typedef __nv_bfloat16 bf;
-      return launch_quant<bf, 8>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, nullptr, mask, nullptr, st, rg);
-    }
+    if (dtype == MCAQ_BF16 || dtype == MCAQ_F16)
+      MCAQ_DISPATCH_16(dtype, h16,
+        return launch_quant<h16, 8>((const h16*)x, (h16*)y, B, C, H, W, bit_map, Ht, Wt, nullptr, mask, nullptr, st, rg));
     return MCAQ_EDTYPE;
   }
   // odd geometry: materialise the table in the caller's workspace, then the scalar kernel
@@ -570,18 +576,18 @@ extern "C" int mcaq_tile_quantize_train_fwd(const void* x, void* y, int dtype, i
   int rc = check_common(x, y, B, C, H, W, bit_map, Ht, Wt, qtable);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if ((dtype == MCAQ_F32 || dtype == MCAQ_BF16) &&
+  if ((dtype == MCAQ_F32 || dtype == MCAQ_BF16 || dtype == MCAQ_F16) &&
       train_vec_ok(x, y, nullptr, mask, nullptr, nullptr, dtype, H, W, Wt))
     return train_fwd_vec(x, y, dtype, B, C, H, W, bit_map, Ht, Wt, qtable, mask, nullptr, nullptr, st);
   if (dtype == MCAQ_F32) {
     if (vec_ok(x, y, H * W, W, 4, nullptr))
       return launch_train_fwd<float, 4>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
     return launch_train_fwd<float, 1>((const float*)x, (float*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
-  } else if (dtype == MCAQ_BF16) {
-    typedef __nv_bfloat16 bf;
-    if (vec_ok(x, y, H * W, W, 8, nullptr))
-      return launch_train_fwd<bf, 8>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
-    return launch_train_fwd<bf, 1>((const bf*)x, (bf*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
+  } else if (dtype == MCAQ_BF16 || dtype == MCAQ_F16) {
+    const bool v8 = vec_ok(x, y, H * W, W, 8, nullptr);
+    MCAQ_DISPATCH_16(dtype, h16,
+      if (v8) return launch_train_fwd<h16, 8>((const h16*)x, (h16*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st);
+      return launch_train_fwd<h16, 1>((const h16*)x, (h16*)y, B, C, H, W, bit_map, Ht, Wt, qtable, mask, st));
   }
   return MCAQ_EDTYPE;
 }
@@ -594,31 +600,56 @@ extern "C" int mcaq_tile_quantize_train_bwd(const void* grad_y, const void* x, v
   if (rc) return rc;
   if (!grad_y || !dbit || (mask && !dmask)) return MCAQ_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  if ((dtype == MCAQ_F32 || dtype == MCAQ_BF16) &&
+  if ((dtype == MCAQ_F32 || dtype == MCAQ_BF16 || dtype == MCAQ_F16) &&
       train_vec_ok(grad_y, grad_x, x, mask, dmask, nullptr, dtype, H, W, Wt))
     return train_bwd_vec(grad_y, x, grad_x, dtype, B, C, H, W, bit_map, Ht, Wt, qtable, mask, nullptr, nullptr,
                          dbit, dmask, st);
   if (dtype == MCAQ_F32)
     return launch_train_bwd<float>((const float*)grad_y, (const float*)x, (float*)grad_x, B, C, H, W, bit_map,
                                    Ht, Wt, qtable, mask, dbit, dmask, st);
-  if (dtype == MCAQ_BF16) {
-    typedef __nv_bfloat16 bf;
-    return launch_train_bwd<bf>((const bf*)grad_y, (const bf*)x, (bf*)grad_x, B, C, H, W, bit_map, Ht, Wt,
-                                qtable, mask, dbit, dmask, st);
-  }
+  if (dtype == MCAQ_BF16 || dtype == MCAQ_F16)
+    MCAQ_DISPATCH_16(dtype, h16,
+      return launch_train_bwd<h16>((const h16*)grad_y, (const h16*)x, (h16*)grad_x, B, C, H, W, bit_map, Ht, Wt,
+                                   qtable, mask, dbit, dmask, st));
   return MCAQ_EDTYPE;
 }
 
+// Level 0 of the drop-in boundary: the reference's launcher (ops/src/mcaq_kernel.cu:102-111, shared with
+// engine/MCAQPlugin.cpp:15-24) with an error channel.  When the tile grid divides the map (tile_h * n_tiles_h
+// == H, likewise W: every YOLO feature map) and rows / tiles are 16-byte friendly it IS the vector kernel of
+// the fused path (per-channel ranges given directly, no table kernel); other geometries take the scalar
+// kernel with the entry point's own tile rule.  Rounding is half-to-even like the reference's PyTorch path.
+extern "C" int mcaq_spatial_quantization(const float* input, const float* bit_map, const float* min_vals,
+                                         const float* max_vals, const float* mask, float* output, int N, int C,
+                                         int H, int W, int tile_h, int tile_w, int n_tiles_h, int n_tiles_w,
+                                         void* stream) {
+  if (!input || !output || !bit_map || !min_vals || !max_vals) return MCAQ_EINVAL;
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || n_tiles_h <= 0 || n_tiles_w <= 0 || tile_h <= 0 || tile_w <= 0)
+    return MCAQ_EINVAL;
+  if ((long long)H * W > 0x7fffffffLL) return MCAQ_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool divides = (long long)tile_h * n_tiles_h == H && (long long)tile_w * n_tiles_w == W;
+  if (divides && seg_ok(input, output, mask, nullptr, H * W, W, n_tiles_w, 4))
+    return launch_quant<float, 4>(input, output, N, C, H, W, bit_map, n_tiles_h, n_tiles_w, nullptr, mask, nullptr, st,
+                                  QRanges{nullptr, min_vals, max_vals});
+  QGeom g = make_geom(N, C, H, W, n_tiles_h, n_tiles_w, 1);
+  dim3 grid((unsigned)(((long long)N * H * W + 255) / 256), (unsigned)((C + QCHUNK - 1) / QCHUNK));
+  const size_t smem = 7 * QCHUNK * sizeof(float2);
+  if (mask) spatial_quant_compat_kernel<true><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g, tile_h, tile_w);
+  else spatial_quant_compat_kernel<false><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g, tile_h, tile_w);
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+static thread_local int g_level0_status = 0;
+// status of this thread's last launch_spatial_quantization call (0 ok / cudaError_t / negative MCAQ_E*)
+extern "C" int mcaq_level0_status() { return g_level0_status; }
+
+// the reference's exact symbol and argument list: returns void there, so the outcome is kept per thread
 extern "C" void launch_spatial_quantization(const float* input, const float* bit_map, const float* min_vals,
                                             const float* max_vals, const float* mask, float* output, int N,
                                             int C, int H, int W, int tile_h, int tile_w, int n_tiles_h,
                                             int n_tiles_w, void* stream) {
-  (void)tile_h; (void)tile_w;   // the tile of a pixel follows F.interpolate's nearest rule on (H, n_tiles_h)
-  if (!input || !output || N <= 0 || C <= 0 || H <= 0 || W <= 0) return;
-  QGeom g = make_geom(N, C, H, W, n_tiles_h, n_tiles_w, 1);
-  dim3 grid((unsigned)(((long long)N * H * W + 255) / 256), (unsigned)((C + QCHUNK - 1) / QCHUNK));
-  const size_t smem = 7 * QCHUNK * sizeof(float2);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (mask) spatial_quant_compat_kernel<true><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g);
-  else spatial_quant_compat_kernel<false><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g);
+  g_level0_status = mcaq_spatial_quantization(input, bit_map, min_vals, max_vals, mask, output, N, C, H, W, tile_h,
+                                              tile_w, n_tiles_h, n_tiles_w, stream);
 }

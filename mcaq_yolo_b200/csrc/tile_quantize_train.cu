@@ -392,9 +392,9 @@ int train_fwd_vec(const void* x, void* y, int dtype, int B, int C, int H, int W,
     const QGeom g = make_geom(B, C, H, W, Ht, Wt, 4);
     return launch_fwd_vec<float, 4>((const float*)x, (float*)y, g, bit_map, qtable, mask, teacher, kd_sum, st);
   }
-  typedef __nv_bfloat16 bf;
   const QGeom g = make_geom(B, C, H, W, Ht, Wt, 8);
-  return launch_fwd_vec<bf, 8>((const bf*)x, (bf*)y, g, bit_map, qtable, mask, teacher, kd_sum, st);
+  MCAQ_DISPATCH_16(dtype, h16,
+    return launch_fwd_vec<h16, 8>((const h16*)x, (h16*)y, g, bit_map, qtable, mask, teacher, kd_sum, st));
 }
 
 int train_bwd_vec(const void* gy, const void* x, void* gx, int dtype, int B, int C, int H, int W,
@@ -405,10 +405,10 @@ int train_bwd_vec(const void* gy, const void* x, void* gx, int dtype, int B, int
     return launch_bwd_vec<float, 4>((const float*)gy, (const float*)x, (float*)gx, g, bit_map, qtable, mask,
                                     teacher, kd_coef, dbit, dmask, st);
   }
-  typedef __nv_bfloat16 bf;
   const QGeom g = make_geom(B, C, H, W, Ht, Wt, 8);
-  return launch_bwd_vec<bf, 8>((const bf*)gy, (const bf*)x, (bf*)gx, g, bit_map, qtable, mask, teacher, kd_coef,
-                               dbit, dmask, st);
+  MCAQ_DISPATCH_16(dtype, h16,
+    return launch_bwd_vec<h16, 8>((const h16*)gy, (const h16*)x, (h16*)gx, g, bit_map, qtable, mask, teacher, kd_coef,
+                                  dbit, dmask, st));
 }
 
 }  // namespace mcaq
@@ -422,7 +422,7 @@ static int kd_args_ok(const void* x, const void* y, int dtype, int B, int C, int
   if (!x || !y || !bit_map || !qtable || !teacher) return MCAQ_EINVAL;
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || Ht <= 0 || Wt <= 0) return MCAQ_EINVAL;
   if ((long long)H * W > 0x7fffffffLL) return MCAQ_EINVAL;
-  if (dtype != MCAQ_F32 && dtype != MCAQ_BF16) return MCAQ_EDTYPE;
+  if (dtype != MCAQ_F32 && dtype != MCAQ_BF16 && dtype != MCAQ_F16) return MCAQ_EDTYPE;
   return 0;
 }
 

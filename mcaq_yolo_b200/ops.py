@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import MCAQ_BF16, MCAQ_F32, check
+from ._lib import MCAQ_BF16, MCAQ_F16, MCAQ_F32, check
 
 
 def _stream() -> int:
@@ -22,7 +22,9 @@ def _dtype_code(t: torch.Tensor) -> int:
         return MCAQ_F32
     if t.dtype == torch.bfloat16:
         return MCAQ_BF16
-    raise TypeError(f"mcaq_b200 supports float32 / bfloat16 feature maps, got {t.dtype}")
+    if t.dtype == torch.float16:          # hooked backbone outputs under autocast (train.py:192, 582, 748)
+        return MCAQ_F16
+    raise TypeError(f"mcaq_b200 supports float32 / bfloat16 / float16 feature maps, got {t.dtype}")
 
 
 def _need_cuda(*ts):
@@ -65,6 +67,8 @@ def is_nhwc(x: torch.Tensor) -> bool:
     """True when x is a channels_last tensor the NHWC kernels cover (memory (B,H,W,C) dense, C a
     multiple of 16 with C / (16 / itemsize) a power of two <= 256, 16-byte aligned)."""
     if x.dim() != 4 or x.is_contiguous() or not x.is_contiguous(memory_format=torch.channels_last):
+        return False
+    if x.dtype == torch.float16:          # NHWC kernels: fp32 / bf16 (fp16 channels_last is copied to NCHW)
         return False
     C = x.shape[1]
     vec = 16 // x.element_size()
@@ -284,9 +288,14 @@ def spatial_quantize(input: torch.Tensor, bit_map: torch.Tensor, min_vals: torch
     mn, mx = _f32c(min_vals).reshape(-1), _f32c(max_vals).reshape(-1)
     mask = None if mask is None else _f32c(mask)
     out = torch.empty_like(input)
+    if bit_map.dim() != 3 or bit_map.shape[0] != N:
+        raise RuntimeError(f"bit_map must be (N, Ht, Wt) with N={N}, got {tuple(bit_map.shape)}")
+    # the reference's launcher symbol (void) + its per-thread status word: errors surface as RuntimeError
+    lib = _lib.load()
     _call("launch_spatial_quantization", input.data_ptr(), bit_map.data_ptr(), mn.data_ptr(), mx.data_ptr(),
                                             _ptr(mask), out.data_ptr(), N, C, H, W, int(tile_h), int(tile_w),
                                             int(bit_map.shape[1]), int(bit_map.shape[2]), _stream())
+    check(lib.mcaq_level0_status(), "launch_spatial_quantization")
     return out
 
 

@@ -35,22 +35,34 @@ print(f"total warp-instructions {tot_i:.0f}, samples {tot_s:.0f}")
 for key in sorted(inst, key=lambda k: -inst[k])[:top]:
     print(f"{inst[key]:10.0f} {100*inst[key]/tot_i:5.1f}%  smp {100*samp[key]/max(tot_s,1):5.1f}%  {key[0]}:{key[1]:<5d} {src[key].strip()[:110]}")
 
-# optional grouping of morph_fused.cu / tile_nets.cuh lines into stages
+# optional grouping of morph_fused.cu lines into stages: ranges start at marker comments / function heads
 if len(sys.argv) > 3 and sys.argv[3] == "stages":
-    R = [("blur", 144, 190), ("adaptive", 192, 264), ("lbp_var", 266, 350), ("act", 352, 373),
-         ("mag(T2)", 375, 407), ("sobel3+nms_bin", 99, 131), ("nms(T3)", 409, 444), ("otsu", 446, 497),
-         ("hysteresis", 499, 538), ("div helpers", 84, 97), ("prologue+L load", 543, 716), ("N normalise", 717, 733),
-         ("T1 dispatch", 734, 793), ("T2-T4 dispatch", 794, 831), ("T5 counts", 832, 903), ("phi assembly", 904, 964),
-         ("nets dispatch", 965, 1035)]
+    import os, re
+    srcp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mcaq_yolo_b200", "csrc", "morph_fused.cu")
+    marks = [("helpers", r"^__device__ __forceinline__ int clampi"), ("nms_bin+sobel3", r"^// literal atan2 binning"),
+             ("blur", r"^// ---- T1a"), ("adaptive", r"^// ---- T1b"), ("lbp_var", r"^// ---- T1c"), ("act", r"^// ---- T1d"),
+             ("mag(T2)", r"^// ---- T2"), ("nms(T3)", r"^// ---- T3"), ("otsu", r"^// Otsu threshold from"),
+             ("hysteresis", r"^// ---- T4"), ("kernel prologue", r"^morph_fused_kernel"), ("L minmax", r"^  // ---- L:"),
+             ("N normalise", r"^  // ---- N:"), ("T1 dispatch", r"^  // ---- T1:"), ("hist merge+T2 dispatch", r"^  for \(int pr = 0; pr < ns; \+\+pr\) \{  "),
+             ("T3 dispatch+otsu call", r"^  // ---- T3:"), ("T4 dispatch", r"^  // ---- T4:"), ("T5 counts", r"^  // ---- T5:"),
+             ("phi assembly", r"^  // ---- phi1"), ("nets dispatch", r"^  // all-gather of a per-tile array"), ("host", r"^}  // namespace mcaq")]
+    lines = open(srcp).read().split("\n")
+    starts = []
+    for name, rx in marks:
+        for i, l in enumerate(lines, 1):
+            if re.search(rx, l):
+                starts.append((i, name))
+                break
+    starts.sort()
+    def stage(ln):
+        name = "morph_fused.cu:head"
+        for st, n in starts:
+            if ln >= st:
+                name = n
+        return name
     g = defaultdict(float); gs = defaultdict(float)
     for (f, ln), v in inst.items():
-        name = f
-        if f == "morph_fused.cu":
-            name = "morph_fused.cu:other"
-            for n, a, b in R:
-                if a <= ln <= b:
-                    name = n
-                    break
+        name = stage(ln) if f == "morph_fused.cu" else f
         g[name] += v; gs[name] += samp[(f, ln)]
     print()
     for n in sorted(g, key=lambda k: -g[k]):
