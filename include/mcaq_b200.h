@@ -147,11 +147,12 @@ MCAQ_API int mcaq_tile_quantize_train_bwd_kd(const void* grad_y, const void* x, 
 /* Level 0: the reference's launcher, same symbol and argument list (ops/src/mcaq_kernel.cu:102-111,
  * engine/MCAQPlugin.cpp:15-24).  It returns void there; here the outcome of a thread's last call is
  * kept in mcaq_level0_status() (0 / cudaError_t / negative MCAQ_E*), and mcaq_spatial_quantization is the
- * same call returning that code.  When the tile grid divides the map (tile_h * n_tiles_h == H, same for W)
- * and the geometry is 16-byte friendly -- every YOLO feature map -- this IS the vector kernel of the fused
- * path (K3, ranges given directly); other geometries take a scalar kernel with the entry point's own tile
- * rule min(h / tile_h, n_tiles_h - 1).  Rounding follows the reference's PyTorch path (half-to-even, IEEE
- * division), not its kernel's roundf. */
+ * same call returning that code.  tile_h / tile_w must be H / n_tiles_h and W / n_tiles_w, what the
+ * reference's caller passes (quantization.py:641-642); anything else is MCAQ_EINVAL.  For 16-byte friendly
+ * geometries -- every YOLO feature map -- this IS the vector kernel of the fused path (K3, ranges given
+ * directly); others take a scalar kernel.  Tile rule and rounding follow the reference's PyTorch path
+ * (F.interpolate nearest, half-to-even, IEEE division) -- the parity bar -- which coincides with the reference
+ * kernel's h / tile_h whenever the tile grid divides the map. */
 MCAQ_API void launch_spatial_quantization(const float* input, const float* bit_map,
                                  const float* min_vals, const float* max_vals,
                                  const float* mask, float* output,
@@ -177,6 +178,20 @@ MCAQ_API int mcaq_morph_phi(const float* sum_plane, int B, int C, int H, int W, 
                    const float* consts, float* phi,
                    float* gray_dbg, uint32_t* edge_bits_dbg, uint32_t* bin_bits_dbg,
                    int32_t* lbp_hist_dbg, int32_t* counts_dbg, void* stream);
+
+/* Image-sized planes (curriculum scoring on raw 640x640 / 1280x1280 images: utils/dataset.py:345-353 ->
+ * core/morphology.py:923-937; tests/test_smoke.py:33-47 parametrises H=640): the fused kernel above keeps a
+ * plane of at most 160 columns / tiles of at most 32 pixels on chip.  mcaq_morph_fits tells which path a
+ * geometry takes; mcaq_morph_phi_planes computes the same phi with a five-launch pipeline over L2-resident
+ * planes (min/max, stage A, Otsu, stage B; csrc/morph_planes.cu), tiles up to 128 pixels, any plane size,
+ * in a caller-owned workspace of mcaq_morph_planes_workspace bytes (16-byte aligned).  counts_dbg there is
+ * (B,ht,wt,12): edge, area, perimeter, 4*Euler, N_2..N_128 (7 slots), Otsu bin. */
+MCAQ_API int mcaq_morph_fits(int B, int C, int H, int W, int grid_size);
+MCAQ_API long long mcaq_morph_planes_workspace(int B, int C, int H, int W, int grid_size);
+MCAQ_API int mcaq_morph_phi_planes(const float* sum_plane, int B, int C, int H, int W, int grid_size,
+                                   void* workspace, long long workspace_bytes, float* phi, float* gray_dbg,
+                                   uint32_t* edge_bits_dbg, uint32_t* bin_bits_dbg, int32_t* lbp_hist_dbg,
+                                   int32_t* counts_dbg, void* stream);
 
 /* K2 fused: everything between the two HBM sweeps of the inference hook in ONE launch
  * (models/mcaq_yolo.py:426-447): phi -> complexity (MLP, bilateral) -> bit map (MLP mapper, or

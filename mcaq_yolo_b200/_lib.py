@@ -57,6 +57,10 @@ PROTOTYPES = {
     "mcaq_level0_status": (c_int, []),
     "mcaq_morph_phi": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcaq_morph_fits": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "mcaq_morph_planes_workspace": (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
+    "mcaq_morph_phi_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcaq_complexity": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     "mcaq_bit_mapper": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_int, c_int,

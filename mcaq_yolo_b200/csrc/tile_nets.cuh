@@ -54,8 +54,9 @@ __device__ __forceinline__ float sigmoid_exact(float z) {
 }
 
 // n / d for 0 <= n, n * d < 2^32, with magic = 2^32 / d + 1 (one IMAD.HI instead of the division sequence)
+// (d = 1 gives magic 0 = "2^32": the quotient is n itself)
 __device__ __forceinline__ uint32_t div_magic(int d) { return 0xffffffffu / (uint32_t)d + 1u; }
-__device__ __forceinline__ int fast_div(int n, uint32_t magic) { return (int)__umulhi((uint32_t)n, magic); }
+__device__ __forceinline__ int fast_div(int n, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)n, magic) : n; }
 
 // sum over the 32 lanes in xor-butterfly order; every lane returns the same bits
 __device__ __forceinline__ float warp_tree_sum(float v) {

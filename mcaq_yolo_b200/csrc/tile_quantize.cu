@@ -387,15 +387,16 @@ tile_quantize_train_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x
 
 // ---------------------------------------------------------------------------------------------
 // reference-compatible launcher, odd geometries: builds {scale, zp} per (bit, channel) on the fly from
-// min/max (no workspace in that signature), one CTA-level table in shared memory; the tile of a pixel is
-// min(h / tile_h, n_tiles_h - 1) x min(w / tile_w, n_tiles_w - 1), the rule of the entry point it replaces
-// (ops/src/mcaq_kernel.cu:48-51).  Geometries the vector kernel covers never come here.
+// min/max (no workspace in that signature), one CTA-level table in shared memory.  The tile of a pixel follows
+// F.interpolate(nearest) on (H, n_tiles_h) like the reference's PyTorch path (quantization.py:729-744) -- the
+// parity bar -- which coincides with the reference kernel's h / tile_h whenever the grid divides the map.
+// Geometries the vector kernel covers never come here.
 // ---------------------------------------------------------------------------------------------
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(256)
 spatial_quant_compat_kernel(const float* __restrict__ x, const float* __restrict__ bit_map,
                             const float* __restrict__ mn, const float* __restrict__ mx,
-                            const float* __restrict__ mask, float* __restrict__ y, QGeom g, int tile_h, int tile_w) {
+                            const float* __restrict__ mask, float* __restrict__ y, QGeom g) {
   extern __shared__ float2 tab[];                      // [7][cchunk]
   const int cchunk = QCHUNK;
   const int c_begin = blockIdx.y * cchunk;
@@ -417,7 +418,7 @@ spatial_quant_compat_kernel(const float* __restrict__ x, const float* __restrict
   const int b = (int)(gp / g.HW);
   const int pix = (int)(gp - (long long)b * g.HW);
   const int h = pix / g.W, w = pix - h * g.W;
-  const int ty = min(h / tile_h, g.Ht - 1), tx = min(w / tile_w, g.Wt - 1);
+  const int ty = nearest_src(h, g.sy, g.Ht), tx = nearest_src(w, g.sx, g.Wt);
   float bf = rintf(__ldg(bit_map + ((long long)b * g.Ht + ty) * g.Wt + tx));
   bf = fminf(fmaxf(bf, 2.f), 8.f);
   const int bidx = (int)bf - 2;
@@ -615,10 +616,11 @@ extern "C" int mcaq_tile_quantize_train_bwd(const void* grad_y, const void* x, v
 }
 
 // Level 0 of the drop-in boundary: the reference's launcher (ops/src/mcaq_kernel.cu:102-111, shared with
-// engine/MCAQPlugin.cpp:15-24) with an error channel.  When the tile grid divides the map (tile_h * n_tiles_h
-// == H, likewise W: every YOLO feature map) and rows / tiles are 16-byte friendly it IS the vector kernel of
-// the fused path (per-channel ranges given directly, no table kernel); other geometries take the scalar
-// kernel with the entry point's own tile rule.  Rounding is half-to-even like the reference's PyTorch path.
+// engine/MCAQPlugin.cpp:15-24) with an error channel.  tile_h / tile_w must be what the reference's caller
+// passes (H / n_tiles_h, W / n_tiles_w, quantization.py:641-642; anything else is MCAQ_EINVAL).  When the
+// geometry is 16-byte friendly (every YOLO feature map) it IS the vector kernel of the fused path (per-channel
+// ranges given directly, no table kernel); other geometries take the scalar kernel.  Tile rule and rounding
+// follow the reference's PyTorch path (nearest, half-to-even), the parity bar.
 extern "C" int mcaq_spatial_quantization(const float* input, const float* bit_map, const float* min_vals,
                                          const float* max_vals, const float* mask, float* output, int N, int C,
                                          int H, int W, int tile_h, int tile_w, int n_tiles_h, int n_tiles_w,
@@ -628,15 +630,15 @@ extern "C" int mcaq_spatial_quantization(const float* input, const float* bit_ma
     return MCAQ_EINVAL;
   if ((long long)H * W > 0x7fffffffLL) return MCAQ_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool divides = (long long)tile_h * n_tiles_h == H && (long long)tile_w * n_tiles_w == W;
-  if (divides && seg_ok(input, output, mask, nullptr, H * W, W, n_tiles_w, 4))
+  if (tile_h != H / n_tiles_h || tile_w != W / n_tiles_w) return MCAQ_EINVAL;
+  if (seg_ok(input, output, mask, nullptr, H * W, W, n_tiles_w, 4))
     return launch_quant<float, 4>(input, output, N, C, H, W, bit_map, n_tiles_h, n_tiles_w, nullptr, mask, nullptr, st,
                                   QRanges{nullptr, min_vals, max_vals});
   QGeom g = make_geom(N, C, H, W, n_tiles_h, n_tiles_w, 1);
   dim3 grid((unsigned)(((long long)N * H * W + 255) / 256), (unsigned)((C + QCHUNK - 1) / QCHUNK));
   const size_t smem = 7 * QCHUNK * sizeof(float2);
-  if (mask) spatial_quant_compat_kernel<true><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g, tile_h, tile_w);
-  else spatial_quant_compat_kernel<false><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g, tile_h, tile_w);
+  if (mask) spatial_quant_compat_kernel<true><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g);
+  else spatial_quant_compat_kernel<false><<<grid, 256, smem, st>>>(input, bit_map, min_vals, max_vals, mask, output, g);
   MCAQ_LAUNCH_CHECK();
   return 0;
 }

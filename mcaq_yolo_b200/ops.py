@@ -300,16 +300,28 @@ def spatial_quantize(input: torch.Tensor, bit_map: torch.Tensor, min_vals: torch
 
 
 # ----------------------------------------------------------------------------- K2
-def morph_phi(sum_plane: torch.Tensor, C: int, grid_size: int, consts: torch.Tensor, debug: bool = False):
-    """phi tiles (B,ht,wt,8) from the channel-sum plane (morphology.py:826-873)."""
+def morph_fits(B: int, C: int, H: int, W: int, grid_size: int) -> bool:
+    """True when the fused per-image kernel covers the geometry (planes up to 160 columns, tiles up to 32)."""
+    return bool(_lib.load().mcaq_morph_fits(int(B), int(C), int(H), int(W), int(grid_size)))
+
+
+def morph_phi(sum_plane: torch.Tensor, C: int, grid_size: int, consts: torch.Tensor, debug: bool = False,
+              force_planes: bool = False):
+    """phi tiles (B,ht,wt,8) from the channel-sum plane (morphology.py:826-873).  Feature-map sized planes run
+    in the fused per-image kernel; image-sized ones (640x640, 1280x1280: tiles of 64 / 128 pixels, the
+    curriculum-scoring inputs of utils/dataset.py:345-353) in the plane pipeline (csrc/morph_planes.cu)."""
     _need_cuda(sum_plane, consts)
     B, H, W = sum_plane.shape
     tile = tile_size(H, grid_size)
     ht, wt = H // tile, W // tile
+    if ht <= 0 or wt <= 0:
+        raise RuntimeError(f"plane {H}x{W} is smaller than one {tile}-pixel tile")
     Hc, Wc = ht * tile, wt * tile
     dev = sum_plane.device
+    sum_plane = _f32c(sum_plane)
     phi = torch.empty((B, ht, wt, 8), device=dev, dtype=torch.float32)
     dbg = {}
+    fits = morph_fits(B, C, H, W, grid_size) and not force_planes      # force_planes: tests cross-check the two paths
     if debug:
         ww = (Wc + 31) // 32
         dbg = dict(gray=torch.empty((B, Hc, Wc), device=dev, dtype=torch.float32),
@@ -317,10 +329,19 @@ def morph_phi(sum_plane: torch.Tensor, C: int, grid_size: int, consts: torch.Ten
                    bin_bits=torch.zeros((B, Hc, ww), device=dev, dtype=torch.int32),
                    lbp_hist=torch.zeros((B, ht, wt, 10), device=dev, dtype=torch.int32),
                    counts=torch.zeros((B, ht, wt, 12), device=dev, dtype=torch.int32))
-    _call("mcaq_morph_phi", sum_plane.data_ptr(), B, int(C), H, W, int(grid_size), consts.data_ptr(),
-                                     phi.data_ptr(), _ptr(dbg.get("gray")), _ptr(dbg.get("edge_bits")),
-                                     _ptr(dbg.get("bin_bits")), _ptr(dbg.get("lbp_hist")),
-                                     _ptr(dbg.get("counts")), _stream())
+    if fits:
+        _call("mcaq_morph_phi", sum_plane.data_ptr(), B, int(C), H, W, int(grid_size), consts.data_ptr(),
+              phi.data_ptr(), _ptr(dbg.get("gray")), _ptr(dbg.get("edge_bits")),
+              _ptr(dbg.get("bin_bits")), _ptr(dbg.get("lbp_hist")),
+              _ptr(dbg.get("counts")), _stream())
+    else:
+        nbytes = _lib.load().mcaq_morph_planes_workspace(B, int(C), H, W, int(grid_size))
+        if nbytes < 0:
+            check(int(nbytes), "mcaq_morph_planes_workspace")
+        ws = torch.empty((int(nbytes),), device=dev, dtype=torch.uint8)
+        _call("mcaq_morph_phi_planes", sum_plane.data_ptr(), B, int(C), H, W, int(grid_size), ws.data_ptr(),
+              int(nbytes), phi.data_ptr(), _ptr(dbg.get("gray")), _ptr(dbg.get("edge_bits")),
+              _ptr(dbg.get("bin_bits")), _ptr(dbg.get("lbp_hist")), _ptr(dbg.get("counts")), _stream())
     return (phi, dbg) if debug else phi
 
 

@@ -316,7 +316,7 @@ def test_errors_are_loud(ops):
     with pytest.raises(RuntimeError):
         ops.reduce_planes(torch.zeros(1, 4, 8, 8))                      # CPU tensor: no fallback
     with pytest.raises(TypeError):
-        ops.reduce_planes(torch.zeros(1, 4, 8, 8, device="cuda", dtype=torch.float16))
+        ops.reduce_planes(torch.zeros(1, 4, 8, 8, device="cuda", dtype=torch.float64))   # fp32 / bf16 / fp16 only
     x = torch.zeros(1, 4, 8, 8, device="cuda")
     with pytest.raises(RuntimeError):
         ops.tile_quantize(x, torch.zeros(2, 2, 2, device="cuda"), torch.zeros(7, 4, 2, device="cuda"))

@@ -14,7 +14,7 @@ def M():
     return modules
 
 
-@pytest.mark.parametrize("H", [160, 80, 40, 20])
+@pytest.mark.parametrize("H", [640, 160, 80, 40, 20])             # the reference's own list starts at 640
 def test_phi_tiles_shapes(H, M):                                     # test_smoke.py:33-47
     a = M.MorphologicalComplexityAnalyzer(device="cuda")
     torch.manual_seed(0)
@@ -28,15 +28,19 @@ def test_phi_tiles_shapes(H, M):                                     # test_smok
     assert float(phi.min()) >= 0.0 and float(phi.max()) <= 1.0 + 1e-5
 
 
-def test_phi_tiles_beyond_the_on_chip_budget_fail_loudly(M):
-    """640-pixel planes (the reference's first parametrisation: raw images, 64-pixel tiles) are outside the
-    morphology kernel's on-chip budget (<= 160 columns, tiles <= 32): a loud error from the C ABI, never a
-    silent fallback."""
+def test_phi_tiles_on_image_sized_planes(M):
+    """Planes beyond the fused kernel's on-chip budget (> 160 columns or tiles > 32 pixels: raw 640 / 1280
+    images, utils/dataset.py:345-353) take the plane pipeline (csrc/morph_planes.cu), same results contract."""
+    from mcaq_yolo_b200 import ops
     a = M.MorphologicalComplexityAnalyzer(device="cuda")
-    with pytest.raises(RuntimeError, match="mcaq_morph_phi failed"):
-        a.compute_phi_tiles(torch.rand(1, 3, 640, 640, device="cuda"))
-    with pytest.raises(RuntimeError, match="on-chip budget"):
-        a.compute_phi_tiles(torch.rand(1, 3, 192, 192, device="cuda"))      # 16-pixel tiles, 192 columns = 6 words per row
+    assert not ops.morph_fits(1, 3, 640, 640, 8) and not ops.morph_fits(1, 3, 192, 192, 8)
+    assert ops.morph_fits(64, 64, 80, 80, 8) and ops.morph_fits(8, 128, 160, 160, 8)
+    for H, ht in ((1280, 10), (192, 12), (200, 12)):
+        phi, _ = a.compute_phi_tiles(torch.rand(1, 3, H, H, device="cuda"))
+        assert phi.shape == (1, ht, ht, 8) and bool(torch.isfinite(phi).all())
+        assert float(phi.min()) >= 0.0 and float(phi.max()) <= 1.0 + 1e-5
+    s = a.score_image(torch.rand(3, 3, 640, 640, device="cuda"))
+    assert s.shape == (3,) and float(s.min()) >= 0.0 and float(s.max()) <= 1.0
 
 
 def test_analyzer_forward_range_and_grad(M):                         # test_smoke.py:50-59

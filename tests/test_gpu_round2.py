@@ -60,9 +60,16 @@ def test_full_batch64_bf16_against_oracle(M, W):
         xu = xb.float().cpu().numpy()
         d = {}
         r = o.hook_forward(xu, W["analyzer"], W["mapper"], W["quantizer"], 8, 1.0, detail=d)
-        assert int(bit_ambiguous(d["bits_pre_round"]).sum()) == 0, "ambiguous tiles in the full-size case"
+        # 6400 tiles per scale: a tile whose continuous bit value sits within 1e-4 of a .5 boundary does occur
+        # here (unlike in the small committed cases); bit maps must be EQUAL everywhere else
+        amb = bit_ambiguous(d["bits_pre_round"])
+        assert int(amb.sum()) <= 4, f"{int(amb.sum())} ambiguous tiles"
         bm = rec["bit_map"].cpu().numpy()
-        assert np.array_equal(bm, r["bit_map"]), f"C{3 + si}: {(bm != r['bit_map']).sum()} bit-map tiles differ"
+        nd = int(((bm != r["bit_map"]) & ~amb).sum())
+        assert nd == 0, f"C{3 + si}: {nd} bit-map tiles differ outside the ambiguity set"
+        if not np.array_equal(bm, r["bit_map"]):          # continue on the GPU's choice for the ambiguous tile(s)
+            r["m"] = o.soft_mask(bm, r["abs_sum"], C, W["quantizer"])
+            r["y"], r["codes"] = o.quantize_eval(xu, bm, r["min"], r["max"], r["m"])
         np.testing.assert_allclose(rec["complexity"].cpu().numpy(), r["complexity"], rtol=RTOL, atol=ATOL)
         # integer codes: K3 on the same bit map / ranges / mask the fused launch used
         with torch.no_grad():
@@ -259,3 +266,23 @@ def test_no_ambiguous_tiles_in_committed_cases(name, M, W):
     with torch.no_grad():
         rec = M.mcaq_hook_forward(torch.from_numpy(x).cuda(), a, m, q, temperature=1.0)
     assert np.array_equal(rec["bit_map"].cpu().numpy(), c["bit_map_mlp"])
+
+
+# ------------------------------------------------------------------ Level-0 launcher
+def test_level0_launcher_vector_path_and_error_channel(W):
+    """`launch_spatial_quantization` (ops/src/mcaq_kernel.cu:102-111): routed to the vector kernel, equal to the
+    table path; inconsistent tile arguments surface as an error (the reference's void launcher had none)."""
+    from mcaq_yolo_b200 import _lib, ops
+    c = Case("c3_v8n_smooth")
+    x = dev(c.x())
+    bm = dev(c["bit_map_rand"])
+    mn, mx = dev(c["ch_min"]), dev(c["ch_max"])
+    m = dev(c["soft_mask"]).unsqueeze(1)
+    y = ops.spatial_quantize(x, bm, mn.view(1, -1, 1, 1), mx.view(1, -1, 1, 1), c.tile, c.tile, m)
+    yo, _ = o.quantize_eval(c.x(), c["bit_map_rand"], c["ch_min"], c["ch_max"], c["soft_mask"])
+    assert np.array_equal(y.cpu().numpy(), yo)
+    assert _lib.load().mcaq_level0_status() == 0
+    with pytest.raises(RuntimeError, match="launch_spatial_quantization"):
+        ops.spatial_quantize(x, bm, mn.view(1, -1, 1, 1), mx.view(1, -1, 1, 1), c.tile + 1, c.tile, m)
+    with pytest.raises(RuntimeError):
+        ops.spatial_quantize(x, bm, mn[:3], mx[:3], c.tile, c.tile, m)
