@@ -272,6 +272,43 @@ MCAQ_API int mcaq_soft_mask(const float* bit_map, int Ht, int Wt, const float* a
                    int B, int C, int H, int W, const float* softmask, float* mask_tiles /* nullable */,
                    float* mask, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training forms of the three tile-level networks (csrc/train_nets.cu).  The reference trains them through
+ * ~10^3 eager autograd kernels per step (core/morphology.py:81-97, 309-354; core/bit_allocation.py:218-280 with
+ * train-mode BatchNorm1d :126; core/quantization.py:213-239); here a network is one or two launches per
+ * direction.  Parameter / gradient blocks are the flat concatenation of the torch parameters in module order
+ * (complexity MLP 2881, mapper 4609, soft mask 170 floats); gradient blocks are ACCUMULATED into.
+ *   complexity: forward = mcaq_complexity (keep its raw output); mcaq_complexity_train_bwd = bilateral + clamp +
+ *               MLP backward (scratch: mcaq_cmlp_train_scratch_floats(B*ht*wt) floats, grad_craw_ws: B*ht*wt)
+ *   mapper    : mcaq_mapper_train_fwd / _bwd run as ONE 8-CTA thread-block cluster; BatchNorm batch statistics
+ *               are reduced through distributed shared memory and -- xchg_world > 1, buffers of a C = 128 range
+ *               exchange -- merged with the other ranks of the node over NVLink peer memory inside the kernel
+ *               (rank-ordered Chan merge: every rank gets the statistics of the unsharded batch).
+ *               scratch: mcaq_mapper_train_scratch_floats(N) floats shared by forward and backward; stats: 256.
+ *   soft mask : forward = mcaq_soft_mask; mcaq_softmask_act gives the normalised tile activity the backward needs
+ *   losses    : mcaq_bit_stats adds sum(bit_map) and its total variation into out2 (Lbit / Lsmooth,
+ *               models/mcaq_yolo.py:86-118, 575) and, given weights2, writes d(w0 sum + w1 TV)/d bit_map */
+MCAQ_API long long mcaq_cmlp_train_scratch_floats(int N);
+MCAQ_API long long mcaq_mapper_train_scratch_floats(int N);
+MCAQ_API int mcaq_complexity_train_bwd(const float* phi, const float* craw, const float* grad_out, int B, int ht, int wt,
+                                       const float* params, float* scratch, float* grad_craw_ws, float* grad_params,
+                                       void* stream);
+MCAQ_API int mcaq_mapper_train_fwd(const float* cmap, int N, const float* params, float temperature, int use_temperature,
+                                   float min_bits, float max_bits, float* scratch, float* stats, float* rm0, float* rv0,
+                                   float* rm1, float* rv1, float* rm2, float* rv2, float momentum, float eps, float* bits,
+                                   void* const* xchg_peers, int xchg_rank, int xchg_world, void* stream);
+MCAQ_API int mcaq_mapper_train_bwd(const float* cmap, int N, const float* params, float temperature, int use_temperature,
+                                   float min_bits, float max_bits, float* scratch, const float* stats, float eps,
+                                   const float* grad_bits, float* grad_c, float* grad_params, void* const* xchg_peers,
+                                   int xchg_rank, int xchg_world, void* stream);
+MCAQ_API int mcaq_softmask_act(const float* abs_plane, int B, int C, int H, int W, int Ht, int Wt, float* act_norm,
+                               void* stream);
+MCAQ_API int mcaq_softmask_train_bwd(const float* grad_mask, const float* bit_map, const float* act_norm,
+                                     const float* params, int B, int H, int W, int Ht, int Wt, float* grad_bit_map,
+                                     float* grad_params, void* stream);
+MCAQ_API int mcaq_bit_stats(const float* bit_map, int B, int ht, int wt, float* out2, const float* weights2,
+                            float* grad_bit_map, void* stream);
+
 /* Self test of the quantiser's division (RN(x/scale) by Markstein's correction with RN(1/scale))
  * against div.rn: sweeps numerators with bit patterns first + i*stride, i < count, for every
  * scale; *mismatches must be zeroed by the caller. */

@@ -82,6 +82,19 @@ PROTOTYPES = {
                                       c_void_p]),
     "mcaq_tile_quantize_xchg": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                         c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcaq_cmlp_train_scratch_floats": (c_longlong, [c_int]),
+    "mcaq_mapper_train_scratch_floats": (c_longlong, [c_int]),
+    "mcaq_complexity_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p]),
+    "mcaq_mapper_train_fwd": (c_int, [c_void_p, c_int, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                      c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mcaq_mapper_train_bwd": (c_int, [c_void_p, c_int, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p,
+                                      c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mcaq_softmask_act": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mcaq_softmask_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p]),
+    "mcaq_bit_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcaq_soft_mask": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -19,6 +19,7 @@ import torch.nn.functional as F
 
 from . import constants as K
 from . import ops
+from . import train_nets as TN
 
 
 # ---------------------------------------------------------------------------------------------
@@ -140,8 +141,11 @@ class MorphologicalComplexityAnalyzer(nn.Module):
         B, ht, wt, _ = phi.shape
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.complexity_mlp.parameters())
         if needs_grad:
-            cmap = self.complexity_mlp(phi.reshape(-1, 8)).reshape(B, ht, wt)
-            cmap = self.bilateral_filter(cmap).clamp(0.0, 1.0)
+            # training: the inference kernel forward (raw MLP output kept), native backward through clamp, bilateral
+            # filter and the MLP with its LayerNorms (csrc/train_nets.cu) -- two launches instead of ~150
+            flat = TN.flat_params(self.complexity_mlp.parameters())
+            cmap = TN.ComplexityTrainFn.apply(phi, flat, K.pack_complexity_mlp(self.complexity_mlp),
+                                              K.device_constants(features.device))
         else:
             cmap = ops.complexity(phi, K.pack_complexity_mlp(self.complexity_mlp),
                                   K.device_constants(features.device))
@@ -212,6 +216,9 @@ class ComplexityToBitMappingNetwork(nn.Module):
             d = h
         layers += [nn.Linear(d, 1), nn.Sigmoid()]
         self.mapping_network = nn.Sequential(*layers)
+        # multi-GPU training: a peer.RangeExchange.create(128) makes the BatchNorm statistics those of the whole
+        # (sharded) batch, merged inside the kernels over NVLink peer memory; None = this rank's rows only
+        self.stat_exchange = None
         for m in self.mapping_network:
             if isinstance(m, nn.Linear):
                 nn.init.xavier_uniform_(m.weight, gain=0.5)
@@ -242,9 +249,18 @@ class ComplexityToBitMappingNetwork(nn.Module):
         if self._kernel_ok() and not wants_grad:
             return ops.bit_mapper(c, K.pack_mapping_network(self.mapping_network), temperature,
                                   return_continuous, self.min_bits, self.max_bits)
-        # training (BatchNorm batch statistics, autograd): tiny (B*ht*wt, 3) problem
-        c = c.clamp(0.0, 1.0)
         B, H, W = c.shape
+        if self.training and self.hidden_dims == [32, 64, 32] and c.is_cuda:
+            # train mode: BatchNorm batch statistics over all B*ht*wt tiles (of all ranks when `stat_exchange`
+            # is set), running statistics updated, one cluster launch per direction (csrc/train_nets.cu)
+            seq = self.mapping_network
+            bits = TN.MapperTrainFn.apply(c.reshape(-1), TN.flat_params(seq.parameters()), (seq[1], seq[4], seq[7]),
+                                          temperature, self.min_bits, self.max_bits, self.stat_exchange).reshape(B, H, W)
+            if not return_continuous:
+                bits = bits + (torch.round(bits) - bits).detach()
+            return bits
+        # eval-mode BatchNorm with gradients wanted, or a non-default width: torch autograd on the tiny problem
+        c = c.clamp(0.0, 1.0)
         h = self.mapping_network(self.create_augmented_features(c.reshape(-1, 1)))
         bits = (self.min_bits + (self.max_bits - self.min_bits) * h).reshape(B, H, W)
         return _ste_finish(bits, temperature, self.min_bits, self.max_bits, return_continuous)
@@ -277,6 +293,11 @@ class LearnedSoftMask(nn.Module):
             bit_map.requires_grad or any(p.requires_grad for p in self.net.parameters()))
         if not wants_grad and self.hidden == 8 and self.kernel_size == 5:
             return ops.soft_mask(bit_map, abs_plane, C, K.pack_soft_mask(self)).unsqueeze(1)
+        if self.hidden == 8 and self.kernel_size == 5:
+            # training: inference kernel forward, native backward (smoothing / upsampling transposed, softmax, the
+            # two convolutions) -- gradients to the bit map and the four parameter tensors
+            flat = TN.flat_params(self.net.parameters())
+            return TN.SoftMaskTrainFn.apply(bit_map, flat, abs_plane, C, K.pack_soft_mask(self)).unsqueeze(1)
         Ht, Wt = bit_map.shape[-2:]
         with torch.no_grad():
             act = F.adaptive_avg_pool2d((abs_plane / C).unsqueeze(1), (Ht, Wt))
