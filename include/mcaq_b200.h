@@ -295,7 +295,8 @@ MCAQ_API int mcaq_complexity_train_bwd(const float* phi, const float* craw, cons
                                        void* stream);
 MCAQ_API int mcaq_mapper_train_fwd(const float* cmap, int N, const float* params, float temperature, int use_temperature,
                                    float min_bits, float max_bits, float* scratch, float* stats, float* rm0, float* rv0,
-                                   float* rm1, float* rv1, float* rm2, float* rv2, float momentum, float eps, float* bits,
+                                   float* rm1, float* rv1, float* rm2, float* rv2, long long* nbt0, long long* nbt1,
+                                   long long* nbt2, float momentum, float eps, float* bits,
                                    void* const* xchg_peers, int xchg_rank, int xchg_world, void* stream);
 MCAQ_API int mcaq_mapper_train_bwd(const float* cmap, int N, const float* params, float temperature, int use_temperature,
                                    float min_bits, float max_bits, float* scratch, const float* stats, float eps,

@@ -87,8 +87,8 @@ PROTOTYPES = {
     "mcaq_complexity_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p]),
     "mcaq_mapper_train_fwd": (c_int, [c_void_p, c_int, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p,
-                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
-                                      c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mcaq_mapper_train_bwd": (c_int, [c_void_p, c_int, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p,
                                       c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mcaq_softmask_act": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

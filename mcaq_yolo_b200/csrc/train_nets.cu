@@ -29,93 +29,27 @@ namespace cg = cooperative_groups;
 
 namespace mcaq {
 
-// ---- small dense helpers: thread-private vectors, weights read at warp-uniform addresses (broadcast) ----------
-template <int IN, int OUT>
-__device__ __forceinline__ void dense_fwd(const float* __restrict__ Wm, const float* __restrict__ b, const float (&x)[IN],
-                                          float (&y)[OUT]) {
-#pragma unroll 4
-  for (int j = 0; j < OUT; ++j) {
-    float a = 0.f;
+// ---- warp helpers: a warp carries one row (tile) at a time, lane = unit ------------------------------------------
+__device__ __forceinline__ float wsum(float v) {
 #pragma unroll
-    for (int i = 0; i < IN; ++i) a = fmaf(__ldg(Wm + j * IN + i), x[i], a);
-    y[j] = __fadd_rn(a, __ldg(b + j));
-  }
+  for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
 }
-template <int IN, int OUT>
-__device__ __forceinline__ void dense_bwd_data(const float* __restrict__ Wm, const float (&gy)[OUT], float (&gx)[IN]) {
-#pragma unroll
-  for (int i = 0; i < IN; ++i) gx[i] = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < OUT; ++j) {
-    const float g = gy[j];
-#pragma unroll
-    for (int i = 0; i < IN; ++i) gx[i] = fmaf(__ldg(Wm + j * IN + i), g, gx[i]);
-  }
+// stage a row-major [OUT][IN] matrix into shared memory with row stride IN + 1 (conflict-free by row AND by column)
+__device__ __forceinline__ void stage_matrix(const float* __restrict__ Wg, float* Ws, int OUT, int IN) {
+  for (int i = threadIdx.x; i < OUT * IN; i += blockDim.x) Ws[(i / IN) * (IN + 1) + (i % IN)] = __ldg(Wg + i);
 }
-
-// gW[j][i] += sum_r GY[r][j] * X[r][i], gb[j] += sum_r GY[r][j] over rows [r0, r1): thread per parameter
-__device__ __forceinline__ void wgrad_rows(const float* __restrict__ GY, int ldg_, const float* __restrict__ X, int ldx,
-                                           int r0, int r1, int IN, int OUT, float* __restrict__ gW, float* __restrict__ gb) {
-  for (int p = threadIdx.x; p < OUT * IN + OUT; p += blockDim.x) {
-    float acc = 0.f;
-    if (p < OUT * IN) {
-      const int j = p / IN, i = p - j * IN;
-      for (int r = r0; r < r1; ++r) acc = fmaf(GY[(long long)r * ldg_ + j], X[(long long)r * ldx + i], acc);
-      atomicAdd(gW + p, acc);
-    } else {
-      const int j = p - OUT * IN;
-      for (int r = r0; r < r1; ++r) acc = __fadd_rn(acc, GY[(long long)r * ldg_ + j]);
-      atomicAdd(gb + j, acc);
-    }
-  }
+// add a CTA's per-warp register accumulators into a global gradient block: smem staging (one atomic per warp and
+// value into shared memory, then one global atomic per CTA and value)
+__device__ __forceinline__ void flush_begin(float* buf, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) buf[i] = 0.f;
+  __syncthreads();
 }
-// column sums of P[r][k] (and optionally Q[r][k]) over rows [r0, r1) added into g1 / g2 (LN / BN affine gradients)
-__device__ __forceinline__ void colsum_rows(const float* __restrict__ P, const float* __restrict__ Q, int ld, int r0, int r1,
-                                            int K, float* __restrict__ g1, float* __restrict__ g2) {
-  for (int k = threadIdx.x; k < 2 * K; k += blockDim.x) {
-    const float* src = k < K ? P : Q;
-    if (!src) continue;
-    const int kk = k < K ? k : k - K;
-    float acc = 0.f;
-    for (int r = r0; r < r1; ++r) acc = __fadd_rn(acc, src[(long long)r * ld + kk]);
-    atomicAdd((k < K ? g1 : g2) + kk, acc);
-  }
-}
-
-template <int D>
-__device__ __forceinline__ void ln_fwd(const float (&z)[D], const float* __restrict__ g, const float* __restrict__ b,
-                                       float (&xh)[D], float (&y)[D], float& rstd) {
-  float m = 0.f;
-#pragma unroll
-  for (int k = 0; k < D; ++k) m = __fadd_rn(m, z[k]);
-  m = __fmul_rn(m, 1.0f / D);
-  float v = 0.f;
-#pragma unroll
-  for (int k = 0; k < D; ++k) { const float d = __fsub_rn(z[k], m); v = fmaf(d, d, v); }
-  v = __fmul_rn(v, 1.0f / D);
-  rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(v, 1e-5f)));
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    xh[k] = __fmul_rn(__fsub_rn(z[k], m), rstd);
-    y[k] = fmaxf(fmaf(xh[k], __ldg(g + k), __ldg(b + k)), 0.f);
-  }
-}
-// gz from gy (gradient at the LN output BEFORE the ReLU mask is applied by the caller)
-template <int D>
-__device__ __forceinline__ void ln_bwd(const float (&gy)[D], const float (&xh)[D], const float* __restrict__ g, float rstd,
-                                       float (&gz)[D]) {
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    const float gx = __fmul_rn(gy[k], __ldg(g + k));
-    gz[k] = gx;
-    s1 = __fadd_rn(s1, gx);
-    s2 = fmaf(gx, xh[k], s2);
-  }
-  s1 = __fmul_rn(s1, 1.0f / D);
-  s2 = __fmul_rn(s2, 1.0f / D);
-#pragma unroll
-  for (int k = 0; k < D; ++k) gz[k] = __fmul_rn(rstd, __fsub_rn(__fsub_rn(gz[k], s1), __fmul_rn(xh[k], s2)));
+__device__ __forceinline__ void flush_end(const float* buf, int n, float* __restrict__ g) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (buf[i] != 0.f) atomicAdd(g + i, buf[i]);
+  __syncthreads();
 }
 
 // =================================================================================================
@@ -164,99 +98,197 @@ bilateral_bwd_kernel(const float* __restrict__ craw, const float* __restrict__ g
   for (int i = threadIdx.x; i < nt; i += blockDim.x) gcraw[(long long)b * nt + i] = acc[i];
 }
 
-// (2) MLP: rows [blockIdx.x * rpc, ...): data path (thread per row) into scratch, then the CTA's share of the
-//     parameter gradients.  scratch per row (floats): H1[64] GZ1[64] P1[64] Q1[64] | H2[32] GZ2[32] P2[32] Q2[32] | GZ3
-constexpr int CM_SCR = 4 * 64 + 4 * 32 + 4;
-__global__ void __launch_bounds__(128)
-cmlp_bwd_kernel(const float* __restrict__ phi, const float* __restrict__ gcraw, const float* __restrict__ P, int N, int rpc,
-                float* __restrict__ scratch, float* __restrict__ gP) {
+// (2) MLP: a warp carries a row through the recomputed forward and the backward; lane = unit (two units per lane in
+//     the 64-wide layer), LayerNorm statistics by warp shuffles, the 64 x 32 matrix in shared memory (stride 65),
+//     parameter gradients in per-lane registers over the warp's rows, flushed once per CTA.
+constexpr int CM_NT = 128;
+__global__ void __launch_bounds__(CM_NT)
+cmlp_bwd_kernel(const float* __restrict__ phi, const float* __restrict__ gcraw, const float* __restrict__ P, int N,
+                float* __restrict__ gP) {
+  __shared__ float W3s[32 * 65];
+  __shared__ float rowbuf[CM_NT / 32][64];
+  __shared__ float fb[2881];
   const float* W0 = P; const float* b0 = P + 512; const float* g1 = P + 576; const float* be1 = P + 640;
   const float* W3 = P + 704; const float* b3 = P + 2752; const float* g4 = P + 2784; const float* be4 = P + 2816;
   const float* W6 = P + 2848; const float* b6 = P + 2880;
-  const int r0 = blockIdx.x * rpc, r1 = min(r0 + rpc, N);
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-    float x[8], z1[64], xh1[64], h1[64], z2[32], xh2[32], h2[32];
-    float rs1, rs2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  stage_matrix(W3, W3s, 32, 64);
+  flush_begin(fb, 2881);
+  // per-lane constants: units u0 = lane, u1 = lane + 32 of layer 1; unit lane of layer 2
+  float w0a[8], w0b[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = phi[(long long)r * 8 + i];
-    dense_fwd<8, 64>(W0, b0, x, z1);
-    ln_fwd<64>(z1, g1, be1, xh1, h1, rs1);
-    dense_fwd<64, 32>(W3, b3, h1, z2);
-    ln_fwd<32>(z2, g4, be4, xh2, h2, rs2);
-    float z3 = 0.f;
+  for (int i = 0; i < 8; ++i) { w0a[i] = __ldg(W0 + lane * 8 + i); w0b[i] = __ldg(W0 + (lane + 32) * 8 + i); }
+  const float b0a = __ldg(b0 + lane), b0b = __ldg(b0 + lane + 32);
+  const float g1a = __ldg(g1 + lane), g1b = __ldg(g1 + lane + 32), e1a = __ldg(be1 + lane), e1b = __ldg(be1 + lane + 32);
+  const float b3l = __ldg(b3 + lane), g4l = __ldg(g4 + lane), e4l = __ldg(be4 + lane), w6l = __ldg(W6 + lane), b6v = __ldg(b6);
+  // gradient accumulators
+  float dW0a[8], dW0b[8], dW3r[64];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) z3 = fmaf(__ldg(W6 + k), h2[k], z3);
-    z3 = __fadd_rn(z3, __ldg(b6));
+  for (int i = 0; i < 8; ++i) { dW0a[i] = 0.f; dW0b[i] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < 64; ++k) dW3r[k] = 0.f;
+  float db0a = 0.f, db0b = 0.f, dg1a = 0.f, dg1b = 0.f, de1a = 0.f, de1b = 0.f, db3 = 0.f, dg4 = 0.f, de4 = 0.f, dW6 = 0.f, db6 = 0.f;
+  float* rb = rowbuf[warp];
+  const int nw = gridDim.x * (CM_NT / 32);
+  for (int r = blockIdx.x * (CM_NT / 32) + warp; r < N; r += nw) {
+    float x[8];
+    {
+      const float4 pa = __ldg(reinterpret_cast<const float4*>(phi + (long long)r * 8));
+      const float4 pb = __ldg(reinterpret_cast<const float4*>(phi + (long long)r * 8) + 1);
+      x[0] = pa.x; x[1] = pa.y; x[2] = pa.z; x[3] = pa.w; x[4] = pb.x; x[5] = pb.y; x[6] = pb.z; x[7] = pb.w;
+    }
+    float za = 0.f, zb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { za = fmaf(w0a[i], x[i], za); zb = fmaf(w0b[i], x[i], zb); }
+    za = __fadd_rn(za, b0a); zb = __fadd_rn(zb, b0b);
+    // LayerNorm(64) + ReLU
+    const float m1 = __fmul_rn(wsum(__fadd_rn(za, zb)), 1.0f / 64);
+    const float da = __fsub_rn(za, m1), dbv = __fsub_rn(zb, m1);
+    const float v1 = __fmul_rn(wsum(fmaf(da, da, __fmul_rn(dbv, dbv))), 1.0f / 64);
+    const float rs1 = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(v1, 1e-5f)));
+    const float xha = __fmul_rn(da, rs1), xhb = __fmul_rn(dbv, rs1);
+    const float h1a = fmaxf(fmaf(xha, g1a, e1a), 0.f), h1b = fmaxf(fmaf(xhb, g1b, e1b), 0.f);
+    __syncwarp();
+    rb[lane] = h1a; rb[lane + 32] = h1b;
+    __syncwarp();
+    // layer 2: unit = lane
+    float z2 = 0.f;
+#pragma unroll 16
+    for (int k = 0; k < 64; ++k) z2 = fmaf(W3s[lane * 65 + k], rb[k], z2);
+    z2 = __fadd_rn(z2, b3l);
+    const float m2 = __fmul_rn(wsum(z2), 1.0f / 32);
+    const float d2 = __fsub_rn(z2, m2);
+    const float v2 = __fmul_rn(wsum(__fmul_rn(d2, d2)), 1.0f / 32);
+    const float rs2 = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(v2, 1e-5f)));
+    const float xh2 = __fmul_rn(d2, rs2);
+    const float h2 = fmaxf(fmaf(xh2, g4l, e4l), 0.f);
+    const float z3 = __fadd_rn(wsum(__fmul_rn(w6l, h2)), b6v);
     const float c = sigmoid_exact(z3);
-    const float gz3 = __fmul_rn(gcraw[r], __fmul_rn(c, __fsub_rn(1.0f, c)));
-    float* s = scratch + (long long)r * CM_SCR;
-    float gy2[32], gz2[32];
+    const float gz3 = __fmul_rn(__ldg(gcraw + r), __fmul_rn(c, __fsub_rn(1.0f, c)));
+    dW6 = fmaf(gz3, h2, dW6);
+    db6 = __fadd_rn(db6, gz3);
+    // LN(32) backward
+    const float gy2 = h2 > 0.f ? __fmul_rn(gz3, w6l) : 0.f;
+    dg4 = fmaf(gy2, xh2, dg4);
+    de4 = __fadd_rn(de4, gy2);
+    const float gx2 = __fmul_rn(gy2, g4l);
+    const float t1 = __fmul_rn(wsum(gx2), 1.0f / 32), t2 = __fmul_rn(wsum(__fmul_rn(gx2, xh2)), 1.0f / 32);
+    const float gz2 = __fmul_rn(rs2, __fsub_rn(__fsub_rn(gx2, t1), __fmul_rn(xh2, t2)));
+    db3 = __fadd_rn(db3, gz2);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) gy2[k] = h2[k] > 0.f ? __fmul_rn(gz3, __ldg(W6 + k)) : 0.f;
-    ln_bwd<32>(gy2, xh2, g4, rs2, gz2);
-    float gh1[64], gz1[64];
-    dense_bwd_data<64, 32>(W3, gz2, gh1);
+    for (int k = 0; k < 64; ++k) dW3r[k] = fmaf(gz2, rb[k], dW3r[k]);
+    // data gradient of layer 2: gh1[k] = sum_j W3[j][k] gz2[j], k = lane and lane + 32
+    float gha = 0.f, ghb = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float gj = __shfl_sync(0xffffffffu, gz2, j);
+      gha = fmaf(W3s[j * 65 + lane], gj, gha);
+      ghb = fmaf(W3s[j * 65 + lane + 32], gj, ghb);
+    }
+    const float gya = h1a > 0.f ? gha : 0.f, gyb = h1b > 0.f ? ghb : 0.f;
+    dg1a = fmaf(gya, xha, dg1a); dg1b = fmaf(gyb, xhb, dg1b);
+    de1a = __fadd_rn(de1a, gya); de1b = __fadd_rn(de1b, gyb);
+    const float gxa = __fmul_rn(gya, g1a), gxb = __fmul_rn(gyb, g1b);
+    const float u1 = __fmul_rn(wsum(__fadd_rn(gxa, gxb)), 1.0f / 64);
+    const float u2 = __fmul_rn(wsum(fmaf(gxa, xha, __fmul_rn(gxb, xhb))), 1.0f / 64);
+    const float gza = __fmul_rn(rs1, __fsub_rn(__fsub_rn(gxa, u1), __fmul_rn(xha, u2)));
+    const float gzb = __fmul_rn(rs1, __fsub_rn(__fsub_rn(gxb, u1), __fmul_rn(xhb, u2)));
+    db0a = __fadd_rn(db0a, gza); db0b = __fadd_rn(db0b, gzb);
 #pragma unroll
-    for (int k = 0; k < 64; ++k) gh1[k] = h1[k] > 0.f ? gh1[k] : 0.f;
-    ln_bwd<64>(gh1, xh1, g1, rs1, gz1);
-#pragma unroll
-    for (int k = 0; k < 64; ++k) { s[k] = h1[k]; s[64 + k] = gz1[k]; s[128 + k] = __fmul_rn(gh1[k], xh1[k]); s[192 + k] = gh1[k]; }
-#pragma unroll
-    for (int k = 0; k < 32; ++k) { s[256 + k] = h2[k]; s[288 + k] = gz2[k]; s[320 + k] = __fmul_rn(gy2[k], xh2[k]); s[352 + k] = gy2[k]; }
-    s[384] = gz3;
+    for (int i = 0; i < 8; ++i) { dW0a[i] = fmaf(gza, x[i], dW0a[i]); dW0b[i] = fmaf(gzb, x[i], dW0b[i]); }
   }
+  // flush: per-warp accumulators -> shared block -> global
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { atomicAdd(fb + lane * 8 + i, dW0a[i]); atomicAdd(fb + (lane + 32) * 8 + i, dW0b[i]); }
+  atomicAdd(fb + 512 + lane, db0a); atomicAdd(fb + 512 + lane + 32, db0b);
+  atomicAdd(fb + 576 + lane, dg1a); atomicAdd(fb + 576 + lane + 32, dg1b);
+  atomicAdd(fb + 640 + lane, de1a); atomicAdd(fb + 640 + lane + 32, de1b);
+#pragma unroll
+  for (int k = 0; k < 64; ++k) atomicAdd(fb + 704 + k * 32 + lane, dW3r[k]);      // [k][unit] while in shared memory
+  atomicAdd(fb + 2752 + lane, db3); atomicAdd(fb + 2784 + lane, dg4); atomicAdd(fb + 2816 + lane, de4);
+  atomicAdd(fb + 2848 + lane, dW6);
+  if (lane == 0) atomicAdd(fb + 2880, db6);
   __syncthreads();
-  const float* S = scratch;
-  wgrad_rows(S + 64, CM_SCR, phi, 8, r0, r1, 8, 64, gP, gP + 512);                     // W0, b0
-  colsum_rows(S + 128, S + 192, CM_SCR, r0, r1, 64, gP + 576, gP + 640);               // g1, be1
-  wgrad_rows(S + 288, CM_SCR, S, CM_SCR, r0, r1, 64, 32, gP + 704, gP + 2752);         // W3, b3
-  colsum_rows(S + 320, S + 352, CM_SCR, r0, r1, 32, gP + 2784, gP + 2816);             // g4, be4
-  wgrad_rows(S + 384, CM_SCR, S + 256, CM_SCR, r0, r1, 32, 1, gP + 2848, gP + 2880);   // W6, b6
+  for (int i = threadIdx.x; i < 2881; i += blockDim.x) {
+    const float v = fb[i];
+    if (v == 0.f) continue;
+    const int q = i - 704;                                     // the 32 x 64 block is stored [k][unit]
+    atomicAdd(gP + ((q >= 0 && q < 2048) ? 704 + (q & 31) * 64 + (q >> 5) : i), v);
+  }
 }
 
 // =================================================================================================
-// mapper with train-mode BatchNorm: one cluster of MAP_CL CTAs
+// mapper with train-mode BatchNorm: one cluster of MAP_CL CTAs, rows split over the CTAs, a warp per row
 // =================================================================================================
 constexpr int MAP_CL = 8;
-constexpr int MAP_NT = 256;
-// scratch per row: Z1[32] Z2[64] Z3[32] (forward, kept for backward) | F[4] H1[32] H2[64] H3[32] GZ1[32] GZ2[64] GZ3[32] GZ4[4]
-constexpr int MP_Z = 128;
-constexpr int MP_SCR = MP_Z + 4 + 128 + 128 + 4;
-// saved statistics: mean[128] rstd[128] (layer offsets 0 / 32 / 96)
+constexpr int MAP_NT = 512;
+// scratch per row: Z1[32] Z2[64] Z3[32] (forward, kept for backward) | GY3[32] GY2[64] GY1[32] (backward)
+constexpr int MP_SCR = 256;
+constexpr int GATH = 132;                                      // gather row: up to 2 * 64 + 1 values per CTA
 struct MapArgs {
   const float* c; const float* P; int N; int rpc;
   float temperature; int use_t; float lo, hi;
   float* scratch; float* stats;
   float* rm[3]; float* rv[3]; float momentum; float eps;      // running statistics (NULL: not tracked)
+  long long* nbt[3];                                           // num_batches_tracked of the three BatchNorm layers (NULL: skip)
   float* out;
   const float* gout; float* gc; float* gP;                     // backward
   XchgPeers px;                                                // world > 1: statistics merged over the ranks
 };
+// shared memory of both kernels (floats): work[392] | gather[MAP_CL][GATH] | mean[64] var[64] | W3s[64][33] | W6s[32][65]
+// | rowbuf[MAP_NT / 32][64] | fb[2112]
+constexpr int MAP_SM_WORK = 0, MAP_SM_GATH = 392, MAP_SM_MEAN = MAP_SM_GATH + MAP_CL * GATH, MAP_SM_VAR = MAP_SM_MEAN + 64;
+constexpr int MAP_SM_W3 = MAP_SM_VAR + 64, MAP_SM_W6 = MAP_SM_W3 + 64 * 33, MAP_SM_ROW = MAP_SM_W6 + 32 * 65;
+constexpr int MAP_SM_FB = MAP_SM_ROW + (MAP_NT / 32) * 64, MAP_SM_FLOATS = MAP_SM_FB + 2112;
+
+// exchange of a short vector with the other GPU ranks by cluster CTA 0 (peer_exchange.cuh protocol, bounded wait):
+// returns in xm[0..n) the per-rank vectors' rank-ordered combination computed by `merge`.  A timed-out exchange
+// degrades to this rank's own values (error word set; peer.RangeExchange.check raises).
+template <typename Merge>
+__device__ __forceinline__ void rank_exchange(const XchgPeers& px, const float* mine, int n, float* xm, Merge merge) {
+  __shared__ int step_s;
+  const int tid = threadIdx.x;
+  float* local = px.base[px.rank];
+  if (tid == 0) { int* ep = reinterpret_cast<int*>(local); step_s = *ep + 1; *ep = step_s; }
+  __syncthreads();
+  const int e = step_s;
+  const int slotf = 2 * 128;                                   // slot capacity (floats) of a C = 128 exchange buffer
+  for (int p = 0; p < px.world; ++p) {
+    float* dst = px.base[p] + XCHG_SLOTS + (long long)((e & 1) * px.world + px.rank) * slotf;
+    if (tid < n) dst[tid] = mine[tid];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < px.world) st_release_sys(reinterpret_cast<int*>(px.base[tid]) + XCHG_FLAGS + 8 * (e & 1) + px.rank, e);
+  const bool ok = xchg_wait(local, px.world, e, tid, px.timeout_ns);
+  const bool all_ok = __syncthreads_and(ok);
+  const float* slots = local + XCHG_SLOTS + (long long)((e & 1) * px.world) * slotf;
+  merge(slots, slotf, all_ok, xm);
+  __syncthreads();
+}
 
 // Cluster-wide per-feature statistics of Zl[r][0..F) over ALL rows of the cluster (and of all ranks):
 // two-pass mean / M2 inside a CTA (fixed order), Chan merge over the CTAs in rank order through DSMEM, then over
-// the GPU ranks through peer memory.  Result in sm_mean / sm_var (biased), count in *n_tot.  sm: >= 6*F + 8 floats.
-__device__ void batch_stats(cg::cluster_group& cl, const float* Zl, int ld, int r0, int r1, int F, float* sm,
-                            float* gather /*[MAP_CL][2F+1] in EVERY CTA*/, const XchgPeers& px, float* sm_mean, float* sm_var,
-                            float& n_tot) {
+// the GPU ranks through peer memory.  Result in sm_mean / sm_var (biased), total count returned.
+__device__ float batch_stats(cg::cluster_group& cl, const float* Zl, int ld, int r0, int r1, int F, float* sm,
+                             float* gather, const XchgPeers& px, float* sm_mean, float* sm_var) {
   const int tid = threadIdx.x, NT = blockDim.x;
-  const int SL = NT / F;                                       // row slices per feature
+  const int SL = min(NT / F, 256 / F);                         // row slices per feature (part[] is 256 floats)
   float* part = sm;                                            // [SL][F]
   const int f = tid % F, sl = tid / F;
   const int n = r1 - r0;
-  // pass 1: mean
   float a = 0.f;
-  if (sl < SL) for (int r = r0 + sl; r < r1; r += SL) a = __fadd_rn(a, Zl[(long long)r * ld + f]);
-  if (sl < SL) part[sl * F + f] = a;
-  __syncthreads();
-  float mean = 0.f;
-  if (tid < F) {
-    for (int s_ = 0; s_ < SL; ++s_) mean = __fadd_rn(mean, part[s_ * F + tid]);
-    mean = n > 0 ? __fdiv_rn(mean, (float)n) : 0.f;
-    sm_mean[tid] = mean;
+  if (sl < SL) {
+    for (int r = r0 + sl; r < r1; r += SL) a = __fadd_rn(a, Zl[(long long)r * ld + f]);
+    part[sl * F + f] = a;
   }
   __syncthreads();
-  // pass 2: M2 around the CTA's mean
+  if (tid < F) {
+    float mean = 0.f;
+    for (int s_ = 0; s_ < SL; ++s_) mean = __fadd_rn(mean, part[s_ * F + tid]);
+    sm_mean[tid] = n > 0 ? __fdiv_rn(mean, (float)n) : 0.f;
+  }
+  __syncthreads();
   a = 0.f;
   if (sl < SL) {
     const float m = sm_mean[f];
@@ -269,7 +301,7 @@ __device__ void batch_stats(cg::cluster_group& cl, const float* Zl, int ld, int 
     float m2 = 0.f;
     for (int s_ = 0; s_ < SL; ++s_) m2 = __fadd_rn(m2, part[s_ * F + tid]);
     for (int p = 0; p < ncta; ++p) {                           // all-gather (count, mean, M2) into every CTA
-      float* g = cl.map_shared_rank(gather, p) + rank * (2 * F + 1);
+      float* g = cl.map_shared_rank(gather, p) + rank * GATH;
       g[tid] = sm_mean[tid];
       g[F + tid] = m2;
       if (tid == 0) g[2 * F] = (float)n;
@@ -280,7 +312,7 @@ __device__ void batch_stats(cg::cluster_group& cl, const float* Zl, int ld, int 
   float cnt = 0.f, mu = 0.f, M2 = 0.f;
   if (tid < F) {
     for (int p = 0; p < ncta; ++p) {
-      const float* g = gather + p * (2 * F + 1);
+      const float* g = gather + p * GATH;
       const float nb = g[2 * F];
       if (nb <= 0.f) continue;
       const float d = __fsub_rn(g[tid], mu), tot = __fadd_rn(cnt, nb);
@@ -289,128 +321,82 @@ __device__ void batch_stats(cg::cluster_group& cl, const float* Zl, int ld, int 
       cnt = tot;
     }
   }
-  // GPU ranks: CTA 0 publishes (count, mean, M2), waits for all, every CTA then reads the merged values from
-  // CTA 0's shared memory.  Same protocol / bounded wait as the range exchange (peer_exchange.cuh).
+  float* xv = sm;                                              // [mean F | M2 F | count] of this CTA's merged values
+  float* xm = sm + 192;                                        // CTA 0: merged over the GPU ranks
   if (px.world > 1) {
-    float* xm = sm + 3 * F;                                    // CTA 0: merged [mean F | M2 F | count]
-    if (rank == 0) {
-      __shared__ int step_s;
-      float* local = px.base[px.rank];
-      if (tid == 0) { int* ep = reinterpret_cast<int*>(local); step_s = *ep + 1; *ep = step_s; }
-      __syncthreads();
-      const int e = step_s;
-      const int slotf = 2 * 128;                               // slot capacity (floats) of a C = 128 exchange buffer
-      for (int p = 0; p < px.world; ++p) {
-        float* dst = px.base[p] + XCHG_SLOTS + (long long)((e & 1) * px.world + px.rank) * slotf;
-        if (tid < F) { dst[tid] = mu; dst[F + tid] = M2; }
-        if (tid == 0) dst[2 * F] = cnt;
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (tid < px.world) st_release_sys(reinterpret_cast<int*>(px.base[tid]) + XCHG_FLAGS + 8 * (e & 1) + px.rank, e);
-      const bool ok = xchg_wait(local, px.world, e, tid, px.timeout_ns);
-      const bool all_ok = __syncthreads_and(ok);
-      if (tid < F) {
-        float c2 = 0.f, m_ = 0.f, q_ = 0.f;
-        for (int q = 0; q < px.world; ++q) {
-          // a timed-out exchange degrades to this rank's own statistics (error word set, peer.check raises)
-          const volatile float* s_ = local + XCHG_SLOTS + (long long)((e & 1) * px.world + q) * slotf;
-          const float nb = all_ok ? s_[2 * F] : (q == px.rank ? cnt : 0.f);
-          if (nb <= 0.f) continue;
-          const float mq = all_ok ? s_[tid] : mu, qq = all_ok ? s_[F + tid] : M2;
-          const float d = __fsub_rn(mq, m_), tot = __fadd_rn(c2, nb);
-          m_ = __fadd_rn(m_, __fmul_rn(d, __fdiv_rn(nb, tot)));
-          q_ = __fadd_rn(__fadd_rn(q_, qq), __fmul_rn(__fmul_rn(d, d), __fdiv_rn(__fmul_rn(c2, nb), tot)));
-          c2 = tot;
+    __syncthreads();
+    if (tid < F) { xv[tid] = mu; xv[F + tid] = M2; if (tid == 0) xv[2 * F] = cnt; }
+    __syncthreads();
+    if (rank == 0)
+      rank_exchange(px, xv, 2 * F + 1, xm, [&](const float* slots, int slotf, bool all_ok, float* out) {
+        if (tid < F) {
+          float c2 = 0.f, m_ = 0.f, q_ = 0.f;
+          for (int q = 0; q < px.world; ++q) {
+            const volatile float* s_ = slots + (long long)q * slotf;
+            const float nb = all_ok ? s_[2 * F] : (q == px.rank ? xv[2 * F] : 0.f);
+            if (nb <= 0.f) continue;
+            const float mq = all_ok ? s_[tid] : xv[tid], qq = all_ok ? s_[F + tid] : xv[F + tid];
+            const float d = __fsub_rn(mq, m_), tot = __fadd_rn(c2, nb);
+            m_ = __fadd_rn(m_, __fmul_rn(d, __fdiv_rn(nb, tot)));
+            q_ = __fadd_rn(__fadd_rn(q_, qq), __fmul_rn(__fmul_rn(d, d), __fdiv_rn(__fmul_rn(c2, nb), tot)));
+            c2 = tot;
+          }
+          out[tid] = m_; out[F + tid] = q_;
+          if (tid == 0) out[2 * F] = c2;
         }
-        xm[tid] = m_; xm[F + tid] = q_;
-        if (tid == 0) xm[2 * F] = c2;
-      }
-    }
+      });
     cl.sync();
     if (tid < F) {
-      const float* x0 = cl.map_shared_rank(sm + 3 * F, 0);
+      const float* x0 = cl.map_shared_rank(sm + 192, 0);
       mu = x0[tid]; M2 = x0[F + tid]; cnt = x0[2 * F];
     }
-    cl.sync();                                                 // CTA 0's buffer is free for the next layer
+    cl.sync();                                                 // CTA 0's buffer is free again
   }
   if (tid < F) { sm_mean[tid] = mu; sm_var[tid] = cnt > 0.f ? __fdiv_rn(M2, cnt) : 0.f; }
-  if (tid == 0) sm[6 * F] = cnt;
+  if (tid == 0) sm[391] = cnt;
   __syncthreads();
-  n_tot = sm[6 * F];
+  return sm[391];
 }
 
-// cluster-wide sums of two per-feature quantities (BatchNorm backward: sum gy, sum gy * xhat), ranks included
-__device__ void batch_sums2(cg::cluster_group& cl, const float* A, const float* Bq, int ld, int r0, int r1, int F, float* sm,
-                            float* gather, const XchgPeers& px, float* s1, float* s2) {
-  const int tid = threadIdx.x, NT = blockDim.x;
-  const int SL = NT / (2 * F) > 0 ? NT / (2 * F) : 1;
-  float* part = sm;                                            // [SL][2F]
-  const int q = tid % (2 * F), sl = tid / (2 * F);
-  float a = 0.f;
-  if (sl < SL) {
-    const float* src = q < F ? A : Bq;
-    const int k = q < F ? q : q - F;
-    for (int r = r0 + sl; r < r1; r += SL) a = __fadd_rn(a, src[(long long)r * ld + k]);
-    part[sl * 2 * F + q] = a;
-  }
-  __syncthreads();
+// cluster-wide (and rank-wide) SUM of a CTA-local shared vector v[0..n), n <= GATH: result back in v on every CTA
+__device__ void cluster_sum(cg::cluster_group& cl, float* v, int n, float* sm, float* gather, const XchgPeers& px) {
+  const int tid = threadIdx.x;
   const int rank = (int)cl.block_rank(), ncta = (int)cl.num_blocks();
-  if (tid < 2 * F) {
-    float t = 0.f;
-    for (int s_ = 0; s_ < SL; ++s_) t = __fadd_rn(t, part[s_ * 2 * F + tid]);
-    for (int p = 0; p < ncta; ++p) cl.map_shared_rank(gather, p)[rank * (2 * F + 1) + tid] = t;
-  }
+  __syncthreads();
+  if (tid < n)
+    for (int p = 0; p < ncta; ++p) cl.map_shared_rank(gather, p)[rank * GATH + tid] = v[tid];
   cl.sync();
   float tot = 0.f;
-  if (tid < 2 * F)
-    for (int p = 0; p < ncta; ++p) tot = __fadd_rn(tot, gather[p * (2 * F + 1) + tid]);
+  if (tid < n)
+    for (int p = 0; p < ncta; ++p) tot = __fadd_rn(tot, gather[p * GATH + tid]);
   if (px.world > 1) {
-    float* xm = sm + 3 * F;
-    if (rank == 0) {
-      __shared__ int step_b;
-      float* local = px.base[px.rank];
-      if (tid == 0) { int* ep = reinterpret_cast<int*>(local); step_b = *ep + 1; *ep = step_b; }
-      __syncthreads();
-      const int e = step_b;
-      const int slotf = 2 * 128;
-      for (int p = 0; p < px.world; ++p) {
-        float* dst = px.base[p] + XCHG_SLOTS + (long long)((e & 1) * px.world + px.rank) * slotf;
-        if (tid < 2 * F) dst[tid] = tot;
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (tid < px.world) st_release_sys(reinterpret_cast<int*>(px.base[tid]) + XCHG_FLAGS + 8 * (e & 1) + px.rank, e);
-      const bool ok = xchg_wait(local, px.world, e, tid, px.timeout_ns);
-      const bool all_ok = __syncthreads_and(ok);
-      if (tid < 2 * F) {
-        float t = 0.f;
-        for (int w = 0; w < px.world; ++w) {
-          const volatile float* s_ = local + XCHG_SLOTS + (long long)((e & 1) * px.world + w) * slotf;
-          t = __fadd_rn(t, all_ok ? s_[tid] : (w == px.rank ? tot : 0.f));
+    float* xv = sm;
+    float* xm = sm + 192;
+    if (tid < n) xv[tid] = tot;
+    __syncthreads();
+    if (rank == 0)
+      rank_exchange(px, xv, n, xm, [&](const float* slots, int slotf, bool all_ok, float* out) {
+        if (tid < n) {
+          float t = 0.f;
+          for (int q = 0; q < px.world; ++q) {
+            const volatile float* s_ = slots + (long long)q * slotf;
+            t = __fadd_rn(t, all_ok ? s_[tid] : (q == px.rank ? xv[tid] : 0.f));
+          }
+          out[tid] = t;
         }
-        xm[tid] = t;
-      }
-    }
+      });
     cl.sync();
-    if (tid < 2 * F) tot = cl.map_shared_rank(sm + 3 * F, 0)[tid];
+    if (tid < n) tot = cl.map_shared_rank(sm + 192, 0)[tid];
     cl.sync();
   }
-  if (tid < F) s1[tid] = tot;
-  else if (tid < 2 * F) s2[tid - F] = tot;
+  if (tid < n) v[tid] = tot;
   __syncthreads();
 }
 
-// BN (train) + ReLU of a stored pre-activation row
-template <int F>
-__device__ __forceinline__ void bn_relu_row(const float* __restrict__ z, const float* mean, const float* var, float eps,
-                                            const float* __restrict__ g, const float* __restrict__ b, float (&h)[F]) {
-#pragma unroll
-  for (int k = 0; k < F; ++k) {
-    const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[k], eps)));
-    h[k] = fmaxf(fmaf(__fmul_rn(__fsub_rn(z[k], mean[k]), rstd), __ldg(g + k), __ldg(b + k)), 0.f);
-  }
+__device__ __forceinline__ float bn_relu1(float z, float mean, float rstd, float g, float b) {
+  return fmaxf(fmaf(__fmul_rn(__fsub_rn(z, mean), rstd), g, b), 0.f);
 }
+__device__ __forceinline__ float rstd_of(float var, float eps) { return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps))); }
 
 __device__ __forceinline__ void update_running(float* rm, float* rv, const float* mean, const float* var, float n, int F,
                                                float momentum) {
@@ -422,76 +408,97 @@ __device__ __forceinline__ void update_running(float* rm, float* rv, const float
 }
 
 __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs A) {
-  extern __shared__ float sm[];                                // work [6*64+8] | gather [MAP_CL][2*64+1] | mean[64] var[64]
+  extern __shared__ float sm[];
   cg::cluster_group cl = cg::this_cluster();
-  float* gather = sm + 6 * 64 + 8;
-  float* mean = gather + MAP_CL * (2 * 64 + 1);
-  float* var = mean + 64;
+  float* gather = sm + MAP_SM_GATH;
+  float* mean = sm + MAP_SM_MEAN;
+  float* var = sm + MAP_SM_VAR;
+  float* W3s = sm + MAP_SM_W3;
+  float* W6s = sm + MAP_SM_W6;
   const float* P = A.P;
   const float* W0 = P; const float* b0 = P + 96; const float* g0 = P + 128; const float* be0 = P + 160;
   const float* W3 = P + 192; const float* b3 = P + 2240; const float* g3 = P + 2304; const float* be3 = P + 2368;
   const float* W6 = P + 2432; const float* b6 = P + 4480; const float* g6 = P + 4512; const float* be6 = P + 4544;
   const float* W9 = P + 4576; const float* b9 = P + 4608;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = MAP_NT / 32;
+  float* rb = sm + MAP_SM_ROW + warp * 64;
   const int rank = (int)cl.block_rank();
   const int r0 = min(rank * A.rpc, A.N), r1 = min(r0 + A.rpc, A.N);
-  float ntot;
-  // layer 1
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-    const float c = fminf(fmaxf(A.c[r], 0.f), 1.f);
-    float f[3] = {c, __fmul_rn(c, c), log1p_f64(c)}, z[32];
-    dense_fwd<3, 32>(W0, b0, f, z);
-    float* s = A.scratch + (long long)r * MP_SCR;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) s[k] = z[k];
+  stage_matrix(W3, W3s, 64, 32);
+  stage_matrix(W6, W6s, 32, 64);
+  // layer 1: unit = lane
+  {
+    const float w0 = __ldg(W0 + lane * 3), w1 = __ldg(W0 + lane * 3 + 1), w2 = __ldg(W0 + lane * 3 + 2), bb = __ldg(b0 + lane);
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+      const float c = fminf(fmaxf(__ldg(A.c + r), 0.f), 1.f);
+      float a = 0.f;
+      a = fmaf(w0, c, a); a = fmaf(w1, __fmul_rn(c, c), a); a = fmaf(w2, log1p_f64(c), a);
+      A.scratch[(long long)r * MP_SCR + lane] = __fadd_rn(a, bb);
+    }
   }
   __syncthreads();
-  batch_stats(cl, A.scratch, MP_SCR, r0, r1, 32, sm, gather, A.px, mean, var, ntot);
+  float ntot = batch_stats(cl, A.scratch, MP_SCR, r0, r1, 32, sm, gather, A.px, mean, var);
   if (rank == 0) {
     update_running(A.rm[0], A.rv[0], mean, var, ntot, 32, A.momentum);
+    if (threadIdx.x < 3 && A.nbt[threadIdx.x]) *A.nbt[threadIdx.x] += 1;
     if (threadIdx.x < 32) { A.stats[threadIdx.x] = mean[threadIdx.x]; A.stats[128 + threadIdx.x] = var[threadIdx.x]; }
   }
-  // layer 2
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-    float* s = A.scratch + (long long)r * MP_SCR;
-    float h[32], z[64];
-    bn_relu_row<32>(s, mean, var, A.eps, g0, be0, h);
-    dense_fwd<32, 64>(W3, b3, h, z);
-#pragma unroll
-    for (int k = 0; k < 64; ++k) s[32 + k] = z[k];
+  // layer 2: units lane, lane + 32
+  {
+    const float mu = mean[lane], rs = rstd_of(var[lane], A.eps), gg = __ldg(g0 + lane), ee = __ldg(be0 + lane);
+    const float ba = __ldg(b3 + lane), bb = __ldg(b3 + lane + 32);
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+      float* s = A.scratch + (long long)r * MP_SCR;
+      __syncwarp();
+      rb[lane] = bn_relu1(s[lane], mu, rs, gg, ee);
+      __syncwarp();
+      float za = 0.f, zb = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) { const float h = rb[k]; za = fmaf(W3s[lane * 33 + k], h, za); zb = fmaf(W3s[(lane + 32) * 33 + k], h, zb); }
+      s[32 + lane] = __fadd_rn(za, ba);
+      s[64 + lane] = __fadd_rn(zb, bb);
+    }
   }
   __syncthreads();
-  batch_stats(cl, A.scratch + 32, MP_SCR, r0, r1, 64, sm, gather, A.px, mean, var, ntot);
+  ntot = batch_stats(cl, A.scratch + 32, MP_SCR, r0, r1, 64, sm, gather, A.px, mean, var);
   if (rank == 0) {
     update_running(A.rm[1], A.rv[1], mean, var, ntot, 64, A.momentum);
     if (threadIdx.x < 64) { A.stats[32 + threadIdx.x] = mean[threadIdx.x]; A.stats[160 + threadIdx.x] = var[threadIdx.x]; }
   }
-  // layer 3
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-    float* s = A.scratch + (long long)r * MP_SCR;
-    float h[64], z[32];
-    bn_relu_row<64>(s + 32, mean, var, A.eps, g3, be3, h);
-    dense_fwd<64, 32>(W6, b6, h, z);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) s[96 + k] = z[k];
+  // layer 3: unit = lane
+  {
+    const float mua = mean[lane], rsa = rstd_of(var[lane], A.eps), ga = __ldg(g3 + lane), ea = __ldg(be3 + lane);
+    const float mub = mean[lane + 32], rsb = rstd_of(var[lane + 32], A.eps), gb = __ldg(g3 + lane + 32), eb = __ldg(be3 + lane + 32);
+    const float bb = __ldg(b6 + lane);
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+      float* s = A.scratch + (long long)r * MP_SCR;
+      __syncwarp();
+      rb[lane] = bn_relu1(s[32 + lane], mua, rsa, ga, ea);
+      rb[lane + 32] = bn_relu1(s[64 + lane], mub, rsb, gb, eb);
+      __syncwarp();
+      float z = 0.f;
+#pragma unroll 16
+      for (int k = 0; k < 64; ++k) z = fmaf(W6s[lane * 65 + k], rb[k], z);
+      s[96 + lane] = __fadd_rn(z, bb);
+    }
   }
   __syncthreads();
-  batch_stats(cl, A.scratch + 96, MP_SCR, r0, r1, 32, sm, gather, A.px, mean, var, ntot);
+  ntot = batch_stats(cl, A.scratch + 96, MP_SCR, r0, r1, 32, sm, gather, A.px, mean, var);
   if (rank == 0) {
     update_running(A.rm[2], A.rv[2], mean, var, ntot, 32, A.momentum);
     if (threadIdx.x < 32) { A.stats[96 + threadIdx.x] = mean[threadIdx.x]; A.stats[224 + threadIdx.x] = var[threadIdx.x]; }
   }
   // head: 32 -> 1, sigmoid, Eq.17, temperature, straight-through clamp (bit_allocation.py:258-273)
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-    const float* s = A.scratch + (long long)r * MP_SCR;
-    float h[32];
-    bn_relu_row<32>(s + 96, mean, var, A.eps, g6, be6, h);
-    float z = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) z = fmaf(__ldg(W9 + k), h[k], z);
-    const float sg = sigmoid_exact(__fadd_rn(z, __ldg(b9)));
-    float bits = __fadd_rn(A.lo, __fmul_rn(__fsub_rn(A.hi, A.lo), sg));
-    if (A.use_t) bits = __fmul_rn(bits, A.temperature);
-    A.out[r] = fminf(fmaxf(bits, A.lo), A.hi);                 // value of bits + (clamp(bits) - bits).detach()
+  {
+    const float mu = mean[lane], rs = rstd_of(var[lane], A.eps), gg = __ldg(g6 + lane), ee = __ldg(be6 + lane);
+    const float w9 = __ldg(W9 + lane), bb = __ldg(b9);
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+      const float h = bn_relu1(A.scratch[(long long)r * MP_SCR + 96 + lane], mu, rs, gg, ee);
+      const float sg = sigmoid_exact(__fadd_rn(wsum(__fmul_rn(w9, h)), bb));
+      float bits = __fadd_rn(A.lo, __fmul_rn(__fsub_rn(A.hi, A.lo), sg));
+      if (A.use_t) bits = __fmul_rn(bits, A.temperature);
+      if (lane == 0) A.out[r] = fminf(fmaxf(bits, A.lo), A.hi);   // value of bits + (clamp(bits) - bits).detach()
+    }
   }
   cl.sync();                                                   // nobody leaves while a peer may still read its gather area
 }
@@ -499,9 +506,11 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs 
 __global__ void __launch_bounds__(MAP_NT) mapper_train_bwd_kernel(const MapArgs A) {
   extern __shared__ float sm[];
   cg::cluster_group cl = cg::this_cluster();
-  float* gather = sm + 6 * 64 + 8;
-  float* s1 = gather + MAP_CL * (2 * 64 + 1);
-  float* s2 = s1 + 64;
+  float* gather = sm + MAP_SM_GATH;
+  float* sv = sm + MAP_SM_MEAN;                                // [s1 64 | s2 64]: BatchNorm backward sums (+ count at [128]... see below)
+  float* W3s = sm + MAP_SM_W3;
+  float* W6s = sm + MAP_SM_W6;
+  float* fb = sm + MAP_SM_FB;
   const float* P = A.P;
   const float* W0 = P; const float* g0 = P + 128; const float* be0 = P + 160;
   const float* W3 = P + 192; const float* g3 = P + 2304; const float* be3 = P + 2368;
@@ -509,142 +518,187 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_bwd_kernel(const MapArgs 
   const float* W9 = P + 4576; const float* b9 = P + 4608;
   const float* mean = A.stats; const float* var = A.stats + 128;
   float* gP = A.gP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = MAP_NT / 32;
+  float* rb = sm + MAP_SM_ROW + warp * 64;
   const int rank = (int)cl.block_rank();
   const int r0 = min(rank * A.rpc, A.N), r1 = min(r0 + A.rpc, A.N);
-  // total row count (all CTAs / ranks): the BN backward divides by it; counts travel with batch_sums2 as a feature
-  // scratch columns (per row): 128 F[4] | 132 H1[32] | 164 H2[64] | 228 H3[32] | 260 GZ1[32] | 292 GZ2[64] | 356 GZ3[32] | 388 GZ4
-  // ---- head + BN3: gy3 and gy3 * xhat3 into GZ3 / H3 columns temporarily --------------------------------------
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-    float* s = A.scratch + (long long)r * MP_SCR;
-    float h[32];
-    bn_relu_row<32>(s + 96, mean + 96, var + 96, A.eps, g6, be6, h);
-    float z = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) z = fmaf(__ldg(W9 + k), h[k], z);
-    const float sg = sigmoid_exact(__fadd_rn(z, __ldg(b9)));
-    float g = __fmul_rn(A.gout[r], __fmul_rn(__fsub_rn(A.hi, A.lo), __fmul_rn(sg, __fsub_rn(1.f, sg))));
-    if (A.use_t) g = __fmul_rn(g, A.temperature);
-    s[388] = g;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      s[228 + k] = h[k];
-      const float gy = h[k] > 0.f ? __fmul_rn(g, __ldg(W9 + k)) : 0.f;
-      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[96 + k], A.eps)));
-      const float xh = __fmul_rn(__fsub_rn(s[96 + k], mean[96 + k]), rstd);
-      s[356 + k] = gy;                                         // gy3
-      s[132 + k] = __fmul_rn(gy, xh);                          // gy3 * xhat3 (H1 columns are free until layer 1)
-    }
-    s[389] = 1.0f;                                             // row counter
-  }
-  __syncthreads();
-  wgrad_rows(A.scratch + 388, MP_SCR, A.scratch + 228, MP_SCR, r0, r1, 32, 1, gP + 4576, gP + 4608);   // W9, b9
-  batch_sums2(cl, A.scratch + 356, A.scratch + 132, MP_SCR, r0, r1, 32, sm, gather, A.px, s1, s2);
-  colsum_rows(A.scratch + 132, A.scratch + 356, MP_SCR, r0, r1, 32, gP + 4512, gP + 4544);              // g6, be6 (local rows)
-  // global row count: sum of the counter column
-  float* cnt_s = sm + 6 * 64;                                  // survives batch_sums2's scratch use (part < 6*64)
+  stage_matrix(W3, W3s, 64, 32);
+  stage_matrix(W6, W6s, 32, 64);
+  // ---- head + BN3 sums (units = lane) ----------------------------------------------------------------------
+  const float mu3 = __ldg(mean + 96 + lane), rs3 = rstd_of(__ldg(var + 96 + lane), A.eps), g6l = __ldg(g6 + lane), e6l = __ldg(be6 + lane);
   {
-    float* c1 = s1 + 32;                                       // s1[32..63], s2[32..63] unused at F = 32
-    batch_sums2(cl, A.scratch + 389, A.scratch + 389, MP_SCR, r0, r1, 1, sm, gather, A.px, c1, c1 + 1);
-    if (threadIdx.x == 0) cnt_s[0] = c1[0];
+    const float w9 = __ldg(W9 + lane), bb = __ldg(b9);
+    float dW9 = 0.f, db9 = 0.f, s1 = 0.f, s2 = 0.f;
+    flush_begin(fb, 130);                                      // [dW9 32 | db9 | pad | s1 32 | s2 32 | count]
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+      float* s = A.scratch + (long long)r * MP_SCR;
+      const float z3 = s[96 + lane];
+      const float h = bn_relu1(z3, mu3, rs3, g6l, e6l);
+      const float sg = sigmoid_exact(__fadd_rn(wsum(__fmul_rn(w9, h)), bb));
+      float g = __fmul_rn(__ldg(A.gout + r), __fmul_rn(__fsub_rn(A.hi, A.lo), __fmul_rn(sg, __fsub_rn(1.f, sg))));
+      if (A.use_t) g = __fmul_rn(g, A.temperature);
+      dW9 = fmaf(g, h, dW9);
+      db9 = __fadd_rn(db9, g);
+      const float gy = h > 0.f ? __fmul_rn(g, w9) : 0.f;
+      s[128 + lane] = gy;
+      s1 = __fadd_rn(s1, gy);
+      s2 = fmaf(gy, __fmul_rn(__fsub_rn(z3, mu3), rs3), s2);
+    }
+    atomicAdd(fb + lane, dW9);
+    if (lane == 0) atomicAdd(fb + 32, db9);
+    atomicAdd(fb + 34 + lane, s1);
+    atomicAdd(fb + 66 + lane, s2);
     __syncthreads();
-  }
-  const float ninv = __fdiv_rn(1.0f, cnt_s[0]);
-  __syncthreads();
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {   // gz3, then layer-3 data gradient -> gy2
-    float* s = A.scratch + (long long)r * MP_SCR;
-    float gz[32], gh[64], h2[64];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[96 + k], A.eps)));
-      const float xh = __fmul_rn(__fsub_rn(s[96 + k], mean[96 + k]), rstd);
-      gz[k] = __fmul_rn(__fmul_rn(__ldg(g6 + k), rstd),
-                        __fsub_rn(__fsub_rn(s[356 + k], __fmul_rn(s1[k], ninv)), __fmul_rn(xh, __fmul_rn(s2[k], ninv))));
-      s[356 + k] = gz[k];
+    if (threadIdx.x < 33 && fb[threadIdx.x] != 0.f) atomicAdd(gP + 4576 + threadIdx.x, fb[threadIdx.x]);      // W9, b9
+    if (threadIdx.x < 32) {                                                                                      // be6, g6: local rows
+      atomicAdd(gP + 4544 + threadIdx.x, fb[34 + threadIdx.x]);
+      atomicAdd(gP + 4512 + threadIdx.x, fb[66 + threadIdx.x]);
+      sv[threadIdx.x] = fb[34 + threadIdx.x];
+      sv[32 + threadIdx.x] = fb[66 + threadIdx.x];
     }
-    dense_bwd_data<64, 32>(W6, gz, gh);
-    bn_relu_row<64>(s + 32, mean + 32, var + 32, A.eps, g3, be3, h2);
-#pragma unroll
-    for (int k = 0; k < 64; ++k) {
-      s[164 + k] = h2[k];
-      const float gy = h2[k] > 0.f ? gh[k] : 0.f;
-      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[32 + k], A.eps)));
-      const float xh = __fmul_rn(__fsub_rn(s[32 + k], mean[32 + k]), rstd);
-      s[292 + k] = gy;                                         // gy2
-      gh[k] = __fmul_rn(gy, xh);
-    }
-    // gy2 * xhat2 parked in the Z3 columns?  no: Z3 is still needed by nobody after gz3 -> reuse 96..127 + 228.. is H3
-    // (64 values: first 32 into the dead Z3 columns, last 32 into the dead "gy3 * xhat3" columns 132..163)
-#pragma unroll
-    for (int k = 0; k < 32; ++k) { s[96 + k] = gh[k]; s[132 + k] = gh[32 + k]; }
+    if (threadIdx.x == 0) sv[64] = (float)(r1 - r0);          // the global row count travels with the first reduction
+    cluster_sum(cl, sv, 65, sm, gather, A.px);
   }
+  const float ninv = __fdiv_rn(1.0f, sv[64]);
   __syncthreads();
-  wgrad_rows(A.scratch + 356, MP_SCR, A.scratch + 164, MP_SCR, r0, r1, 64, 32, gP + 2432, gP + 4480);   // W6, b6
-  // BN2 sums over 64 features: gy2 at 292..355; gy2 * xhat2 split over two column groups -> two calls of 32
-  batch_sums2(cl, A.scratch + 292, A.scratch + 96, MP_SCR, r0, r1, 32, sm, gather, A.px, s1, s2);
-  colsum_rows(A.scratch + 96, A.scratch + 292, MP_SCR, r0, r1, 32, gP + 2304, gP + 2368);
+  // ---- layer 3 backward (W6: 32 x 64) + BN2 sums (units lane, lane + 32) -----------------------------------------
+  const float mu2a = __ldg(mean + 32 + lane), rs2a = rstd_of(__ldg(var + 32 + lane), A.eps), g3a = __ldg(g3 + lane), e3a = __ldg(be3 + lane);
+  const float mu2b = __ldg(mean + 64 + lane), rs2b = rstd_of(__ldg(var + 64 + lane), A.eps), g3b = __ldg(g3 + lane + 32), e3b = __ldg(be3 + lane + 32);
   {
-    float* s1b = s1 + 32;
-    float* s2b = s2 + 32;
-    batch_sums2(cl, A.scratch + 324, A.scratch + 132, MP_SCR, r0, r1, 32, sm, gather, A.px, s1b, s2b);
-    colsum_rows(A.scratch + 132, A.scratch + 324, MP_SCR, r0, r1, 32, gP + 2304 + 32, gP + 2368 + 32);
-  }
-  __syncthreads();                                             // column sums done before the columns are rewritten
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {   // gz2, layer-2 data gradient -> gy1
-    float* s = A.scratch + (long long)r * MP_SCR;
-    float gz[64], gh[32], h1[32];
+    const float c1 = __fmul_rn(sv[lane], ninv), c2 = __fmul_rn(sv[32 + lane], ninv);
+    __syncthreads();
+    float dW[64];
 #pragma unroll
-    for (int k = 0; k < 64; ++k) {
-      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[32 + k], A.eps)));
-      const float xh = __fmul_rn(__fsub_rn(s[32 + k], mean[32 + k]), rstd);
-      gz[k] = __fmul_rn(__fmul_rn(__ldg(g3 + k), rstd),
-                        __fsub_rn(__fsub_rn(s[292 + k], __fmul_rn(s1[k], ninv)), __fmul_rn(xh, __fmul_rn(s2[k], ninv))));
-      s[292 + k] = gz[k];
-    }
-    dense_bwd_data<32, 64>(W3, gz, gh);
-    bn_relu_row<32>(s, mean, var, A.eps, g0, be0, h1);
+    for (int k = 0; k < 64; ++k) dW[k] = 0.f;
+    float db = 0.f, s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+    flush_begin(fb, 2048 + 32);
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+      float* s = A.scratch + (long long)r * MP_SCR;
+      const float xh3 = __fmul_rn(__fsub_rn(s[96 + lane], mu3), rs3);
+      const float gz = __fmul_rn(__fmul_rn(g6l, rs3), __fsub_rn(__fsub_rn(s[128 + lane], c1), __fmul_rn(xh3, c2)));
+      const float z2a = s[32 + lane], z2b = s[64 + lane];
+      const float ha = bn_relu1(z2a, mu2a, rs2a, g3a, e3a), hb = bn_relu1(z2b, mu2b, rs2b, g3b, e3b);
+      __syncwarp();
+      rb[lane] = ha; rb[lane + 32] = hb;
+      __syncwarp();
+      db = __fadd_rn(db, gz);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      s[132 + k] = h1[k];
-      const float gy = h1[k] > 0.f ? gh[k] : 0.f;
-      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[k], A.eps)));
-      const float xh = __fmul_rn(__fsub_rn(s[k], mean[k]), rstd);
-      s[260 + k] = gy;                                         // gy1
-      s[96 + k] = __fmul_rn(gy, xh);                           // gy1 * xhat1
+      for (int k = 0; k < 64; ++k) dW[k] = fmaf(gz, rb[k], dW[k]);
+      float gha = 0.f, ghb = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const float gj = __shfl_sync(0xffffffffu, gz, j);
+        gha = fmaf(W6s[j * 65 + lane], gj, gha);
+        ghb = fmaf(W6s[j * 65 + lane + 32], gj, ghb);
+      }
+      const float gya = ha > 0.f ? gha : 0.f, gyb = hb > 0.f ? ghb : 0.f;
+      s[160 + lane] = gya; s[192 + lane] = gyb;
+      s1a = __fadd_rn(s1a, gya); s1b = __fadd_rn(s1b, gyb);
+      s2a = fmaf(gya, __fmul_rn(__fsub_rn(z2a, mu2a), rs2a), s2a);
+      s2b = fmaf(gyb, __fmul_rn(__fsub_rn(z2b, mu2b), rs2b), s2b);
     }
-  }
-  __syncthreads();
-  wgrad_rows(A.scratch + 292, MP_SCR, A.scratch + 132, MP_SCR, r0, r1, 32, 64, gP + 192, gP + 2240);    // W3, b3
-  batch_sums2(cl, A.scratch + 260, A.scratch + 96, MP_SCR, r0, r1, 32, sm, gather, A.px, s1, s2);
-  colsum_rows(A.scratch + 96, A.scratch + 260, MP_SCR, r0, r1, 32, gP + 128, gP + 160);
-  __syncthreads();
-  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {   // gz1, input gradient
-    float* s = A.scratch + (long long)r * MP_SCR;
-    float gz[32], gf[3];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[k], A.eps)));
-      const float xh = __fmul_rn(__fsub_rn(s[k], mean[k]), rstd);
-      gz[k] = __fmul_rn(__fmul_rn(__ldg(g0 + k), rstd),
-                        __fsub_rn(__fsub_rn(s[260 + k], __fmul_rn(s1[k], ninv)), __fmul_rn(xh, __fmul_rn(s2[k], ninv))));
-      s[260 + k] = gz[k];
+    for (int k = 0; k < 64; ++k) atomicAdd(fb + k * 32 + lane, dW[k]);      // [k][unit]: conflict-free across lanes
+    atomicAdd(fb + 2048 + lane, db);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += MAP_NT) atomicAdd(gP + 2432 + (i & 31) * 64 + (i >> 5), fb[i]);   // W6[unit][k]
+    if (threadIdx.x < 32) atomicAdd(gP + 4480 + threadIdx.x, fb[2048 + threadIdx.x]);                           // b6
+    __syncthreads();
+    flush_begin(fb, 128);
+    atomicAdd(fb + lane, s1a); atomicAdd(fb + 32 + lane, s1b); atomicAdd(fb + 64 + lane, s2a); atomicAdd(fb + 96 + lane, s2b);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      atomicAdd(gP + 2368 + threadIdx.x, fb[threadIdx.x]);                                                       // be3
+      atomicAdd(gP + 2304 + threadIdx.x, fb[64 + threadIdx.x]);                                                  // g3
     }
-    dense_bwd_data<3, 32>(W0, gz, gf);
-    const float craw = A.c[r];
-    const float c = fminf(fmaxf(craw, 0.f), 1.f);
-    s[128] = c; s[129] = __fmul_rn(c, c); s[130] = log1p_f64(c);
-    // d/dc [c, c^2, log1p c] and the clamp's pass-through inside [0, 1]
-    const float g = __fadd_rn(__fadd_rn(gf[0], __fmul_rn(gf[1], __fmul_rn(2.f, c))), __fdiv_rn(gf[2], __fadd_rn(1.f, c)));
-    if (A.gc) A.gc[r] = (craw >= 0.f && craw <= 1.f) ? g : 0.f;
+    if (threadIdx.x < 128) sv[threadIdx.x] = fb[threadIdx.x];
+    cluster_sum(cl, sv, 128, sm, gather, A.px);
   }
-  __syncthreads();
-  wgrad_rows(A.scratch + 260, MP_SCR, A.scratch + 128, MP_SCR, r0, r1, 3, 32, gP, gP + 96);             // W0, b0
+  // ---- layer 2 backward (W3: 64 x 32) + BN1 sums (unit lane) ------------------------------------------------------
+  const float mu1 = __ldg(mean + lane), rs1 = rstd_of(__ldg(var + lane), A.eps), g0l = __ldg(g0 + lane), e0l = __ldg(be0 + lane);
+  {
+    const float c1a = __fmul_rn(sv[lane], ninv), c1b = __fmul_rn(sv[32 + lane], ninv);
+    const float c2a = __fmul_rn(sv[64 + lane], ninv), c2b = __fmul_rn(sv[96 + lane], ninv);
+    __syncthreads();
+    float dWa[32], dWb[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { dWa[k] = 0.f; dWb[k] = 0.f; }
+    float dba = 0.f, dbb = 0.f, s1 = 0.f, s2 = 0.f;
+    flush_begin(fb, 2048 + 64);
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+      float* s = A.scratch + (long long)r * MP_SCR;
+      const float xa = __fmul_rn(__fsub_rn(s[32 + lane], mu2a), rs2a), xb = __fmul_rn(__fsub_rn(s[64 + lane], mu2b), rs2b);
+      const float gza = __fmul_rn(__fmul_rn(g3a, rs2a), __fsub_rn(__fsub_rn(s[160 + lane], c1a), __fmul_rn(xa, c2a)));
+      const float gzb = __fmul_rn(__fmul_rn(g3b, rs2b), __fsub_rn(__fsub_rn(s[192 + lane], c1b), __fmul_rn(xb, c2b)));
+      const float z1 = s[lane];
+      const float h1 = bn_relu1(z1, mu1, rs1, g0l, e0l);
+      __syncwarp();
+      rb[lane] = h1;
+      __syncwarp();
+      dba = __fadd_rn(dba, gza); dbb = __fadd_rn(dbb, gzb);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) { const float h = rb[k]; dWa[k] = fmaf(gza, h, dWa[k]); dWb[k] = fmaf(gzb, h, dWb[k]); }
+      float gh = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        gh = fmaf(W3s[j * 33 + lane], __shfl_sync(0xffffffffu, gza, j), gh);
+        gh = fmaf(W3s[(j + 32) * 33 + lane], __shfl_sync(0xffffffffu, gzb, j), gh);
+      }
+      const float gy = h1 > 0.f ? gh : 0.f;
+      s[224 + lane] = gy;
+      s1 = __fadd_rn(s1, gy);
+      s2 = fmaf(gy, __fmul_rn(__fsub_rn(z1, mu1), rs1), s2);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { atomicAdd(fb + k * 64 + lane, dWa[k]); atomicAdd(fb + k * 64 + 32 + lane, dWb[k]); }   // [k][unit]
+    atomicAdd(fb + 2048 + lane, dba); atomicAdd(fb + 2048 + 32 + lane, dbb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += MAP_NT) atomicAdd(gP + 192 + (i & 63) * 32 + (i >> 6), fb[i]);    // W3[unit][k]
+    if (threadIdx.x < 64) atomicAdd(gP + 2240 + threadIdx.x, fb[2048 + threadIdx.x]);                           // b3
+    __syncthreads();
+    flush_begin(fb, 64);
+    atomicAdd(fb + lane, s1); atomicAdd(fb + 32 + lane, s2);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      atomicAdd(gP + 160 + threadIdx.x, fb[threadIdx.x]);                                                        // be0
+      atomicAdd(gP + 128 + threadIdx.x, fb[32 + threadIdx.x]);                                                   // g0
+    }
+    if (threadIdx.x < 64) sv[threadIdx.x] = fb[threadIdx.x];
+    cluster_sum(cl, sv, 64, sm, gather, A.px);
+  }
+  // ---- layer 1 backward (W0: 32 x 3) and the input gradient ------------------------------------------------------------
+  {
+    const float c1 = __fmul_rn(sv[lane], ninv), c2 = __fmul_rn(sv[32 + lane], ninv);
+    const float w0 = __ldg(W0 + lane * 3), w1 = __ldg(W0 + lane * 3 + 1), w2 = __ldg(W0 + lane * 3 + 2);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, dbv = 0.f;
+    __syncthreads();
+    flush_begin(fb, 128);
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+      const float* s = A.scratch + (long long)r * MP_SCR;
+      const float xh = __fmul_rn(__fsub_rn(s[lane], mu1), rs1);
+      const float gz = __fmul_rn(__fmul_rn(g0l, rs1), __fsub_rn(__fsub_rn(s[224 + lane], c1), __fmul_rn(xh, c2)));
+      const float craw = __ldg(A.c + r);
+      const float c = fminf(fmaxf(craw, 0.f), 1.f);
+      const float f1 = __fmul_rn(c, c), f2 = log1p_f64(c);
+      d0 = fmaf(gz, c, d0); d1 = fmaf(gz, f1, d1); d2 = fmaf(gz, f2, d2);
+      dbv = __fadd_rn(dbv, gz);
+      const float gf0 = wsum(__fmul_rn(w0, gz)), gf1 = wsum(__fmul_rn(w1, gz)), gf2 = wsum(__fmul_rn(w2, gz));
+      // d/dc [c, c^2, log1p c] and the clamp's pass-through inside [0, 1]
+      const float g = __fadd_rn(__fadd_rn(gf0, __fmul_rn(gf1, __fmul_rn(2.f, c))), __fdiv_rn(gf2, __fadd_rn(1.f, c)));
+      if (A.gc && lane == 0) A.gc[r] = (craw >= 0.f && craw <= 1.f) ? g : 0.f;
+    }
+    atomicAdd(fb + lane * 3, d0); atomicAdd(fb + lane * 3 + 1, d1); atomicAdd(fb + lane * 3 + 2, d2);
+    atomicAdd(fb + 96 + lane, dbv);
+    flush_end(fb, 128, gP);                                                                                     // W0, b0
+  }
   cl.sync();
 }
 
 // =================================================================================================
 // soft mask: backward of m = smooth5x5(nearest_up(softmax(net([bits_norm, act]))[0]))  (quantization.py:213-239)
 // =================================================================================================
-// one CTA per image.  smem: dmt[nt] | gin[nt] | gw[170]
+// one CTA per image.  smem: dmt[nt] | rec[nt][36]: gl, hid[8], gh[8], in[2][9] (+1 pad)
+constexpr int SM_REC = 36;
 __global__ void __launch_bounds__(256)
 softmask_bwd_kernel(const float* __restrict__ dm, const float* __restrict__ bit_map, const float* __restrict__ act_n,
                     const float* __restrict__ P, int H, int W, int Ht, int Wt, float* __restrict__ dbit,
@@ -652,44 +706,67 @@ softmask_bwd_kernel(const float* __restrict__ dm, const float* __restrict__ bit_
   extern __shared__ float sm[];
   const int nt = Ht * Wt, b = blockIdx.x;
   float* dmt = sm;
-  float* gin = dmt + nt;
-  float* gw = gin + nt;
+  float* rec = dmt + nt;
   const float* W0 = P; const float* b0 = P + 144; const float* W2 = P + 152; const float* b2 = P + 168; const float* ks = P + 170;
-  for (int i = threadIdx.x; i < 2 * nt + 170; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  // (1) smoothing (replicate padding) + nearest upsampling, transposed: pixel gradients scattered to tiles
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // (1) smoothing (replicate padding) + nearest upsampling, transposed -- as a GATHER per tile: a warp sums, over the
+  //     pixels whose 5x5 window can reach the tile, the pixel gradient times the weight of the taps that land in it
   const float sy = (float)Ht / (float)H, sx = (float)Wt / (float)W;
   const float* g = dm + (long long)b * H * W;
-  for (int p = threadIdx.x; p < H * W; p += blockDim.x) {
-    const int h = p / W, w = p - h * W;
-    const float gp = g[p];
-    if (gp == 0.f) continue;
+  for (int t = warp; t < nt; t += nwarps) {
+    const int ny = t / Wt, nx = t - ny * Wt;
+    // pixel range of the tile under the nearest rule: [hs, he) x [ws, we)
+    int hs = (int)ceilf((float)ny / sy), he = (int)ceilf((float)(ny + 1) / sy);
+    while (hs > 0 && nearest_src(hs - 1, sy, Ht) >= ny) --hs;
+    while (hs < H && nearest_src(hs, sy, Ht) < ny) ++hs;
+    he = min(max(he, hs), H);
+    while (he > hs && nearest_src(he - 1, sy, Ht) > ny) --he;
+    while (he < H && nearest_src(he, sy, Ht) <= ny) ++he;
+    int ws = (int)ceilf((float)nx / sx), we = (int)ceilf((float)(nx + 1) / sx);
+    while (ws > 0 && nearest_src(ws - 1, sx, Wt) >= nx) --ws;
+    while (ws < W && nearest_src(ws, sx, Wt) < nx) ++ws;
+    we = min(max(we, ws), W);
+    while (we > ws && nearest_src(we - 1, sx, Wt) > nx) --we;
+    while (we < W && nearest_src(we, sx, Wt) <= nx) ++we;
+    const int y0 = max(hs - 2, 0), y1 = min(he + 2, H), x0 = max(ws - 2, 0), x1 = min(we + 2, W);
+    const int ww = x1 - x0, np = (y1 - y0) * ww;
+    float acc = 0.f;
+    for (int i = lane; i < np; i += 32) {
+      const int h = y0 + i / ww, w = x0 + i % ww;
+      const float gp = __ldg(g + (long long)h * W + w);
+      float wt_ = 0.f;
 #pragma unroll
-    for (int ky = 0; ky < 5; ++ky) {
-      const int iy = nearest_src(min(max(h + ky - 2, 0), H - 1), sy, Ht);
+      for (int ky = 0; ky < 5; ++ky) {
+        const int q = min(max(h + ky - 2, 0), H - 1);
+        if (q < hs || q >= he) continue;
 #pragma unroll
-      for (int kx = 0; kx < 5; ++kx) {
-        const int ix = nearest_src(min(max(w + kx - 2, 0), W - 1), sx, Wt);
-        atomicAdd(dmt + iy * Wt + ix, __fmul_rn(gp, __ldg(ks + ky * 5 + kx)));
+        for (int kx = 0; kx < 5; ++kx) {
+          const int p = min(max(w + kx - 2, 0), W - 1);
+          if (p >= ws && p < we) wt_ = __fadd_rn(wt_, __ldg(ks + ky * 5 + kx));
+        }
       }
+      acc = fmaf(gp, wt_, acc);
     }
+    acc = wsum(acc);
+    if (lane == 0) dmt[t] = acc;
   }
   __syncthreads();
-  // (2) tile head backward
+  // (2) tile head: recomputed forward, per-tile records for the parameter gradients
   const float* bm = bit_map + (long long)b * nt;
   const float* an = act_n + (long long)b * nt;
   for (int t = threadIdx.x; t < nt; t += blockDim.x) {
     const int i = t / Wt, j = t - i * Wt;
+    float* rc = rec + t * SM_REC;
     float in[2][9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int yy = i + ky - 1, xx = j + kx - 1;
-        const bool ok = yy >= 0 && yy < Ht && xx >= 0 && xx < Wt;
-        in[0][ky * 3 + kx] = ok ? fminf(fmaxf(__fdiv_rn(__fsub_rn(bm[yy * Wt + xx], 2.0f), 6.0f), 0.f), 1.f) : 0.f;
-        in[1][ky * 3 + kx] = ok ? an[yy * Wt + xx] : 0.f;
-      }
+    for (int k = 0; k < 9; ++k) {
+      const int yy = i + k / 3 - 1, xx = j + k % 3 - 1;
+      const bool ok = yy >= 0 && yy < Ht && xx >= 0 && xx < Wt;
+      in[0][k] = ok ? fminf(fmaxf(__fdiv_rn(__fsub_rn(bm[yy * Wt + xx], 2.0f), 6.0f), 0.f), 1.f) : 0.f;
+      in[1][k] = ok ? an[yy * Wt + xx] : 0.f;
+      rc[17 + k] = in[0][k];
+      rc[26 + k] = in[1][k];
+    }
     float hid[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
@@ -707,32 +784,46 @@ softmask_bwd_kernel(const float* __restrict__ dm, const float* __restrict__ bit_
     const float e0 = exp_f64(__fsub_rn(l0, mx)), e1 = exp_f64(__fsub_rn(l1, mx));
     const float m = __fdiv_rn(e0, __fadd_rn(e0, e1));
     const float gl = __fmul_rn(dmt[t], __fmul_rn(m, __fsub_rn(1.f, m)));     // d m / d l0 = m (1 - m) = - d m / d l1
-    if (gl == 0.f) continue;
-    atomicAdd(gw + 168, gl);
-    atomicAdd(gw + 169, -gl);
+    rc[0] = gl;
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
-      atomicAdd(gw + 152 + o, __fmul_rn(gl, hid[o]));
-      atomicAdd(gw + 160 + o, -__fmul_rn(gl, hid[o]));
-      const float gh = hid[o] > 0.f ? __fmul_rn(gl, __fsub_rn(__ldg(W2 + o), __ldg(W2 + 8 + o))) : 0.f;
-      if (gh == 0.f) continue;
-      atomicAdd(gw + 144 + o, gh);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        atomicAdd(gw + (o * 2 + 0) * 9 + k, __fmul_rn(gh, in[0][k]));
-        atomicAdd(gw + (o * 2 + 1) * 9 + k, __fmul_rn(gh, in[1][k]));
-        const int yy = i + k / 3 - 1, xx = j + k % 3 - 1;
-        if (yy >= 0 && yy < Ht && xx >= 0 && xx < Wt) atomicAdd(gin + yy * Wt + xx, __fmul_rn(gh, __ldg(W0 + (o * 2) * 9 + k)));
-      }
+      rc[1 + o] = hid[o];
+      rc[9 + o] = hid[o] > 0.f ? __fmul_rn(gl, __fsub_rn(__ldg(W2 + o), __ldg(W2 + 8 + o))) : 0.f;
     }
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < nt; t += blockDim.x) {
-    const float bn = __fdiv_rn(__fsub_rn(bm[t], 2.0f), 6.0f);
-    dbit[(long long)b * nt + t] = (bn >= 0.f && bn <= 1.f) ? __fdiv_rn(gin[t], 6.0f) : 0.f;
+  // (3) parameter gradients: a thread per parameter sums over the tiles; d bit_map: a thread per tile gathers
+  for (int p = threadIdx.x; p < 170; p += blockDim.x) {
+    float a = 0.f;
+    if (p < 144) {
+      const int o = p / 18, ck = p - o * 18;                   // W0[o][c][k]: in[c][k] at rec[17 + c * 9 + k]
+      for (int t = 0; t < nt; ++t) a = fmaf(rec[t * SM_REC + 9 + o], rec[t * SM_REC + 17 + ck], a);
+    } else if (p < 152) {
+      for (int t = 0; t < nt; ++t) a = __fadd_rn(a, rec[t * SM_REC + 9 + (p - 144)]);
+    } else if (p < 168) {
+      const int q = p - 152, i = q & 7;
+      for (int t = 0; t < nt; ++t) a = fmaf(rec[t * SM_REC], rec[t * SM_REC + 1 + i], a);
+      if (q >= 8) a = -a;
+    } else {
+      for (int t = 0; t < nt; ++t) a = __fadd_rn(a, rec[t * SM_REC]);
+      if (p == 169) a = -a;
+    }
+    if (a != 0.f) atomicAdd(gP + p, a);
   }
-  for (int i = threadIdx.x; i < 170; i += blockDim.x)
-    if (gw[i] != 0.f) atomicAdd(gP + i, gw[i]);
+  for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+    const int i = t / Wt, j = t - i * Wt;
+    float gin = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {                              // tile s = t - (k - centre) reads this tile through tap k
+      const int yy = i - (k / 3 - 1), xx = j - (k % 3 - 1);
+      if (yy < 0 || yy >= Ht || xx < 0 || xx >= Wt) continue;
+      const float* rs_ = rec + (yy * Wt + xx) * SM_REC + 9;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) gin = fmaf(rs_[o], __ldg(W0 + (o * 2) * 9 + k), gin);
+    }
+    const float bn = __fdiv_rn(__fsub_rn(bm[t], 2.0f), 6.0f);
+    dbit[(long long)b * nt + t] = (bn >= 0.f && bn <= 1.f) ? __fdiv_rn(gin, 6.0f) : 0.f;
+  }
 }
 
 // normalised tile activity act / (max_img + 1e-8) of the soft mask (quantization.py:224-226), no gradient:
@@ -788,7 +879,7 @@ bit_stats_kernel(const float* __restrict__ bm, int ht, int wt, float* __restrict
 
 using namespace mcaq;
 
-extern "C" long long mcaq_cmlp_train_scratch_floats(int N) { return N > 0 ? (long long)N * CM_SCR : MCAQ_EINVAL; }
+extern "C" long long mcaq_cmlp_train_scratch_floats(int N) { return N > 0 ? 4 : MCAQ_EINVAL; }   // none needed any more
 extern "C" long long mcaq_mapper_train_scratch_floats(int N) { return N > 0 ? (long long)N * MP_SCR : MCAQ_EINVAL; }
 
 // complexity path backward: g_craw (through bilateral + clamp) and the MLP's parameter gradients (gP: 2881 floats,
@@ -801,14 +892,22 @@ extern "C" int mcaq_complexity_train_bwd(const float* phi, const float* craw, co
   cudaStream_t st = (cudaStream_t)stream;
   const int nt = ht * wt, N = B * nt;
   bilateral_bwd_kernel<<<B, 256, nt * sizeof(float), st>>>(craw, grad_out, ht, wt, grad_craw_ws);
-  const int rpc = 128;
-  cmlp_bwd_kernel<<<(N + rpc - 1) / rpc, 128, 0, st>>>(phi, grad_craw_ws, params, N, rpc, scratch, grad_params);
+  (void)scratch;
+  int ctas = (N + 4 * (CM_NT / 32) - 1) / (4 * (CM_NT / 32));       // >= 4 rows per warp, at most 64 CTAs (one flush each)
+  ctas = ctas < 1 ? 1 : (ctas > 64 ? 64 : ctas);
+  cmlp_bwd_kernel<<<ctas, CM_NT, 0, st>>>(phi, grad_craw_ws, params, N, grad_params);
   MCAQ_LAUNCH_CHECK();
   return 0;
 }
 
 static int launch_mapper(void (*k)(const MapArgs), MapArgs& A, cudaStream_t st) {
-  const size_t smem = (6 * 64 + 8 + MAP_CL * (2 * 64 + 1) + 128) * sizeof(float);
+  const size_t smem = (size_t)MAP_SM_FLOATS * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mapper_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(mapper_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(MAP_CL);
   cfg.blockDim = dim3(MAP_NT);
@@ -841,12 +940,14 @@ static int fill_px(XchgPeers& px, void* const* peers, int rank, int world) {
 // the batch is sharded over ranks (statistics of the whole batch on every rank), else world = 1.
 extern "C" int mcaq_mapper_train_fwd(const float* cmap, int N, const float* params, float temperature, int use_temperature,
                                      float min_bits, float max_bits, float* scratch, float* stats, float* rm0, float* rv0,
-                                     float* rm1, float* rv1, float* rm2, float* rv2, float momentum, float eps, float* bits,
+                                     float* rm1, float* rv1, float* rm2, float* rv2, long long* nbt0, long long* nbt1,
+                                     long long* nbt2, float momentum, float eps, float* bits,
                                      void* const* xchg_peers, int xchg_rank, int xchg_world, void* stream) {
   if (!cmap || !params || !scratch || !stats || !bits || N <= 0) return MCAQ_EINVAL;
   MapArgs A = {};
   A.c = cmap; A.P = params; A.N = N; A.temperature = temperature; A.use_t = use_temperature; A.lo = min_bits; A.hi = max_bits;
   A.scratch = scratch; A.stats = stats; A.rm[0] = rm0; A.rv[0] = rv0; A.rm[1] = rm1; A.rv[1] = rv1; A.rm[2] = rm2; A.rv[2] = rv2;
+  A.nbt[0] = nbt0; A.nbt[1] = nbt1; A.nbt[2] = nbt2;
   A.momentum = momentum; A.eps = eps; A.out = bits;
   int rc = fill_px(A.px, xchg_peers, xchg_rank, xchg_world);
   if (rc) return rc;
@@ -882,7 +983,13 @@ extern "C" int mcaq_softmask_train_bwd(const float* grad_mask, const float* bit_
   if (!grad_mask || !bit_map || !act_norm || !params || !grad_bit_map || !grad_params || B <= 0 || H <= 0 || W <= 0 ||
       Ht <= 0 || Wt <= 0)
     return MCAQ_EINVAL;
-  const size_t smem = (2 * (size_t)Ht * Wt + 170) * sizeof(float);
+  const size_t smem = ((size_t)Ht * Wt * (1 + SM_REC)) * sizeof(float);
+  if (smem > 200 * 1024) return MCAQ_ETOOBIG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(softmask_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
   softmask_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(grad_mask, bit_map, act_norm, params, H, W, Ht, Wt, grad_bit_map,
                                                             grad_params);
   MCAQ_LAUNCH_CHECK();

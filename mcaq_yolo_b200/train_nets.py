@@ -67,18 +67,16 @@ class MapperTrainFn(torch.autograd.Function):
         bits = torch.empty_like(c)
         use_t = temperature is not None
         t = max(float(temperature), 0.1) if use_t else 1.0
-        run = []
+        run, nbt = [], []
         for bn in bns:
             track = bn.track_running_stats and bn.running_mean is not None
             run += [bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None]
+            nbt.append(bn.num_batches_tracked.data_ptr() if track and bn.num_batches_tracked is not None else None)
         mom = bns[0].momentum if bns[0].momentum is not None else 0.1
         peers, rank, world = _xchg_args(xchg)
         ops._call("mcaq_mapper_train_fwd", c.data_ptr(), N, flat.data_ptr(), t, int(use_t), float(lo), float(hi),
-                  scratch.data_ptr(), stats.data_ptr(), *run, float(mom), float(bns[0].eps), bits.data_ptr(),
-                  peers, rank, world, ops._stream())
-        for bn in bns:
-            if bn.track_running_stats and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked.add_(1)
+                  scratch.data_ptr(), stats.data_ptr(), *run, *nbt, float(mom), float(bns[0].eps), bits.data_ptr(),
+                  peers, rank, world, ops._stream())          # num_batches_tracked += 1 happens in the kernel
         ctx.save_for_backward(c, flat, scratch, stats)
         ctx.cfg = (t, int(use_t), float(lo), float(hi), float(bns[0].eps), xchg)
         return bits

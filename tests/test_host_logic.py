@@ -201,3 +201,85 @@ def test_mlp_mapper_is_a_staircase_in_the_oracle():
         assert np.all(np.diff(bits) >= 0), "mapper output must be non-decreasing in complexity"
         assert set(np.unique(bits)) <= set(np.arange(2, 9, dtype=np.float32))
     assert np.unique(o.mlp_bit_mapper(c.reshape(1, 1, -1), W["mapper"], temperature=1.0, continuous=False)).size >= 4
+
+
+# ---- training-time exchanges of the sharded batch over gloo, world size 2 -------------------------
+def _gloo_train_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mcaq_yolo_b200 import train_nets as TN
+        torch.manual_seed(5)
+        ok = True
+        # (1) SyncBN merge: rank-ordered Chan merge of per-rank (count, mean, M2) == statistics of the whole batch
+        z = torch.randn(10, 16) * 3 + 1.5
+        parts_idx = [(0, 7), (7, 10)]                        # uneven shards
+        s, e = parts_idx[rank]
+        mine = z[s:e]
+        local = torch.cat([torch.tensor([float(e - s)]), mine.mean(0), ((mine - mine.mean(0)) ** 2).sum(0)])
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        cnt, mean, m2 = TN.merge_batch_stats([(float(g[0]), g[1:17], g[17:]) for g in gathered])
+        ok = ok and cnt == 10 and torch.allclose(mean, z.mean(0), atol=1e-6) and \
+            torch.allclose(m2 / cnt, z.var(0, unbiased=False), atol=1e-5)
+        # (2) avg_bits / Lbit / Lsmooth over the GLOBAL batch with a local straight-through gradient
+        maps_full = [torch.rand(4, 6, 6) * 6 + 2, torch.rand(4, 3, 3) * 6 + 2]
+
+        class _CpuBitStats(torch.autograd.Function):          # CPU stand-in for the bit_stats kernel (same reductions)
+            @staticmethod
+            def forward(ctx, b):
+                ctx.save_for_backward(b)
+                dx = (b[:, 1:, :] - b[:, :-1, :]).abs().sum()
+                dy = (b[:, :, 1:] - b[:, :, :-1]).abs().sum()
+                return torch.stack([b.sum(), dx + dy])
+
+            @staticmethod
+            def backward(ctx, g):
+                b, = ctx.saved_tensors
+                with torch.enable_grad():
+                    bb = b.detach().requires_grad_(True)
+                    tv = (bb[:, 1:, :] - bb[:, :-1, :]).abs().sum() + (bb[:, :, 1:] - bb[:, :, :-1]).abs().sum()
+                    (g[0] * bb.sum() + g[1] * tv).backward()
+                return bb.grad
+
+        TN.BitStatsFn = _CpuBitStats
+        shard = [m[2 * rank:2 * rank + 2].clone().requires_grad_(True) for m in maps_full]
+        avg, lbit, lsm = TN.bit_map_losses(shard, 4.0)
+        (lbit + lsm).backward()
+        full = [m.clone().requires_grad_(True) for m in maps_full]
+        avg_f = torch.stack([m.mean() for m in full]).mean()
+        tv = []
+        for m in full:
+            dx = (m[:, 1:, :] - m[:, :-1, :]).abs()
+            dy = (m[:, :, 1:] - m[:, :, :-1]).abs()
+            tv.append((dx.sum() + dy.sum()) / (dx.numel() + dy.numel()))
+        ((avg_f - 4.0) ** 2 + sum(tv) / 2).backward()
+        ok = ok and torch.allclose(avg, avg_f, atol=1e-6) and torch.allclose(lsm, sum(tv) / 2, atol=1e-6)
+        for a, b in zip(shard, full):
+            ok = ok and torch.allclose(a.grad, b.grad[2 * rank:2 * rank + 2], atol=1e-6)
+        # (3) one flat all-reduce of the small networks' gradients
+        lin = torch.nn.Linear(3, 2)
+        for p in lin.parameters():
+            p.grad = torch.full_like(p, float(rank + 1))
+        TN.allreduce_grads([lin])
+        ok = ok and all(torch.equal(p.grad, torch.full_like(p, 3.0)) for p in lin.parameters())
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_training_exchanges_world_size_2_gloo():
+    """SyncBN statistics merge, global avg_bits with local gradient, flat gradient all-reduce."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)], res
