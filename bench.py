@@ -33,6 +33,13 @@ WORKLOADS = {
     "yolov8s_1280_b32_f32": (32, [(128, 160, 160), (256, 80, 80), (512, 40, 40)], "f32", 8),
     "yolov8n_640_b1_f32": (1, [(64, 80, 80), (128, 40, 40), (256, 20, 20)], "f32", 8),
 }
+# model-level workloads (north_star reporting): synthetic images through a random-init minimal YOLOv8 driven by the
+# UNMODIFIED reference MCAQYOLO (tests/harness + baseline/_ref), native hooks installed; name: (scale, size, batch, dtype)
+MODEL_WORKLOADS = {
+    "model_v8n_640_b64": ("n", 640, 64, "bf16"),
+    "model_v8s_1280_b32": ("s", 1280, 32, "f32"),
+    "model_v8n_640_b1": ("n", 640, 1, "f32"),
+}
 INPUT_SETS = 4          # rotating input sets: 4 x 92 MB > 126 MB L2, so no step starts L2-warm
 
 
@@ -42,7 +49,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="yolov8n_640_b64_bf16", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="yolov8n_640_b64_bf16", choices=sorted(WORKLOADS) + sorted(MODEL_WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-streams", action="store_true", help="run the three scales on one stream")
@@ -83,6 +90,51 @@ def _oracle_worker(job):
     return time.perf_counter() - t0
 
 
+_REF_STATE = {}
+
+
+def _reference_available():
+    """True when an importable copy of the UNMODIFIED reference is reachable: /root/reference in the build
+    container, or baseline/_ref (pip --target install, git-ignored, travels to the GPU box with the snapshot)."""
+    from harness import ref_model
+    return ref_model.reference_root() is not None
+
+
+def _reference_worker(job):
+    """One bounded sample through the reference's OWN modules on CPU (core/morphology.py, bit_allocation.py,
+    quantization.py: the pure-PyTorch path, one torch thread per worker process): analyzer -> mapper ->
+    quantizer(training=False) over the three scales for `nimg` images."""
+    shapes, nimg, seed, grid = job
+    import torch
+    if not _REF_STATE:
+        torch.set_num_threads(1)
+        from harness import ref_model
+        pkg = ref_model.load(with_model=False)
+        from mcaq_yolo.core import bit_allocation, morphology, quantization
+        from golden_util import weights
+        W = weights()
+        sd = lambda d: {k: torch.as_tensor(v) for k, v in d.items()}      # noqa: E731
+        A = morphology.MorphologicalComplexityAnalyzer(grid_size=grid, device="cpu")
+        A.load_state_dict(sd(W["analyzer"]))
+        Mp = bit_allocation.ComplexityToBitMappingNetwork()
+        Mp.load_state_dict(sd(W["mapper"]))
+        Qs = []
+        for _ in shapes:
+            Q = quantization.SpatialAdaptiveQuantization(calibration_mode="minmax", smooth_transitions=True, per_channel=True)
+            Q.load_state_dict(sd(W["quantizer"]))
+            Qs.append(Q.eval())
+        _REF_STATE.update(A=A.eval(), M=Mp.eval(), Q=Qs, pkg=pkg)
+    from inputs import feature_map
+    xs = [torch.from_numpy(feature_map("smooth", nimg, C, H, Wd, seed + i)) for i, (C, H, Wd) in enumerate(shapes)]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for x, Q in zip(xs, _REF_STATE["Q"]):
+            c = _REF_STATE["A"](x)
+            bm = _REF_STATE["M"](c, 1.0)
+            Q(x, bm, training=False)
+    return time.perf_counter() - t0
+
+
 def cpu_sample(shapes, grid, seconds, procs):
     """images/s of the oracle port on `procs` host processes (each its own 2-image batches)."""
     import multiprocessing as mp
@@ -105,9 +157,9 @@ def cpu_sample(shapes, grid, seconds, procs):
 
 
 def run_reference(args):
-    """The reference's CPU implementation of the path (oracle port: the Python reference cannot travel
-    to the GPU box) on all host cores; each step is a bounded sample and the whole run is sized to
-    about two minutes whatever --steps / --warmup are."""
+    """The reference's CPU implementation of the path on all host cores: the reference's OWN torch modules when a
+    copy is reachable (baseline/_ref travels to the GPU box), else the numpy oracle port; each step is a bounded
+    sample and the whole run is sized to about two minutes whatever --steps / --warmup are."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -115,6 +167,8 @@ def run_reference(args):
     B, shapes, dtype, grid = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
+    use_ref = _reference_available()
+    worker = _reference_worker if use_ref else _oracle_worker
     nimg = 2
     nsteps = max(1, args.steps + args.warmup)
     budget = 120.0
@@ -122,17 +176,17 @@ def run_reference(args):
     vals = []
     with ctx.Pool(procs) as pool:
         t0 = time.perf_counter()
-        pool.map(_oracle_worker, [(shapes, nimg, 1000 + i, grid) for i in range(procs)])   # imports + one round
+        pool.map(worker, [(shapes, nimg, 1000 + i, grid) for i in range(procs)])   # imports + one round
         t_round = time.perf_counter() - t0
         t1 = time.perf_counter()
-        pool.map(_oracle_worker, [(shapes, nimg, 2000 + i, grid) for i in range(procs)])
+        pool.map(worker, [(shapes, nimg, 2000 + i, grid) for i in range(procs)])
         t_round = min(t_round, time.perf_counter() - t1)
         rounds = max(1, int(budget / nsteps / max(t_round, 1e-3)))
         if rounds * t_round * nsteps > 2.5 * budget:         # even one round per step is too long: fewer jobs
             rounds = 1
         for i in range(nsteps):
             t0 = time.perf_counter()
-            pool.map(_oracle_worker, [(shapes, nimg, 10 * i + j, grid) for j in range(procs * rounds)])
+            pool.map(worker, [(shapes, nimg, 10 * i + j, grid) for j in range(procs * rounds)])
             dt = time.perf_counter() - t0
             if i >= args.warmup:
                 vals.append((nimg * procs * rounds, dt))
@@ -145,10 +199,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, len(vals)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "grid": grid, "note": "oracle port (numpy) of the reference's "
-                   "pure-PyTorch CPU path; the Python reference itself cannot travel to the GPU box",
+        "config": {"workload": args.workload, "grid": grid,
+                   "note": ("the UNMODIFIED reference's own modules (core/morphology.py, bit_allocation.py, quantization.py: "
+                            "its pure-PyTorch CPU path) from baseline/_ref or /root/reference, one torch thread per process"
+                            if use_ref else
+                            "oracle port (numpy) of the reference's pure-PyTorch CPU path (no copy of the reference reachable)"),
                    "timed_steps": len(vals)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference" if use_ref else "port",
                          "sample": f"{nimg_tot} images in 2-image batches over {procs} processes, {dt:.1f} s"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -693,9 +750,20 @@ def run_native(args):
         line["parity_check_what"] = ("merged ranges == NCCL all_reduce(MIN) of the local ranges; y and bit maps of a sharded "
                                      "step == this rank's slice of the unsharded batch (all-gathered inputs), bit for bit")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, nimg, dt = cpu_sample(shapes, grid, args.cpu_seconds, 1)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"{nimg} images (2-image fp32 batches, same shapes), {dt:.1f} s, numpy oracle"}
+        if _reference_available():
+            t_one = _reference_worker((shapes, 2, 0, grid))             # imports + first call
+            n, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < args.cpu_seconds:
+                _reference_worker((shapes, 2, 1 + n, grid))
+                n += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 2 * n / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "sample": f"{2 * n} images (2-image fp32 batches, same shapes), {dt:.1f} s, the reference's "
+                                              "own torch modules on one host core"}
+        else:
+            v, nimg, dt = cpu_sample(shapes, grid, args.cpu_seconds, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{nimg} images (2-image fp32 batches, same shapes), {dt:.1f} s, numpy oracle"}
     if rank == 0:
         sys.stdout.flush()
         os.write(out_fd, (json.dumps(line) + "\n").encode())
@@ -709,9 +777,101 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def run_model(args):
+    """Whole-model timing on one GPU: the reference's MCAQYOLO wrapper (unmodified, models/mcaq_yolo.py:222-589) on the
+    harness' minimal random-init YOLOv8, (a) hooks inactive, (b) the reference's own torch hooks on CUDA, (c) the
+    native hooks after modules.install().  value = images/s of (c); the hooks' share is (c) - (a)."""
+    import copy
+    import torch
+    from harness import ref_model
+    assert torch.cuda.is_available()
+    pkg = ref_model.load()
+    if pkg is None:
+        print(json.dumps({"metric": METRIC, "unavailable": "no copy of the reference reachable (baseline/_ref or /root/reference)"}))
+        return
+    from mcaq_yolo.models.mcaq_yolo import MCAQYOLO
+    from mcaq_yolo_b200 import modules as M
+    from golden_util import weights
+    scale, size, B, dtype_name = MODEL_WORKLOADS[args.workload]
+    tdtype = torch.bfloat16 if dtype_name == "bf16" else torch.float32
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    ref = MCAQYOLO(f"yolov8{scale}", pretrained=False, device="cuda").eval()
+    W = weights()
+    sd = lambda d: {k: torch.as_tensor(v) for k, v in d.items()}      # noqa: E731
+    ref.complexity_analyzer.load_state_dict(sd(W["analyzer"]))
+    ref.bit_mapper.load_state_dict(sd(W["mapper"]))
+    for q in ref.quantizers.values():
+        q.load_state_dict(sd(W["quantizer"]))
+    nat = copy.deepcopy(ref)
+    layers = list(nat.model.model)
+    for idx in nat.backbone_out_indices:
+        layers[idx]._forward_hooks.clear()
+    nat._mcaq_hooks = [layers[i].register_forward_hook(nat._make_mcaq_hook(i)) for i in nat.backbone_out_indices]
+    M.install(nat)
+    nat.model.to(tdtype)
+    # the reference cannot run a bf16-weight model (its eval quantiser returns fp32 = bf16 * fp32 mask, which the next
+    # bf16 layer rejects): its arm keeps fp32 weights and runs under autocast, as its own trainer does (train.py:748)
+    ref_ctx = (lambda: torch.autocast("cuda", dtype=tdtype)) if tdtype != torch.float32 else (lambda: torch.autocast("cuda", enabled=False))
+    xs = [torch.rand(B, 3, size, size, device="cuda").to(tdtype) for _ in range(3)]
+
+    def timed(fn, n, warm=3):
+        with torch.no_grad():
+            for i in range(warm):
+                fn(xs[i % 3])
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(n):
+                fn(xs[i % 3])
+            b.record()
+            torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    n = max(3, args.steps)
+    t_plain = timed(lambda x: nat.model(x), n)                       # hooks inactive: the bare network
+    t_nat = timed(lambda x: nat(x), n)
+    def ref_fwd(x):
+        with ref_ctx():
+            return ref(x.float() if tdtype != torch.float32 else x)
+    t_ref = timed(ref_fwd, max(2, min(n, 5)), warm=1)
+    # agreement of the bit maps (not timed): the SAME raw backbone features (fp32, TF32 off) through the reference's
+    # modules on CUDA and through the native modules, per scale
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    feats = {}
+    hs = [ref.model.model[i].register_forward_hook(lambda m_, i_, o, k=i: feats.__setitem__(k, o.detach()))
+          for i in ref.backbone_out_indices]
+    with torch.no_grad():
+        ref.model(xs[0].float()[: min(B, 8)])
+        for h in hs:
+            h.remove()
+        agree = []
+        for k in ref.backbone_out_indices:
+            b_ref = ref.bit_mapper(ref.complexity_analyzer(feats[k]), 1.0)
+            b_nat = nat.bit_mapper(nat.complexity_analyzer(feats[k]), 1.0)
+            agree.append(float((b_ref == b_nat).float().mean()))
+        _, a_nat = nat(xs[0])
+    line = {"metric": "MCAQ-YOLO whole forward (backbone + MCAQ hooks + neck + head), images/s", "value": B / t_nat * 1e3,
+            "unit": UNIT, "n_gpus": 1, "steps": n, "warmup": 3, "ms_per_step": t_nat, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype_name, "data": "synthetic images, random-init weights",
+            "config": {"workload": args.workload, "model": f"minimal YOLOv8{scale} (tests/harness), {size}x{size}, batch {B}",
+                       "wrapper": "the reference's MCAQYOLO, unmodified, with an ultralytics stand-in; native modules via install()"},
+            "ms_forward_plain_network": t_plain, "ms_forward_native_hooks": t_nat, "ms_hooks_native": t_nat - t_plain,
+            "ms_forward_reference_hooks_cuda": t_ref, "ms_hooks_reference_cuda": t_ref - t_plain,
+            "hooks_speedup_vs_reference_on_same_gpu": (t_ref - t_plain) / max(t_nat - t_plain, 1e-9),
+            "bit_map_agreement_with_reference_cuda": agree,
+            "bit_map_agreement_note": "fraction of tiles with the same width when the reference's modules (torch ON CUDA, fp32, TF32 "
+                                      "off) and the native modules see the SAME raw C3/C4/C5 features of the first 8 images",
+            "avg_bits": float(a_nat["avg_bits"])}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.workload in MODEL_WORKLOADS:
+        run_model(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_native(a)
