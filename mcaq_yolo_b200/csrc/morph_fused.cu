@@ -1088,8 +1088,11 @@ static long long plan(MorphGeom& g, int B, int C, int H, int W, int grid_size) {
   g.bs = g.Wc + 2;
   g.ns = pick_split(B, g.ht, g.tile);
   long long bytes = layout(g);
-  // planes too large for two CTAs per SM (or for one at all): split the image further
-  while (bytes > 112 * 1024 && g.ns * 2 <= 8 && g.ns * 2 <= g.ht && !g_force_split) {
+  // planes too large for two CTAs per SM (or for one at all): split the image further -- but not below 32-row
+  // bands while one CTA per SM still fits: every band recomputes a 10-row stencil halo, and at 20-row bands that
+  // halo doubles the stencil work (measured on the 160 x 160 maps of YOLOv8s @ 1280: 4 CTAs per image beat 8)
+  while (bytes > 112 * 1024 && g.ns * 2 <= 8 && g.ns * 2 <= g.ht && !g_force_split &&
+         (g.band_max / 2 >= 32 || bytes > 200 * 1024)) {
     g.ns *= 2;
     bytes = layout(g);
   }

@@ -66,6 +66,10 @@ class ScaleWorkspace:
         ops._call("mcaq_ranges_reset", self.keys.data_ptr(), C, ops._stream())
 
 
+import os as _os
+_K1_PRIO = bool(int(_os.environ.get("MCAQ_K1_PRIO", "0")))      # tuning aid: K1 on the high-priority stream too
+
+
 def mapper_block(mapper, temperature) -> torch.Tensor:
     """Parameter block of the MLP mapper for K2: with its step table when the network is monotone in c
     (constants.mapping_is_monotone), the plain block -- K2 then evaluates the network per tile -- when it
@@ -76,7 +80,7 @@ def mapper_block(mapper, temperature) -> torch.Tensor:
 
 
 def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, temperature, ws: ScaleWorkspace | None,
-                        layer: int = -1, xchg=None) -> dict:
+                        layer: int = -1, xchg=None, k2_stream=None) -> dict:
     """Eval-mode hook body for one scale in three launches.  Returns the aux record.
     xchg: a peer.RangeExchange when the batch is sharded over the GPUs of a node -- the range merge
     then happens inside K2 / K3 over peer memory instead of a collective between them."""
@@ -90,16 +94,46 @@ def fused_scale_forward(feat: torch.Tensor, analyzer, mapper, quantizer, tempera
         ws = ScaleWorkspace(C, x.device) if need_ranges else None
     s = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
     a = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
-    ops.reduce_planes_into(x, s, a, ws.keys if need_ranges else None)
+    if k2_stream is not None and _K1_PRIO:
+        cur0 = torch.cuda.current_stream()
+        ev0 = torch.cuda.Event()
+        ev0.record(cur0)
+        k2_stream.wait_event(ev0)
+        with torch.cuda.stream(k2_stream):
+            ops.reduce_planes_into(x, s, a, ws.keys if need_ranges else None)
+            ev1 = torch.cuda.Event()
+            ev1.record(k2_stream)
+        cur0.wait_event(ev1)
+    else:
+        ops.reduce_planes_into(x, s, a, ws.keys if need_ranges else None)
     linear = isinstance(mapper, M.LinearBitMapper)
     sm = quantizer.soft_mask if quantizer.smooth_transitions else None
-    r = ops.morph_fused(s, a if sm is not None else None, C, analyzer.grid_size,
-                        K.pack_complexity_mlp(analyzer.complexity_mlp),
-                        None if linear else mapper_block(mapper, temperature),
-                        None if sm is None else K.pack_soft_mask(sm),
-                        temperature, False, ws.keys if need_ranges else None,
-                        mapper.min_bits, mapper.max_bits, getattr(mapper, "eps_spread", 1e-3),
-                        xchg=xchg if need_ranges else None)
+    def k2():
+        return ops.morph_fused(s, a if sm is not None else None, C, analyzer.grid_size,
+                               K.pack_complexity_mlp(analyzer.complexity_mlp),
+                               None if linear else mapper_block(mapper, temperature),
+                               None if sm is None else K.pack_soft_mask(sm),
+                               temperature, False, ws.keys if need_ranges else None,
+                               mapper.min_bits, mapper.max_bits, getattr(mapper, "eps_spread", 1e-3),
+                               xchg=xchg if need_ranges else None)
+    if k2_stream is None:
+        r = k2()
+    else:
+        # the latency-bound morphology kernel on a HIGH-PRIORITY stream (fork / join by events, capturable): its few
+        # long-lived CTAs are placed ahead of the pending CTAs of the bandwidth kernels of other scales / steps
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        k2_stream.wait_event(ev)
+        with torch.cuda.stream(k2_stream):
+            r = k2()
+            done = torch.cuda.Event()
+            done.record(k2_stream)
+        cur.wait_event(done)
+        _record_on(cur, r)
+        if not torch.cuda.is_current_stream_capturing():
+            s.record_stream(k2_stream)
+            a.record_stream(k2_stream)
     if frozen:
         y = ops.tile_quantize_ranges(x, r["bit_map"], None, quantizer.running_min, quantizer.running_max, r["mask"])
     elif xchg is not None and xchg.world > 1:
@@ -161,12 +195,14 @@ class FusedHotPath:
     wrapper): `run(feats)` takes the C3/C4/C5 maps and returns the aux records."""
 
     def __init__(self, analyzer, mapper, quantizers, temperature: float = 1.0, streams: bool = True,
-                 exchanges=None, latency: bool = False):
+                 exchanges=None, latency: bool = False, k2_priority: bool = False):
         self.analyzer, self.mapper, self.quantizers = analyzer, mapper, list(quantizers)
         self.temperature = temperature
         self.ws = [None] * len(self.quantizers)
         self.use_streams = streams
         self.side = None
+        # optional: one high-priority stream per scale for the morphology kernel (bench.py --k2-priority)
+        self.k2s = [torch.cuda.Stream(priority=-1) for _ in self.quantizers] if k2_priority else [None] * len(self.quantizers)
         # one peer.RangeExchange per scale when the batch is sharded over the GPUs of a node
         self.xchg = list(exchanges) if exchanges is not None else [None] * len(self.quantizers)
         # latency=True: a serial caller -- split every image over a cluster (library-wide policy switch)
@@ -180,7 +216,7 @@ class FusedHotPath:
             out = []
             for i, x in enumerate(feats):
                 rec, self.ws[i] = fused_scale_forward(x, self.analyzer, self.mapper, self.quantizers[i],
-                                                      self.temperature, self.ws[i], i, self.xchg[i])
+                                                      self.temperature, self.ws[i], i, self.xchg[i], self.k2s[i])
                 out.append(rec)
             return out
         # scales are independent: fork one stream per extra scale so K2's per-image latency of one
@@ -197,12 +233,12 @@ class FusedHotPath:
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 out[i], self.ws[i] = fused_scale_forward(feats[i], self.analyzer, self.mapper, self.quantizers[i],
-                                                         self.temperature, self.ws[i], i, self.xchg[i])
+                                                         self.temperature, self.ws[i], i, self.xchg[i], self.k2s[i])
                 ev = torch.cuda.Event()
                 ev.record(st)
                 joins.append(ev)
         out[0], self.ws[0] = fused_scale_forward(feats[0], self.analyzer, self.mapper, self.quantizers[0],
-                                                 self.temperature, self.ws[0], 0, self.xchg[0])
+                                                 self.temperature, self.ws[0], 0, self.xchg[0], self.k2s[0])
         for ev in joins:
             cur.wait_event(ev)
         if not torch.cuda.is_current_stream_capturing():
