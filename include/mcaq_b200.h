@@ -86,6 +86,10 @@ MCAQ_API int mcaq_ranges_decode(const int32_t* keys, int C, float* packed, void*
 /* EMA update of running_min/max (quantization.py:340-347); first!=0 adopts the batch stats */
 MCAQ_API int mcaq_ranges_ema(const float* packed, int C, double momentum, int first,
                     float* running_min, float* running_max, void* stream);
+/* K1's epilogue for training / calibration in one launch: keys -> packed (may be NULL) AND the EMA of the running
+ * statistics (quantization.py:319-353); the separate decode + ema pair remains for the all-reduced (sharded) case */
+MCAQ_API int mcaq_ranges_finish(const int32_t* keys, int C, double momentum, int first, float* running_min,
+                                float* running_max, float* packed, void* stream);
 
 /* qtable[(b-2)*C + c] = {scale, zero_point} for b = 2..8 (quantization.py:41-66).
  * Ranges come either from `packed` (min, -max) or from running_min/max (packed == NULL). */
@@ -110,6 +114,13 @@ MCAQ_API int mcaq_tile_quantize_ranges(const void* x, void* y, int dtype, int B,
                                        const float* bit_map, int Ht, int Wt, const float* packed,
                                        const float* running_min, const float* running_max,
                                        float* qtable_ws, const float* mask, void* stream);
+/* Bulk-copy (TMA) staged variant of mcaq_tile_quantize_ranges: the input tile travels global -> shared memory with
+ * cp.async.bulk + mbarrier (csrc/tile_quantize_tma.cu), identical results.  Covers the vector geometries with
+ * C % 32 == 0 and y != x; MCAQ_EGEOM otherwise (the caller then uses mcaq_tile_quantize_ranges). */
+MCAQ_API int mcaq_tile_quantize_ranges_tma(const void* x, void* y, int dtype, int B, int C, int H, int W,
+                                           const float* bit_map, int Ht, int Wt, const float* packed,
+                                           const float* running_min, const float* running_max, const float* mask,
+                                           void* stream);
 
 /* Training forward (fractional bits, quantization.py:699-727, 742-744):
  *   pre = (1-f) Q_floor(b)(x) + f Q_floor(b)+1(x),  y = pre * m                              */

@@ -29,12 +29,15 @@ PROTOTYPES = {
                                                c_void_p]),
     "mcaq_ranges_decode": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "mcaq_ranges_ema": (c_int, [c_void_p, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "mcaq_ranges_finish": (c_int, [c_void_p, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcaq_build_qtable": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mcaq_tile_quantize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcaq_tile_quantize_ranges": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                           c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p]),
+    "mcaq_tile_quantize_ranges_tma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                              c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcaq_morph_fused": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_float, c_float,
                                  c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -325,6 +325,19 @@ __global__ void ranges_ema_kernel(const float* packed, int C, float momentum, fl
   rmax[i] = __fadd_rn(__fmul_rn(momentum, rmax[i]), __fmul_rn(one_minus, mx));
 }
 
+// K1's epilogue for training / calibration in ONE launch: decode the range keys into packed = [min, -max] and
+// apply the EMA to running_min / running_max (quantization.py:319-353)
+__global__ void ranges_finish_kernel(const int* keys, int C, float momentum, float one_minus, int first, float* rmin,
+                                     float* rmax, float* packed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  const float mn = key_float(keys[i]), mx = key_float(keys[C + i]);
+  if (packed) { packed[i] = mn; packed[C + i] = -mx; }
+  if (first) { rmin[i] = mn; rmax[i] = mx; return; }
+  rmin[i] = __fadd_rn(__fmul_rn(momentum, rmin[i]), __fmul_rn(one_minus, mn));
+  rmax[i] = __fadd_rn(__fmul_rn(momentum, rmax[i]), __fmul_rn(one_minus, mx));
+}
+
 // qtable[(b-2)*C + c] = {scale, zp}   (quantization.py:41-66)
 __global__ void build_qtable_kernel(const float* packed, const float* rmin, const float* rmax, int C,
                                     float2* qtable) {
@@ -438,6 +451,15 @@ extern "C" int mcaq_ranges_ema(const float* packed, int C, double momentum, int 
   const float one_minus = (float)(1.0 - momentum);
   ranges_ema_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(packed, C, (float)momentum, one_minus,
                                                                       first, running_min, running_max);
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mcaq_ranges_finish(const int32_t* keys, int C, double momentum, int first, float* running_min,
+                                  float* running_max, float* packed, void* stream) {
+  if (!keys || !running_min || !running_max || C <= 0) return MCAQ_EINVAL;
+  ranges_finish_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(keys, C, (float)momentum, (float)(1.0 - momentum),
+                                                                         first, running_min, running_max, packed);
   MCAQ_LAUNCH_CHECK();
   return 0;
 }

@@ -392,6 +392,7 @@ class SpatialAdaptiveQuantization(nn.Module):
         self.register_buffer("calibration_histogram", None)
         self.histogram_bins = 2048
         self._frozen_py = None      # host copy of stats_frozen: no device sync on the hot path
+        self._packed_cache = None   # (tensor, version, packed ranges) of the most recent sweep
         # feature-level distillation (train.py:599-610), optional: set `kd_teacher` to the teacher's
         # fp32 feature map of this layer before the student's forward; the training forward then
         # also leaves mse(features_q, teacher) in `kd_feature_loss` (differentiable)
@@ -420,11 +421,15 @@ class SpatialAdaptiveQuantization(nn.Module):
 
     # -- ranges --------------------------------------------------------------------------------
     def _batch_ranges(self, x: torch.Tensor) -> torch.Tensor:
-        """packed [min, -max] of this batch (all ranks when a process group is attached)."""
+        """packed [min, -max] of this batch (all ranks when sync_ranges is set); decoded once per sweep."""
+        hit = self._packed_cache
+        if hit is not None and hit[0] is x and hit[1] == x._version:
+            return hit[2]
         _, _, keys = channel_sweep(x, want_ranges=True)
         packed = ops.ranges_decode(keys)
         if self.sync_ranges:
             allreduce_ranges(packed, self.process_group)
+        self._packed_cache = (x, x._version, packed)
         return packed
 
     @torch.no_grad()
@@ -433,12 +438,20 @@ class SpatialAdaptiveQuantization(nn.Module):
         if self._is_frozen():
             return
         C = x.shape[1]
-        packed = self._batch_ranges(x)
         first = self.running_min is None
         if first:
             self.running_min = torch.empty((1, C, 1, 1), device=x.device, dtype=torch.float32)
             self.running_max = torch.empty((1, C, 1, 1), device=x.device, dtype=torch.float32)
-        ops.ranges_ema(packed, self.running_min, self.running_max, self.momentum, first)
+        import torch.distributed as dist
+        if self.sync_ranges and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            packed = self._batch_ranges(x)                   # decode, all-reduce over the ranks, then the EMA
+            ops.ranges_ema(packed, self.running_min, self.running_max, self.momentum, first)
+        else:
+            # K1's epilogue in one launch: decode + EMA; the batch ranges stay cached for the calibration pass,
+            # which quantises with them (quantization.py:415-417)
+            _, _, keys = channel_sweep(x, want_ranges=True)
+            packed = ops.ranges_finish(keys, self.running_min, self.running_max, self.momentum, first)
+            self._packed_cache = (x, x._version, packed)
         self.num_batches_tracked += 1
 
     def _qtable(self, x: torch.Tensor, training: bool) -> torch.Tensor:
@@ -482,6 +495,7 @@ class SpatialAdaptiveQuantization(nn.Module):
             m3 = None if mask is None else mask.reshape(mask.shape[0], mask.shape[-2], mask.shape[-1])
             y = ops.tile_quantize(x, bit_map, qtable, m3)
         _SWEEP.clear()
+        self._packed_cache = None
         return y
 
     def extra_repr(self) -> str:

@@ -47,6 +47,11 @@ def _ptr(t):
 # kernel launches issued through this module.
 EVENT_HOOK = None
 LAUNCHES = 0
+# K3 input staging: False = LDG.128 into registers (tile_quantize_vec_kernel), True = cp.async.bulk + mbarrier into shared
+# memory (tile_quantize_tma_kernel); both bit-identical (tests/test_gpu_round2.py).  Default from the measurements in
+# profiles/r02_k3_tma.txt; MCAQ_K3_TMA=0/1 overrides.
+import os as _os
+K3_TMA = bool(int(_os.environ.get("MCAQ_K3_TMA", "0")))
 
 
 def _call(name: str, *args):
@@ -128,6 +133,18 @@ def ranges_ema(packed: torch.Tensor, running_min: torch.Tensor, running_max: tor
     assert running_min.is_contiguous() and running_max.is_contiguous()
     _call("mcaq_ranges_ema", packed.data_ptr(), C, float(momentum), int(bool(first)),
                                       running_min.data_ptr(), running_max.data_ptr(), _stream())
+
+
+def ranges_finish(keys: torch.Tensor, running_min: torch.Tensor, running_max: torch.Tensor, momentum: float,
+                  first: bool) -> torch.Tensor:
+    """keys -> packed [min, -max] AND the in-place EMA of running_min / running_max, one launch
+    (quantization.py:319-353); returns packed (the batch ranges, which the calibration pass also quantises with)."""
+    C = keys.numel() // 2
+    assert running_min.numel() == C and running_max.numel() == C
+    packed = torch.empty((2 * C,), device=keys.device, dtype=torch.float32)
+    _call("mcaq_ranges_finish", keys.data_ptr(), C, float(momentum), int(bool(first)), running_min.data_ptr(),
+          running_max.data_ptr(), packed.data_ptr(), _stream())
+    return packed
 
 
 def build_qtable(packed: torch.Tensor | None = None, running_min: torch.Tensor | None = None,
@@ -461,6 +478,10 @@ def tile_quantize_ranges(x: torch.Tensor, bit_map: torch.Tensor, packed: torch.T
         return y
     vec = 4 if x.dtype == torch.float32 else 8
     needs_ws = not ((H * W) % vec == 0 and W % 4 == 0 and W % Wt == 0 and (W // Wt) % 4 == 0)
+    if K3_TMA and not needs_ws and C % 32 == 0 and y.data_ptr() != x.data_ptr() and (xchg is None or xchg.world <= 1):
+        _call("mcaq_tile_quantize_ranges_tma", x.data_ptr(), y.data_ptr(), _dtype_code(x), B, C, H, W, bit_map.data_ptr(),
+              Ht, Wt, _ptr(packed), _ptr(running_min), _ptr(running_max), _ptr(mask), _stream())
+        return y
     ws = torch.empty((7, C, 2), device=x.device, dtype=torch.float32) if needs_ws else None
     if xchg is not None and xchg.world > 1:
         pws = torch.empty((2 * C,), device=x.device, dtype=torch.float32)

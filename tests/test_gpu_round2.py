@@ -286,3 +286,31 @@ def test_level0_launcher_vector_path_and_error_channel(W):
         ops.spatial_quantize(x, bm, mn.view(1, -1, 1, 1), mx.view(1, -1, 1, 1), c.tile + 1, c.tile, m)
     with pytest.raises(RuntimeError):
         ops.spatial_quantize(x, bm, mn[:3], mx[:3], c.tile, c.tile, m)
+
+
+# ------------------------------------------------------------------ K3 with bulk-copy (TMA) staged input
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(3, 64, 80, 80), (2, 128, 40, 40), (5, 256, 20, 20), (1, 128, 160, 160)])
+def test_k3_tma_variant_is_bit_identical(shape, dtype):
+    """tile_quantize_tma_kernel (cp.async.bulk + mbarrier staging) against tile_quantize_vec_kernel: same bytes."""
+    from mcaq_yolo_b200 import ops
+    B, C, H, Wd = shape
+    torch.manual_seed(11)
+    x = (torch.randn(B, C, H, Wd, device="cuda") * 2 + 0.3).to(dtype)
+    tile = ops.tile_size(H, 8)
+    ht = H // tile
+    bm = torch.randint(2, 9, (B, ht, ht), device="cuda").float()
+    mask = torch.rand(B, H, Wd, device="cuda") * 0.3 + 0.7
+    _, _, keys = ops.reduce_planes(x)
+    packed = ops.ranges_decode(keys)
+    saved = ops.K3_TMA
+    try:
+        for mk in (mask, None):
+            ops.K3_TMA = False
+            y0 = ops.tile_quantize_ranges(x, bm, packed, None, None, mk)
+            ops.K3_TMA = True
+            y1 = ops.tile_quantize_ranges(x, bm, packed, None, None, mk)
+            torch.cuda.synchronize()
+            assert torch.equal(y0, y1)
+    finally:
+        ops.K3_TMA = saved

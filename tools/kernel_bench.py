@@ -74,6 +74,16 @@ for shp in a.shapes.split(","):
         med, mn = timeit(lambda i: ops.tile_quantize(xs[i], bm, qt, None, out=ys[i]), nbuf, a.iters)
         print(f"K3 (no mask)      {shp:12s} {a.dtype} B={B}: median {med:7.1f} us (min {mn:7.1f})  "
               f"{2 * nbytes / med / 1e3:7.0f} GB/s")
+        pk = ops.ranges_decode(keys)
+        for tag, flag in (("K3 ranges (LDG) ", False), ("K3 ranges (TMA) ", True)):
+            ops.K3_TMA = flag
+            try:
+                med, mn = timeit(lambda i: ops.tile_quantize_ranges(xs[i], bm, pk, None, None, m, out=ys[i]), nbuf, a.iters)
+                print(f"{tag}  {shp:12s} {a.dtype} B={B}: median {med:7.1f} us (min {mn:7.1f})  "
+                      f"{2 * nbytes / med / 1e3:7.0f} GB/s")
+            except RuntimeError as e:
+                print(f"{tag}  {shp:12s}: {e}")
+        ops.K3_TMA = False
         med, mn = timeit(lambda i: ys[i].copy_(xs[i]), nbuf, a.iters)
         print(f"torch copy_       {shp:12s} {a.dtype} B={B}: median {med:7.1f} us (min {mn:7.1f})  "
               f"{2 * nbytes / med / 1e3:7.0f} GB/s")
