@@ -747,21 +747,49 @@ morph_fused_kernel(const FusedArgs A) {
   STAGE_CLOCK(3);
 
   // ---- T2: gradient magnitude + direction for rows [r_lo-1, r_hi+1) ------------------------------
+  // One CTA per image: the histogram is complete after one more barrier, so ONE warp evaluates Otsu's threshold
+  // (16 IEEE divisions per lane, an fp64 scan) while the others start on the magnitude tasks, which are handed out
+  // through a shared counter; with a cluster the histogram only completes at the cluster barrier below and every
+  // warp evaluates the threshold itself.
+  int* t2ctr = reinterpret_cast<int*>(red) + 62;
+  float* t2thr = red + 60;
+  if (ns == 1) {
+    if (tid == 0) *t2ctr = 0;
+    __syncthreads();
+  }
   {
     const int m_lo = max(r_lo - 1, 0), m_hi = min(r_hi + 1, Hc);
     const int nmag = ((m_hi - m_lo + 7) >> 3) * WW;
-    for (int task = warp; task < nmag; task += nwarps) {
-      const int rg = fast_div(task, g.m_ww), k = task - rg * WW;
-      task_mag<8>(c, m_lo + rg * 8, m_hi, k, lane);
+    if (ns == 1) {
+      if (warp == nwarps - 1) {
+        float th;
+        int ob;
+        otsu_warp(hist, lane, th, ob);
+        if (lane == 0) { t2thr[0] = th; t2thr[1] = __int_as_float(ob); }
+      }
+      for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(t2ctr, 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= nmag) break;
+        const int rg = fast_div(task, g.m_ww), k = task - rg * WW;
+        task_mag<8>(c, m_lo + rg * 8, m_hi, k, lane);
+      }
+    } else {
+      for (int task = warp; task < nmag; task += nwarps) {
+        const int rg = fast_div(task, g.m_ww), k = task - rg * WW;
+        task_mag<8>(c, m_lo + rg * 8, m_hi, k, lane);
+      }
     }
   }
   if (ns > 1) cl.sync(); else __syncthreads();       // MAG / DIR complete, whole-image histogram complete
   STAGE_CLOCK(4);
 
-  // ---- T3: Otsu (redundantly per warp), NMS + double threshold -----------------------------------
+  // ---- T3: Otsu, NMS + double threshold ------------------------------------------------------------
   float thr255;
   int otsu_bin;
-  otsu_warp(hist, lane, thr255, otsu_bin);
+  if (ns == 1) { thr255 = t2thr[0]; otsu_bin = __float_as_int(t2thr[1]); }
+  else otsu_warp(hist, lane, thr255, otsu_bin);
   {
     const float thr_lo = __fmul_rn(0.5f, thr255);
     const int RTn = tile >= 8 ? 8 : 4;
