@@ -53,6 +53,33 @@ __device__ __forceinline__ uint4 ldg_plain(const void* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// L2 residency hints (experiment switch MCAQ_L2_HINTS): the channel sweep marks x evict_last so that the quantise
+// sweep of the same scale can still find it in the 126 MB L2, which then reads it evict_first
+#ifndef MCAQ_L2_HINTS
+#define MCAQ_L2_HINTS 0
+#endif
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_stream_hint(const void* p, unsigned long long pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_noalloc_hint(const void* p, unsigned long long pol) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

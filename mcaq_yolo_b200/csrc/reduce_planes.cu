@@ -1,10 +1,12 @@
 // K1: one HBM sweep of an NCHW feature map producing
 //   sum_c x, sum_c |x| per pixel (fp32, torch-CPU cascade order) and per-channel min/max.
 //
-// Layout of the work: a "strip" is 32 consecutive 16-byte pixel vectors of one image; warp g
+// Layout of the work: a "strip" is 32 consecutive 16-byte pixel vectors of the flattened [B, HW] batch (it may
+// straddle two images: every lane derives its own image / pixel, so only the very last strip is ragged); warp g
 // of a CTA owns one 16-channel chunk of the strip per pass (16 independent LDG.128 in flight
 // per thread), sums it sequentially (chunk partial P_g), reduces the chunk's per-channel
-// min/max across the warp with REDUX on order-preserving integer keys, and parks P_g in shared
+// min/max across the warp (REDUX on order-preserving integer keys per vector, or -- when a warp always owns the
+// same 16 channels -- register accumulators joined once per CTA by a transposing butterfly), and parks P_g in shared
 // memory.  The CTA then folds the partials in chunk order exactly like ATen's multi_row_sum
 // (acc1 += P_g, acc2 += acc1 every 16 chunks) so the planes are bit-identical to
 // x.mean(1) * C on the reference's CPU path.  CTAs are persistent over strips; per-channel
@@ -20,7 +22,11 @@ template <typename T, int VEC>
 struct VecIO {
   static_assert(VEC == Elem<T>::VEC, "vector width");
   typedef uint4 Raw;
+#if MCAQ_L2_HINTS
+  __device__ __forceinline__ static Raw load(const T* p) { return ldg_stream_hint(p, l2_policy_evict_last()); }
+#else
   __device__ __forceinline__ static Raw load(const T* p) { return ldg_stream(p); }
+#endif
   __device__ __forceinline__ static Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
   __device__ __forceinline__ static void unpack(const Raw& r, float* f) { Elem<T>::unpack(r, f); }
 };
@@ -47,34 +53,71 @@ struct MinMaxAcc {
   }
   __device__ __forceinline__ float vmin() const { return lo; }
   __device__ __forceinline__ float vmax() const { return hi; }
+  __device__ __forceinline__ void merge(const MinMaxAcc& o) { lo = fminf(lo, o.lo); hi = fmaxf(hi, o.hi); }
+  __device__ __forceinline__ static MinMaxAcc select(bool c, const MinMaxAcc& a, const MinMaxAcc& b) {
+    MinMaxAcc r;
+    r.lo = c ? a.lo : b.lo;
+    r.hi = c ? a.hi : b.hi;
+    return r;
+  }
+  __device__ __forceinline__ MinMaxAcc shfl_xor(int mask) const {
+    MinMaxAcc r;
+    r.lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+    r.hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+    return r;
+  }
+};
+// 16-bit types: the partials live as raw 32-bit words (two packed values), so that selects and shuffles of the
+// butterfly are plain register moves
+template <typename P2, uint32_t POS_INF2, uint32_t NEG_INF2>
+struct MinMaxAcc16 {
+  uint32_t lo, hi;
+  __device__ __forceinline__ static P2 as2(uint32_t w) { return *reinterpret_cast<P2*>(&w); }
+  __device__ __forceinline__ static uint32_t raw(P2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+  __device__ __forceinline__ void init() { lo = POS_INF2; hi = NEG_INF2; }
+  __device__ __forceinline__ void update(const uint4& r) {
+    const P2 a = as2(r.x), b = as2(r.y), c = as2(r.z), d = as2(r.w);
+    lo = raw(__hmin2(as2(lo), __hmin2(__hmin2(a, b), __hmin2(c, d))));
+    hi = raw(__hmax2(as2(hi), __hmax2(__hmax2(a, b), __hmax2(c, d))));
+  }
+  __device__ __forceinline__ float vmin() const { return fminf(__low2float(as2(lo)), __high2float(as2(lo))); }
+  __device__ __forceinline__ float vmax() const { return fmaxf(__low2float(as2(hi)), __high2float(as2(hi))); }
+  __device__ __forceinline__ void merge(const MinMaxAcc16& o) {
+    lo = raw(__hmin2(as2(lo), as2(o.lo)));
+    hi = raw(__hmax2(as2(hi), as2(o.hi)));
+  }
+  __device__ __forceinline__ static MinMaxAcc16 select(bool c, const MinMaxAcc16& a, const MinMaxAcc16& b) {
+    MinMaxAcc16 r;
+    r.lo = c ? a.lo : b.lo;
+    r.hi = c ? a.hi : b.hi;
+    return r;
+  }
+  __device__ __forceinline__ MinMaxAcc16 shfl_xor(int mask) const {
+    MinMaxAcc16 r;
+    r.lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+    r.hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+    return r;
+  }
 };
 template <>
-struct MinMaxAcc<__nv_bfloat16, 8> {
-  __nv_bfloat162 lo, hi;
-  __device__ __forceinline__ static __nv_bfloat162 as2(uint32_t w) { return *reinterpret_cast<__nv_bfloat162*>(&w); }
-  __device__ __forceinline__ void init() { lo = as2(0x7f807f80u); hi = as2(0xff80ff80u); }
-  __device__ __forceinline__ void update(const uint4& r) {
-    const __nv_bfloat162 a = as2(r.x), b = as2(r.y), c = as2(r.z), d = as2(r.w);
-    lo = __hmin2(lo, __hmin2(__hmin2(a, b), __hmin2(c, d)));
-    hi = __hmax2(hi, __hmax2(__hmax2(a, b), __hmax2(c, d)));
-  }
-  __device__ __forceinline__ float vmin() const { return fminf(__low2float(lo), __high2float(lo)); }
-  __device__ __forceinline__ float vmax() const { return fmaxf(__low2float(hi), __high2float(hi)); }
-};
+struct MinMaxAcc<__nv_bfloat16, 8> : MinMaxAcc16<__nv_bfloat162, 0x7f807f80u, 0xff80ff80u> {};
+template <>
+struct MinMaxAcc<__half, 8> : MinMaxAcc16<__half2, 0x7c007c00u, 0xfc00fc00u> {};
 
-template <>
-struct MinMaxAcc<__half, 8> {
-  __half2 lo, hi;
-  __device__ __forceinline__ static __half2 as2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
-  __device__ __forceinline__ void init() { lo = as2(0x7c007c00u); hi = as2(0xfc00fc00u); }
-  __device__ __forceinline__ void update(const uint4& r) {
-    const __half2 a = as2(r.x), b = as2(r.y), c = as2(r.z), d = as2(r.w);
-    lo = __hmin2(lo, __hmin2(__hmin2(a, b), __hmin2(c, d)));
-    hi = __hmax2(hi, __hmax2(__hmax2(a, b), __hmax2(c, d)));
+// One round of the transposing butterfly: the 2*N channel accumulators of every lane become N, lane pairs
+// (l, l ^ MASK) splitting the channels between them (bit MASK of the lane set: keeps the upper half)
+template <int N, int MASK, typename A>
+__device__ __forceinline__ void butterfly_round(A (&v)[16], int lane) {
+  const bool up = (lane & MASK) != 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const auto send = A::select(up, v[i], v[i + N]);
+    auto keep = A::select(up, v[i + N], v[i]);
+    keep.merge(send.shfl_xor(MASK));
+    v[i].lo = keep.lo;
+    v[i].hi = keep.hi;
   }
-  __device__ __forceinline__ float vmin() const { return fminf(__low2float(lo), __high2float(lo)); }
-  __device__ __forceinline__ float vmax() const { return fmaxf(__low2float(hi), __high2float(hi)); }
-};
+}
 
 // RMODE: 0 no ranges, 1 per-vector warp reduction (any C), 2 per-thread running min / max in
 // registers when the CTA's G warps cover all channel chunks in one pass (a warp then always owns
@@ -85,7 +128,7 @@ template <typename T, int VEC, int G, int RMODE>
 __global__ void __launch_bounds__(32 * G, (16 / G) > 0 ? (16 / G) : 1)
 reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
                      float* __restrict__ sum_plane, float* __restrict__ abs_plane,
-                     int* __restrict__ keys, int strips_per_image, long long total_strips) {
+                     int* __restrict__ keys, long long total_vec, long long total_strips) {
   constexpr int NT = 32 * G;
   constexpr int STRIP = 32 * VEC;                 // pixels per strip
   constexpr int NOUT = (2 * STRIP + NT - 1) / NT; // outputs owned per thread in the fold
@@ -116,14 +159,23 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
   }
 
   for (long long strip = blockIdx.x; strip < total_strips; strip += gridDim.x) {
-    const int b = (int)(strip / strips_per_image);
-    const int sv = (int)(strip - (long long)b * strips_per_image);
-    const int v = sv * 32 + lane;
-    const bool active = v < nvec;
+    // strips run over the flattened (image, pixel vector) index: HW % VEC == 0, so vector gv of the batch is
+    // pixels [gv * VEC, gv * VEC + VEC) of the contiguous [B, HW] planes and only the last strip is ragged
+    const long long gv = strip * 32 + lane;
+    const bool active = gv < total_vec;
+    const long long gvc = active ? gv : total_vec - 1;
+    int b, v;
+    if (total_vec <= 0x7fffffffLL) {
+      b = (int)((unsigned)gvc / (unsigned)nvec);
+      v = (int)((unsigned)gvc - (unsigned)b * (unsigned)nvec);
+    } else {
+      b = (int)(gvc / nvec);
+      v = (int)(gvc - (long long)b * nvec);
+    }
     const T* xb = x + ((long long)b * C) * HW + (long long)v * VEC;
 
-    // CTA-uniform: all of C in one pass of full chunks and the whole strip inside the image
-    const bool fastfold = VEC > 1 && npass == 1 && tail == 0 && nfull == G && (sv + 1) * 32 <= nvec;
+    // CTA-uniform: all of C in one pass of full chunks and no ragged lane in the strip
+    const bool fastfold = VEC > 1 && npass == 1 && tail == 0 && nfull == G && (strip + 1) * 32 <= total_vec;
     float acc0[NOUT], acc1[NOUT], acc2[NOUT];
 #pragma unroll
     for (int k = 0; k < NOUT; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; acc2[k] = 0.f; }
@@ -231,7 +283,7 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
 #pragma unroll
               for (int e = 0; e < FV; ++e) r[e] = __fadd_rn(r[e], p[e]);
             }
-            float* dst = (plane ? abs_plane : sum_plane) + (long long)b * HW + (long long)sv * STRIP + q;
+            float* dst = (plane ? abs_plane : sum_plane) + strip * STRIP + q;
             if (FV == 4) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<float4*>(r);
             else if (FV == 2) *reinterpret_cast<float2*>(dst) = *reinterpret_cast<float2*>(r);
             else dst[0] = r[0];
@@ -267,11 +319,11 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
       const int o = threadIdx.x + k * NT;
       if (!fastfold && o < 2 * STRIP) {
         const int plane = o / STRIP, q = o - plane * STRIP;
-        const long long pix = (long long)sv * STRIP + q;
-        if (pix < HW) {
+        const long long pix = strip * STRIP + q;
+        if (pix < total_vec * VEC) {
           const float r = __fadd_rn(__fadd_rn(acc0[k], acc1[k]), acc2[k]);
           float* dst = plane ? abs_plane : sum_plane;
-          dst[(long long)b * HW + pix] = r;
+          dst[pix] = r;
         }
       }
     }
@@ -289,16 +341,17 @@ reduce_planes_kernel(const T* __restrict__ x, int B, int C, int HW,
     const int gi = warp;
     if (gi < ngroups) {
       const int nch = (gi < nfull) ? 16 : tail;
-      int mymin = MCAQ_KEY_POS_INF, mymax = MCAQ_KEY_NEG_INF;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int kmin = __reduce_min_sync(0xffffffffu, float_key(mm[j].vmin()));
-        const int kmax = __reduce_max_sync(0xffffffffu, float_key(mm[j].vmax()));
-        if (lane == j) { mymin = kmin; mymax = kmax; }
-      }
-      if (lane < nch) {
-        atomicMin(keys + (gi << 4) + lane, mymin);
-        atomicMax(keys + C + (gi << 4) + lane, mymax);
+      // transposing butterfly (31 shuffle pairs instead of 32 REDUX + key conversions): after the rounds
+      // 16 / 8 / 4 / 2 lane l holds channel l >> 1 of half the warp, the last round joins the two halves
+      butterfly_round<8, 16>(mm, lane);
+      butterfly_round<4, 8>(mm, lane);
+      butterfly_round<2, 4>(mm, lane);
+      butterfly_round<1, 2>(mm, lane);
+      mm[0].merge(mm[0].shfl_xor(1));
+      const int j = lane >> 1;
+      if (!(lane & 1) && j < nch) {
+        atomicMin(keys + (gi << 4) + j, float_key(mm[0].vmin()));
+        atomicMax(keys + C + (gi << 4) + j, float_key(mm[0].vmax()));
       }
     }
   }
@@ -369,8 +422,8 @@ static int num_sms() {
 template <typename T, int VEC, int G>
 static int launch_reduce(const T* x, int B, int C, int HW, float* sp, float* ap, int* keys, cudaStream_t st) {
   const int nvec = (HW + VEC - 1) / VEC;
-  const int spi = (nvec + 31) / 32;
-  const long long total = (long long)B * spi;
+  const long long total_vec = (long long)B * nvec;
+  const long long total = (total_vec + 31) / 32;
   const size_t smem = (size_t)2 * G * 32 * VEC * sizeof(float) + (size_t)2 * C * sizeof(int);
   // persistent CTAs, exactly the resident wave: 512 threads per SM at <= 128 registers (16 / G CTAs).  A
   // second wave only repeats the per-CTA prologue / epilogue (32 REDUX + 2C atomics): one wave measured
@@ -380,12 +433,12 @@ static int launch_reduce(const T* x, int B, int C, int HW, float* sp, float* ap,
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;
   const int npass = ((C + 15) / 16 + G - 1) / G;
-  void (*k)(const T*, int, int, int, float*, float*, int*, int, long long);
+  void (*k)(const T*, int, int, int, float*, float*, int*, long long, long long);
   if (!keys) k = reduce_planes_kernel<T, VEC, G, 0>;
   else if (VEC > 1 && npass == 1) k = reduce_planes_kernel<T, VEC, G, 2>;
   else k = reduce_planes_kernel<T, VEC, G, 1>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<<<(unsigned)grid, 32 * G, smem, st>>>(x, B, C, HW, sp, ap, keys, spi, total);
+  k<<<(unsigned)grid, 32 * G, smem, st>>>(x, B, C, HW, sp, ap, keys, total_vec, total);
   MCAQ_LAUNCH_CHECK();
   return 0;
 }

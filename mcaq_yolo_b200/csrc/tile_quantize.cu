@@ -250,6 +250,9 @@ tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
       for (int s = 0; s < NSEG; ++s) cdst[s] = cpack[s];
     }
   };
+#if MCAQ_L2_HINTS
+  const unsigned long long l2pol = l2_policy_evict_first();
+#endif
   if (nch == QV_CHUNK) {
     // full chunk (the common case): no per-channel predicates, the whole channel walk unrolled so
     // the table offsets are immediates
@@ -257,7 +260,11 @@ tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
     for (int c0 = 0; c0 < QV_CHUNK; c0 += QV_UNROLL) {
       uint4 raw[QV_UNROLL];
 #pragma unroll
+#if MCAQ_L2_HINTS
+      for (int u = 0; u < QV_UNROLL; ++u) { raw[u] = ldg_noalloc_hint(xb, l2pol); xb += sb; }
+#else
       for (int u = 0; u < QV_UNROLL; ++u) { raw[u] = ldg_noalloc(xb); xb += sb; }
+#endif
 #pragma unroll
       for (int u = 0; u < QV_UNROLL; ++u) { emit(raw[u], c0 + u, yb); yb += sb; }
     }
