@@ -340,6 +340,8 @@ MCAQ_API void mcaq_debug_morph_threads(int n);
 /* debug / tests: 1 = route the training forward / backward through the scalar kernels even when the
  * vector path applies (the two must agree: y and dx bit for bit) */
 MCAQ_API void mcaq_debug_train_scalar(int on);
+/* Tuning aid: channels per CTA of the inference quantise sweep (8 / 16; 0 = the built-in choice). */
+MCAQ_API void mcaq_debug_k3_chunk(int ch);
 
 /* split policy of the morphology kernel: 0 (default) throughput -- one CTA per image unless the batch
  * is too small to fill half the GPU (for callers that keep several launches in flight); 1 latency --

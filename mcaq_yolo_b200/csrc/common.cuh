@@ -228,6 +228,7 @@ __device__ __forceinline__ float2 quant_code_fast2(float2 x, float scale, float 
   const float2 q0 = fmul2(x, r2);
   const float2 r = ffma2(make_float2(-q0.x, -q0.y), s2, x);
   const float2 t = fadd2(ffma2(r, r2, q0), splat2(zp));
+  // (rint as two packed adds of 1.5 * 2^23 instead of two FRND measured no faster: profiles/r02_k3_variants.txt)
   return make_float2(fminf(fmaxf(rintf(t.x), qmin), qmax), fminf(fmaxf(rintf(t.y), qmin), qmax));
 }
 __device__ __forceinline__ float2 dequant2(float2 q, float scale, float zp) {

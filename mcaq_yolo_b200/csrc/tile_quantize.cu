@@ -173,23 +173,24 @@ __device__ __forceinline__ float2 qparams_from_ranges(const QRanges& rg, int C, 
   return make_float2(scale, fminf(fmaxf(zp, qmin), qmax));
 }
 
-template <typename T, int VEC, bool HAS_MASK, bool CODES>
+template <typename T, int VEC, bool HAS_MASK, bool CODES, int CH>
 __global__ void __launch_bounds__(QV_THREADS, K3_MINB)
 tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
                          const float* __restrict__ bit_map, const float2* __restrict__ qtable,
                          const float* __restrict__ mask, int8_t* __restrict__ codes, bool inplace,
                          QRanges rg) {
   constexpr int NSEG = VEC / 4;
-  __shared__ float4 tab[7 * QV_ROW];               // {scale, zero_point, RN(1/scale), -}
-  const int c_begin = blockIdx.y * QV_CHUNK;
-  const int nch = min(QV_CHUNK, g.C - c_begin);
-  for (int i = threadIdx.x; i < 7 * QV_CHUNK; i += QV_THREADS) {
-    const int bi = i / QV_CHUNK, cl = i - bi * QV_CHUNK;
+  constexpr int UN = QV_UNROLL < CH ? QV_UNROLL : CH;
+  __shared__ float4 tab[7 * (CH + 1)];               // {scale, zero_point, RN(1/scale), -}
+  const int c_begin = blockIdx.y * CH;
+  const int nch = min(CH, g.C - c_begin);
+  for (int i = threadIdx.x; i < 7 * CH; i += QV_THREADS) {
+    const int bi = i / CH, cl = i - bi * CH;
     if (cl < nch) {
       float2 p;
       if (qtable) p = __ldg(qtable + (long long)bi * g.C + c_begin + cl);
       else p = qparams_from_ranges(rg, g.C, c_begin + cl, bi);
-      tab[bi * QV_ROW + cl] = make_float4(p.x, p.y, __frcp_rn(p.x), 0.f);
+      tab[bi * (CH + 1) + cl] = make_float4(p.x, p.y, __frcp_rn(p.x), 0.f);
     }
   }
   __syncthreads();
@@ -209,7 +210,7 @@ tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
     float bf = rintf(__ldg(bit_map + ((long long)b * g.Ht + ty) * g.Wt + tx));
     bf = fminf(fmaxf(bf, 2.f), 8.f);
     const int bidx = (int)bf - 2;
-    trow[s] = bidx * QV_ROW;
+    trow[s] = bidx * (CH + 1);
     bit_limits(bidx, qmin[s], qmax[s]);
     if (HAS_MASK) {
       const float4 mv = __ldg(reinterpret_cast<const float4*>(mask + (long long)b * g.HW + pix) + s);
@@ -253,36 +254,36 @@ tile_quantize_vec_kernel(const T* __restrict__ x, T* __restrict__ y, QGeom g,
 #if MCAQ_L2_HINTS
   const unsigned long long l2pol = l2_policy_evict_first();
 #endif
-  if (nch == QV_CHUNK) {
+  if (nch == CH) {
     // full chunk (the common case): no per-channel predicates, the whole channel walk unrolled so
     // the table offsets are immediates
 #pragma unroll
-    for (int c0 = 0; c0 < QV_CHUNK; c0 += QV_UNROLL) {
-      uint4 raw[QV_UNROLL];
+    for (int c0 = 0; c0 < CH; c0 += UN) {
+      uint4 raw[UN];
 #pragma unroll
 #if MCAQ_L2_HINTS
-      for (int u = 0; u < QV_UNROLL; ++u) { raw[u] = ldg_noalloc_hint(xb, l2pol); xb += sb; }
+      for (int u = 0; u < UN; ++u) { raw[u] = ldg_noalloc_hint(xb, l2pol); xb += sb; }
 #else
-      for (int u = 0; u < QV_UNROLL; ++u) { raw[u] = ldg_noalloc(xb); xb += sb; }
+      for (int u = 0; u < UN; ++u) { raw[u] = ldg_noalloc(xb); xb += sb; }
 #endif
 #pragma unroll
-      for (int u = 0; u < QV_UNROLL; ++u) { emit(raw[u], c0 + u, yb); yb += sb; }
+      for (int u = 0; u < UN; ++u) { emit(raw[u], c0 + u, yb); yb += sb; }
     }
     return;
   }
 #pragma unroll 1
-  for (int c0 = 0; c0 < nch; c0 += QV_UNROLL) {
-    uint4 raw[QV_UNROLL];
+  for (int c0 = 0; c0 < nch; c0 += UN) {
+    uint4 raw[UN];
 #pragma unroll
-    for (int u = 0; u < QV_UNROLL; ++u)
+    for (int u = 0; u < UN; ++u)
       if (c0 + u < nch) raw[u] = ldg_noalloc(xb + u * sb);
 #pragma unroll
-    for (int u = 0; u < QV_UNROLL; ++u) {
+    for (int u = 0; u < UN; ++u) {
       if (c0 + u >= nch) break;
       emit(raw[u], c0 + u, yb + u * sb);
     }
-    xb += QV_UNROLL * sb;
-    yb += QV_UNROLL * sb;
+    xb += UN * sb;
+    yb += UN * sb;
   }
 }
 
@@ -442,6 +443,15 @@ spatial_quant_compat_kernel(const float* __restrict__ x, const float* __restrict
   }
 }
 
+static int g_k3_chunk = 0;     // tuning aid (mcaq_debug_k3_chunk): 0 = heuristic, else 8 / 16
+static int k3_chunk(unsigned gx, int C) {
+  if (g_k3_chunk == 8 || g_k3_chunk == 16) return g_k3_chunk;
+  // measured (profiles/r02_k3_chunk.txt): 16 everywhere except where that leaves fewer than two CTAs per SM
+  // (C5 bf16 at batch 64: 208 CTAs), where 8 is 13 % faster; 32 is never ahead
+  const long long ctas = (long long)gx * ((C + QV_CHUNK - 1) / QV_CHUNK);
+  return ctas < 2LL * 148 ? 8 : QV_CHUNK;
+}
+
 template <typename T, int VEC>
 static int launch_quant(const T* x, T* y, int B, int C, int H, int W, const float* bit_map, int Ht, int Wt,
                         const float* qtable, const float* mask, int8_t* codes, cudaStream_t st,
@@ -450,13 +460,24 @@ static int launch_quant(const T* x, T* y, int B, int C, int H, int W, const floa
   const bool inplace = (const void*)x == (const void*)y;
   const float2* qt = (const float2*)qtable;
   if (VEC > 1) {
-    dim3 grid((unsigned)((g.nvec_total + QV_THREADS - 1) / QV_THREADS), (unsigned)((C + QV_CHUNK - 1) / QV_CHUNK));
-    if (mask) {
-      if (codes) tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), true, true><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
-      else tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), true, false><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
+    constexpr int V = VEC > 1 ? VEC : 4;
+    const unsigned gx = (unsigned)((g.nvec_total + QV_THREADS - 1) / QV_THREADS);
+    if (codes) {
+      dim3 grid(gx, (unsigned)((C + QV_CHUNK - 1) / QV_CHUNK));
+      if (mask) tile_quantize_vec_kernel<T, V, true, true, QV_CHUNK><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
+      else tile_quantize_vec_kernel<T, V, false, true, QV_CHUNK><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
     } else {
-      if (codes) tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), false, true><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
-      else tile_quantize_vec_kernel<T, (VEC > 1 ? VEC : 4), false, false><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);
+      // channels per CTA: fewer on the small scales, so that the grid still covers every SM a few times over
+      const int ch = k3_chunk(gx, C);
+#define MCAQ_K3_LAUNCH(CHV)                                                                                              \
+  do {                                                                                                                   \
+    dim3 grid(gx, (unsigned)((C + CHV - 1) / CHV));                                                                      \
+    if (mask) tile_quantize_vec_kernel<T, V, true, false, CHV><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg); \
+    else tile_quantize_vec_kernel<T, V, false, false, CHV><<<grid, QV_THREADS, 0, st>>>(x, y, g, bit_map, qt, mask, codes, inplace, rg);   \
+  } while (0)
+      if (ch == 8) MCAQ_K3_LAUNCH(8);
+      else MCAQ_K3_LAUNCH(16);
+#undef MCAQ_K3_LAUNCH
     }
     MCAQ_LAUNCH_CHECK();
     return 0;
@@ -662,3 +683,5 @@ extern "C" void launch_spatial_quantization(const float* input, const float* bit
   g_level0_status = mcaq_spatial_quantization(input, bit_map, min_vals, max_vals, mask, output, N, C, H, W, tile_h,
                                               tile_w, n_tiles_h, n_tiles_w, stream);
 }
+
+extern "C" void mcaq_debug_k3_chunk(int ch) { mcaq::g_k3_chunk = ch; }

@@ -55,10 +55,10 @@ CASES = [
     (r"train_bwd_vec_kernelI13__nv_bfloat16Li8ELb0ELb1E", 2 * 4, 2, 0),
     (r"train_bwd_vec_kernelI13__nv_bfloat16Li8ELb0ELb0E", 4 * 4, 2, 0),
     # inference: unrolled 16-channel walk + generic 8-channel loop, 1 quantisation per element
-    (r"tile_quantize_vec_kernelIfLi4ELb1ELb0E", (16 + 8) * 2, 1, 0),
-    (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb1ELb0E", (16 + 8) * 4, 1, 0),
-    (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb0ELb0E", (16 + 8) * 4, 1, 0),
-    (r"tile_quantize_vec_kernelIfLi4ELb0ELb1E", (16 + 8) * 2, 1, 0),
+    (r"tile_quantize_vec_kernelIfLi4ELb1ELb0ELi16E", (16 + 8) * 2, 1, 0),
+    (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb1ELb0ELi16E", (16 + 8) * 4, 1, 0),
+    (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb0ELb0ELi16E", (16 + 8) * 4, 1, 0),
+    (r"tile_quantize_vec_kernelIfLi4ELb0ELb1ELi16E", (16 + 8) * 2, 1, 0),
 ]
 
 
@@ -70,7 +70,7 @@ def test_ffma2_count_is_exactly_the_source(sass, pattern, pairs, quants, extra):
 
 
 def test_packed_instructions_present(sass):
-    for pattern in (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb1ELb0E", r"train_fwd_vec_kernelIfLi4ELb1ELb0E"):
+    for pattern in (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb1ELb0ELi16E", r"train_fwd_vec_kernelIfLi4ELb1ELb0E"):
         assert count(sass, pattern, "FMUL2") > 0 and count(sass, pattern, "FADD2") > 0
 
 
@@ -101,7 +101,7 @@ def test_register_caps_of_the_hot_kernels(sass):
     # Spill-free builds exist (K3_UNROLL=4, or two CTAs per SM at 125 registers) and were MEASURED slower on B200
     # (profiles/r02_k3_variants.txt: bf16 C3 5055 GB/s with the 128-byte frame vs 4907 / 4312 GB/s without it): ptxas
     # spills values that are cold in the channel walk, the eight loads in flight are what pays.
-    assert all(st <= (256 if re.search(r"Lb[01]ELb1EEEv", n) else 160) for n, (_, st) in k3.items())
+    assert all(st <= (256 if re.search(r"Lb[01]ELb1ELi\d+EEEv", n) else 160) for n, (_, st) in k3.items())
     kt = {n: v for n, v in _res_usage("tile_quantize_train.o").items() if "_vec_kernel" in n}
     assert kt and all(r <= 128 and st <= 64 for r, st in kt.values())
 
@@ -109,6 +109,6 @@ def test_register_caps_of_the_hot_kernels(sass):
 def test_bandwidth_kernels_use_128_bit_accesses(sass):
     txt = subprocess.run(["cuobjdump", "-sass", os.path.join(LIBDIR, "reduce_planes.o")], capture_output=True, text=True).stdout
     assert re.search(r"LDG\.E(\.\w+)*\.128", txt), "K1 loads 16-byte vectors"
-    for pattern in (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb1ELb0E", r"train_bwd_vec_kernelIfLi4ELb1ELb0E"):
+    for pattern in (r"tile_quantize_vec_kernelI13__nv_bfloat16Li8ELb1ELb0ELi16E", r"train_bwd_vec_kernelIfLi4ELb1ELb0E"):
         name, = [n for n in sass if re.search(pattern, n)]
         assert re.search(r"LD(G)?\.E(\.\w+)*\.128", sass[name]) and re.search(r"STG\.E(\.\w+)*\.128", sass[name]), pattern
