@@ -143,7 +143,7 @@ class MorphologicalComplexityAnalyzer(nn.Module):
         if needs_grad:
             # training: the inference kernel forward (raw MLP output kept), native backward through clamp, bilateral
             # filter and the MLP with its LayerNorms (csrc/train_nets.cu) -- two launches instead of ~150
-            flat = TN.flat_params(self.complexity_mlp.parameters())
+            flat = TN.flat_params(self.complexity_mlp.parameters(), owner=self.complexity_mlp)
             cmap = TN.ComplexityTrainFn.apply(phi, flat, K.pack_complexity_mlp(self.complexity_mlp),
                                               K.device_constants(features.device))
         else:
@@ -254,7 +254,7 @@ class ComplexityToBitMappingNetwork(nn.Module):
             # train mode: BatchNorm batch statistics over all B*ht*wt tiles (of all ranks when `stat_exchange`
             # is set), running statistics updated, one cluster launch per direction (csrc/train_nets.cu)
             seq = self.mapping_network
-            bits = TN.MapperTrainFn.apply(c.reshape(-1), TN.flat_params(seq.parameters()), (seq[1], seq[4], seq[7]),
+            bits = TN.MapperTrainFn.apply(c.reshape(-1), TN.flat_params(seq.parameters(), owner=seq), (seq[1], seq[4], seq[7]),
                                           temperature, self.min_bits, self.max_bits, self.stat_exchange).reshape(B, H, W)
             if not return_continuous:
                 bits = bits + (torch.round(bits) - bits).detach()
@@ -296,7 +296,7 @@ class LearnedSoftMask(nn.Module):
         if self.hidden == 8 and self.kernel_size == 5:
             # training: inference kernel forward, native backward (smoothing / upsampling transposed, softmax, the
             # two convolutions) -- gradients to the bit map and the four parameter tensors
-            flat = TN.flat_params(self.net.parameters())
+            flat = TN.flat_params(self.net.parameters(), owner=self.net)
             return TN.SoftMaskTrainFn.apply(bit_map, flat, abs_plane, C, K.pack_soft_mask(self)).unsqueeze(1)
         Ht, Wt = bit_map.shape[-2:]
         with torch.no_grad():

@@ -8,6 +8,7 @@ CUDA tensors only; nothing synchronises (graph-capturable)."""
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import torch
 
@@ -17,9 +18,33 @@ from . import constants as K
 CMLP_PARAMS, MAPPER_PARAMS, SOFTMASK_PARAMS = 2881, 4609, 170
 
 
-def flat_params(params) -> torch.Tensor:
-    """torch.cat of the (flattened) parameters: differentiable, gradients flow back to each parameter."""
-    return torch.cat([p.reshape(-1).float() for p in params])
+_FLAT_CACHE = weakref.WeakKeyDictionary()
+_COUNTS = {}
+
+
+def flat_params(params, owner=None) -> torch.Tensor:
+    """torch.cat of the (flattened) parameters: differentiable, gradients flow back to each parameter.
+
+    With `owner` (the module holding the parameters) the concatenation is shared by every forward of one training
+    step: the three scales of a step call the same nets, and one shared node means autograd sums their three flat
+    gradients (two adds) and splits ONCE, instead of accumulating 3 x P per-parameter slices (the 83 small adds of
+    profiles/r02_train_step_launches.txt).  The shared node is dropped as soon as a backward pass reaches it, or
+    when any parameter changes (optimizer step: `_version`; re-assignment: data pointer)."""
+    params = list(params)
+    if owner is None or not torch.is_grad_enabled():
+        return torch.cat([p.reshape(-1).float() for p in params])
+    key = tuple((p.data_ptr(), p._version, p.requires_grad) for p in params)
+    hit = _FLAT_CACHE.get(owner)          # kept outside the module: a graph tensor in its __dict__ would break deepcopy
+    if hit is not None and hit[0] == key and not hit[2]["consumed"]:
+        return hit[1]
+    flat = torch.cat([p.reshape(-1).float() for p in params])
+    state = {"consumed": False}
+    if flat.requires_grad:
+        def _mark(_g, state=state):
+            state["consumed"] = True
+        flat.register_hook(_mark)
+    _FLAT_CACHE[owner] = (key, flat, state)
+    return flat
 
 
 def _xchg_args(xchg):
@@ -151,8 +176,12 @@ def bit_map_losses(bit_maps, target_bits: float, group=None):
     of the per-edge mean total variation.  With a process group the per-scale means are taken over the GLOBAL batch
     (one all-reduce of 2 x len(bit_maps) floats; the gradient stays local and is scaled by the global count)."""
     stats = torch.stack([BitStatsFn.apply(b) for b in bit_maps])             # (S, 2)
-    counts = torch.tensor([[b.numel(), b.shape[0] * ((b.shape[1] - 1) * b.shape[2] + b.shape[1] * (b.shape[2] - 1))]
-                           for b in bit_maps], device=stats.device, dtype=torch.float32)
+    ckey = (tuple(tuple(b.shape) for b in bit_maps), stats.device)
+    counts = _COUNTS.get(ckey)          # cached: no host-to-device copy in the steady state (graph-capturable)
+    if counts is None:
+        counts = torch.tensor([[b.numel(), b.shape[0] * ((b.shape[1] - 1) * b.shape[2] + b.shape[1] * (b.shape[2] - 1))]
+                               for b in bit_maps], device=stats.device, dtype=torch.float32)
+        _COUNTS[ckey] = counts
     import torch.distributed as dist
     if group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         stats = _AllReduceSum.apply(stats, group)

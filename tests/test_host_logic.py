@@ -283,3 +283,32 @@ def test_training_exchanges_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)], res
+
+
+def test_flat_params_is_shared_within_a_step_and_dropped_after_backward():
+    """train_nets.flat_params(owner=...): one concatenation per training step (the three scales share the node, so
+    autograd splits the summed flat gradient once), rebuilt after a backward pass or a parameter update; gradients
+    equal the per-call concatenation's; the module stays deep-copyable."""
+    import copy
+    import torch
+    from mcaq_yolo_b200 import train_nets as TN
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 1))
+    w = [torch.randn(19) for _ in range(3)]
+    f = [TN.flat_params(m.parameters(), owner=m) for _ in range(3)]
+    assert f[0] is f[1] and f[1] is f[2]
+    sum((fi * wi).sum() for fi, wi in zip(f, w)).backward()
+    got = [p.grad.clone() for p in m.parameters()]
+    for p in m.parameters():
+        p.grad = None
+    sum((TN.flat_params(m.parameters()) * wi).sum() for wi in w).backward()        # no owner: a fresh cat per call
+    for a, p in zip(got, m.parameters()):
+        assert torch.allclose(a, p.grad, rtol=1e-6, atol=1e-6)
+    f3 = TN.flat_params(m.parameters(), owner=m)
+    assert f3 is not f[0]                                   # the backward pass consumed the shared node
+    copy.deepcopy(m)                                        # nothing graph-attached lives in the module
+    with torch.no_grad():
+        assert not TN.flat_params(m.parameters(), owner=m).requires_grad
+        m[0].weight.add_(1.0)                               # what an optimizer step does
+    f4 = TN.flat_params(m.parameters(), owner=m)
+    assert f4 is not f3 and torch.equal(f4[:12], m[0].weight.reshape(-1))

@@ -119,24 +119,41 @@ teach = [[torch.randn(B, C, H, W, device=dev) for C, H, W in shapes] for _ in ra
 gouts = [[torch.randn(B, C, H, W, device=dev).to(dt) * 1e-3 for C, H, W in shapes] for _ in range(NSETS)]
 
 
-def train_step(i, fused_kd=True):
+SCALE_STREAMS = [torch.cuda.Stream() for _ in shapes]
+
+
+def train_step(i, fused_kd=True, scale_streams=False):
+    """One step.  `scale_streams`: each scale's hook (and therefore, through autograd's stream affinity, its
+    backward) runs on its own stream, like the three scale streams of the inference path."""
+    from mcaq_yolo_b200 import train_nets as TN
     k = i % NSETS
     for p in params:
         p.grad = None
-    loss = 0.0
-    bits_all = []
-    for x0, t, go, q in zip(feats[k], teach[k], gouts[k], quants):
-        x = x0.detach().requires_grad_(True)
-        q.kd_teacher = t if fused_kd else None
-        r = M.mcaq_hook_forward(x, analyzer, mapper, q, temperature=1.0, training=True)
-        y = r["features_q"]
-        kd = r.get("kd_feature_loss")
-        if kd is None:
-            kd = torch.nn.functional.mse_loss(y.float(), t)
-        loss = loss + (y * go).sum().float() + kd / len(shapes)          # stand-in for the detection loss + KD
+    main = torch.cuda.current_stream()
+    partial, bits_all = [], []
+    for si, (x0, t, go, q) in enumerate(zip(feats[k], teach[k], gouts[k], quants)):
+        st = SCALE_STREAMS[si] if scale_streams else main
+        if scale_streams:
+            st.wait_stream(main)
+        with torch.cuda.stream(st):
+            x = x0.detach().requires_grad_(True)
+            q.kd_teacher = t if fused_kd else None
+            r = M.mcaq_hook_forward(x, analyzer, mapper, q, temperature=1.0, training=True)
+            y = r["features_q"]
+            kd = r.get("kd_feature_loss")
+            if kd is None:
+                kd = torch.nn.functional.mse_loss(y.float(), t)
+            part = (y * go).sum().float() + kd / len(shapes)      # stand-in for the detection loss + KD
+        if scale_streams:
+            part.record_stream(main)
+            r["bit_map"].record_stream(main)
+        partial.append(part)
         bits_all.append(r["bit_map"])
-    avg_bits = torch.cat([b.reshape(-1) for b in bits_all]).mean()
-    loss = loss + 0.1 * (avg_bits - 4.0) ** 2                                # Lbit (models/mcaq_yolo.py:113-118)
+    if scale_streams:
+        for st in SCALE_STREAMS:
+            main.wait_stream(st)
+    _, lbit, _ = TN.bit_map_losses(bits_all, 4.0)                            # Lbit (models/mcaq_yolo.py:113-118)
+    loss = torch.stack(partial).sum() + 0.1 * lbit
     loss.backward()
     return loss
 
@@ -155,14 +172,14 @@ def time_step(fused_kd):
     return e0.elapsed_time(e1) / a.step_iters, ops.LAUNCHES // a.step_iters
 
 
-def time_step_graph(fused_kd):
+def time_step_graph(fused_kd, scale_streams=False):
     """Whole training step (forward, loss, backward) of one input set captured in a CUDA graph per
-    set and replayed: removes the host launch cost of the ~10^3 small autograd kernels."""
+    set and replayed: removes the host launch cost of the small autograd kernels."""
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for i in range(3):
-            train_step(i, fused_kd)
+            train_step(i, fused_kd, scale_streams)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     graphs = []
@@ -171,7 +188,7 @@ def time_step_graph(fused_kd):
             p.grad = None
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            train_step(k, fused_kd)
+            train_step(k, fused_kd, scale_streams)
         graphs.append(g)
     for g in graphs:
         g.replay()
@@ -193,6 +210,12 @@ try:
 except Exception as e:          # noqa: BLE001 -- report, the eager number stands
     graph_err = f"{type(e).__name__}: {str(e)[:200]}"
     torch.cuda.synchronize()
+graph_ss_ms, graph_ss_err = None, None
+try:
+    graph_ss_ms = time_step_graph(True, scale_streams=True)
+except Exception as e:          # noqa: BLE001
+    graph_ss_err = f"{type(e).__name__}: {str(e)[:200]}"
+    torch.cuda.synchronize()
 ms_f, launches = time_step(True)
 ms_u, _ = time_step(False)
 elems = sum(C * H * W for C, H, W in shapes)
@@ -203,10 +226,14 @@ out = {"what": "MCAQ training hot path (K1 + phi + nets + fractional quantise fw
        "train_step_ms_cuda_graph": None if graph_ms is None else round(graph_ms, 3),
        "images_per_s_cuda_graph": None if graph_ms is None else round(B / graph_ms * 1e3, 1),
        "cuda_graph_error": graph_err,
+       "train_step_ms_cuda_graph_scale_streams": None if graph_ss_ms is None else round(graph_ss_ms, 3),
+       "images_per_s_cuda_graph_scale_streams": None if graph_ss_ms is None else round(B / graph_ss_ms * 1e3, 1),
+       "cuda_graph_scale_streams_error": graph_ss_err,
        "native_launches_per_step": launches,
        "algorithmic_bytes_per_step": 6 * es * elems * B,
        "note": "step = 3 hooks forward (train mode: EMA ranges, continuous bits, soft mask) + loss + backward; the three "
-               "tiny networks run in torch autograd (host-launch bound), the HBM sweeps are native kernels"}
+               "tile-level networks, their batch statistics and the bit-map losses are native kernels behind autograd "
+               "Functions (train_nets.py); *_scale_streams: one stream per scale, forward and backward"}
 line = json.dumps(out)
 print(line)
 if a.out:
