@@ -342,6 +342,8 @@ MCAQ_API void mcaq_debug_morph_threads(int n);
 MCAQ_API void mcaq_debug_train_scalar(int on);
 /* Tuning aid: channels per CTA of the inference quantise sweep (8 / 16; 0 = the built-in choice). */
 MCAQ_API void mcaq_debug_k3_chunk(int ch);
+/* Tuning aid: cluster size of the train-mode mapper kernels (8 or 16; 0 = probe the device once). */
+MCAQ_API void mcaq_debug_mapper_cluster(int n);
 
 /* split policy of the morphology kernel: 0 (default) throughput -- one CTA per image unless the batch
  * is too small to fill half the GPU (for callers that keep several launches in flight); 1 latency --

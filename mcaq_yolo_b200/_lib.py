@@ -54,6 +54,7 @@ PROTOTYPES = {
                                                 c_void_p, c_void_p, c_void_p]),
     "mcaq_debug_train_scalar": (None, [c_int]),
     "mcaq_debug_k3_chunk": (None, [c_int]),
+    "mcaq_debug_mapper_cluster": (None, [c_int]),
     "launch_spatial_quantization": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mcaq_spatial_quantization": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -127,6 +128,8 @@ def load():
             lib.mcaq_debug_morph_threads(int(os.environ["MCAQ_K2_THREADS"]))
         if os.environ.get("MCAQ_K2_SPLIT"):        # tuning aid: force the morphology kernel's cluster split
             lib.mcaq_debug_cluster_split(int(os.environ["MCAQ_K2_SPLIT"]))
+        if os.environ.get("MCAQ_MAPPER_CLUSTER"):
+            lib.mcaq_debug_mapper_cluster(int(os.environ["MCAQ_MAPPER_CLUSTER"]))
         if os.environ.get("MCAQ_K3_CHUNK"):
             lib.mcaq_debug_k3_chunk(int(os.environ["MCAQ_K3_CHUNK"]))
         _lib = lib

@@ -220,9 +220,9 @@ cmlp_bwd_kernel(const float* __restrict__ phi, const float* __restrict__ gcraw, 
 // =================================================================================================
 // mapper with train-mode BatchNorm: one cluster of MAP_CL CTAs, rows split over the CTAs, a warp per row
 // =================================================================================================
-constexpr int MAP_CL = 8;
+constexpr int MAP_CL = 16;                                     // largest cluster (non-portable size, opted into); 8 is the fallback
 constexpr int MAP_NT = 512;
-// scratch per row: Z1[32] Z2[64] Z3[32] (forward, kept for backward) | GY3[32] GY2[64] GY1[32] (backward)
+// scratch per row: Z1[32] Z2[64] Z3[32] (forward, kept for backward) | GY3[32] (later GY1) GY2[64] (backward)
 constexpr int MP_SCR = 256;
 constexpr int GATH = 132;                                      // gather row: up to 2 * 64 + 1 values per CTA
 struct MapArgs {
@@ -240,6 +240,13 @@ struct MapArgs {
 constexpr int MAP_SM_WORK = 0, MAP_SM_GATH = 392, MAP_SM_MEAN = MAP_SM_GATH + MAP_CL * GATH, MAP_SM_VAR = MAP_SM_MEAN + 64;
 constexpr int MAP_SM_W3 = MAP_SM_VAR + 64, MAP_SM_W6 = MAP_SM_W3 + 64 * 33, MAP_SM_ROW = MAP_SM_W6 + 32 * 65;
 constexpr int MAP_SM_FB = MAP_SM_ROW + (MAP_NT / 32) * 64, MAP_SM_FLOATS = MAP_SM_FB + 2112;
+// Row cache: when a CTA's share of the rows fits, the per-row record lives in shared memory for the whole kernel
+// (the statistics passes and the next layer re-read it at LDS latency instead of L2's); the forward still stores the
+// pre-activations to the global scratch for the backward launch, the backward loads them once and keeps its GY slots
+// on chip.  GY1 reuses GY3's slot (dead after the layer-3 phase), so a cached row is 224 floats.
+constexpr int MAP_ROWF = 224;
+constexpr int MAP_GY1 = 128;                                   // offset of GY1 (aliases GY3) in both layouts
+constexpr int MAP_ROWS_MAX = (227 * 1024 / 4 - MAP_SM_FLOATS) / MAP_ROWF;      // rows per CTA that fit (218)
 
 // exchange of a short vector with the other GPU ranks by cluster CTA 0 (peer_exchange.cuh protocol, bounded wait):
 // returns in xm[0..n) the per-rank vectors' rank-ordered combination computed by `merge`.  A timed-out exchange
@@ -408,7 +415,7 @@ __device__ __forceinline__ void update_running(float* rm, float* rv, const float
 }
 
 __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs A) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   cg::cluster_group cl = cg::this_cluster();
   float* gather = sm + MAP_SM_GATH;
   float* mean = sm + MAP_SM_MEAN;
@@ -424,6 +431,11 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs 
   float* rb = sm + MAP_SM_ROW + warp * 64;
   const int rank = (int)cl.block_rank();
   const int r0 = min(rank * A.rpc, A.N), r1 = min(r0 + A.rpc, A.N);
+  const bool cached = A.rpc <= MAP_ROWS_MAX;                   // launch_mapper sized the dynamic smem accordingly
+  float* rows = sm + MAP_SM_FLOATS;
+  // record of row r as this kernel re-reads it, and its leading dimension
+  const int ld = cached ? MAP_ROWF : MP_SCR;
+  float* zb = cached ? rows - (long long)r0 * MAP_ROWF : A.scratch;
   stage_matrix(W3, W3s, 64, 32);
   stage_matrix(W6, W6s, 32, 64);
   // layer 1: unit = lane
@@ -433,11 +445,13 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs 
       const float c = fminf(fmaxf(__ldg(A.c + r), 0.f), 1.f);
       float a = 0.f;
       a = fmaf(w0, c, a); a = fmaf(w1, __fmul_rn(c, c), a); a = fmaf(w2, log1p_f64(c), a);
-      A.scratch[(long long)r * MP_SCR + lane] = __fadd_rn(a, bb);
+      const float z = __fadd_rn(a, bb);
+      A.scratch[(long long)r * MP_SCR + lane] = z;
+      if (cached) zb[(long long)r * ld + lane] = z;
     }
   }
   __syncthreads();
-  float ntot = batch_stats(cl, A.scratch, MP_SCR, r0, r1, 32, sm, gather, A.px, mean, var);
+  float ntot = batch_stats(cl, zb, ld, r0, r1, 32, sm, gather, A.px, mean, var);
   if (rank == 0) {
     update_running(A.rm[0], A.rv[0], mean, var, ntot, 32, A.momentum);
     if (threadIdx.x < 3 && A.nbt[threadIdx.x]) *A.nbt[threadIdx.x] += 1;
@@ -448,19 +462,21 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs 
     const float mu = mean[lane], rs = rstd_of(var[lane], A.eps), gg = __ldg(g0 + lane), ee = __ldg(be0 + lane);
     const float ba = __ldg(b3 + lane), bb = __ldg(b3 + lane + 32);
     for (int r = r0 + warp; r < r1; r += nwarps) {
-      float* s = A.scratch + (long long)r * MP_SCR;
+      float* s = zb + (long long)r * ld;
+      float* sg = A.scratch + (long long)r * MP_SCR;
       __syncwarp();
       rb[lane] = bn_relu1(s[lane], mu, rs, gg, ee);
       __syncwarp();
-      float za = 0.f, zb = 0.f;
+      float za = 0.f, zc = 0.f;
 #pragma unroll 8
-      for (int k = 0; k < 32; ++k) { const float h = rb[k]; za = fmaf(W3s[lane * 33 + k], h, za); zb = fmaf(W3s[(lane + 32) * 33 + k], h, zb); }
-      s[32 + lane] = __fadd_rn(za, ba);
-      s[64 + lane] = __fadd_rn(zb, bb);
+      for (int k = 0; k < 32; ++k) { const float h = rb[k]; za = fmaf(W3s[lane * 33 + k], h, za); zc = fmaf(W3s[(lane + 32) * 33 + k], h, zc); }
+      za = __fadd_rn(za, ba); zc = __fadd_rn(zc, bb);
+      sg[32 + lane] = za; sg[64 + lane] = zc;
+      if (cached) { s[32 + lane] = za; s[64 + lane] = zc; }
     }
   }
   __syncthreads();
-  ntot = batch_stats(cl, A.scratch + 32, MP_SCR, r0, r1, 64, sm, gather, A.px, mean, var);
+  ntot = batch_stats(cl, zb + 32, ld, r0, r1, 64, sm, gather, A.px, mean, var);
   if (rank == 0) {
     update_running(A.rm[1], A.rv[1], mean, var, ntot, 64, A.momentum);
     if (threadIdx.x < 64) { A.stats[32 + threadIdx.x] = mean[threadIdx.x]; A.stats[160 + threadIdx.x] = var[threadIdx.x]; }
@@ -471,7 +487,7 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs 
     const float mub = mean[lane + 32], rsb = rstd_of(var[lane + 32], A.eps), gb = __ldg(g3 + lane + 32), eb = __ldg(be3 + lane + 32);
     const float bb = __ldg(b6 + lane);
     for (int r = r0 + warp; r < r1; r += nwarps) {
-      float* s = A.scratch + (long long)r * MP_SCR;
+      float* s = zb + (long long)r * ld;
       __syncwarp();
       rb[lane] = bn_relu1(s[32 + lane], mua, rsa, ga, ea);
       rb[lane + 32] = bn_relu1(s[64 + lane], mub, rsb, gb, eb);
@@ -479,11 +495,13 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs 
       float z = 0.f;
 #pragma unroll 16
       for (int k = 0; k < 64; ++k) z = fmaf(W6s[lane * 65 + k], rb[k], z);
-      s[96 + lane] = __fadd_rn(z, bb);
+      z = __fadd_rn(z, bb);
+      A.scratch[(long long)r * MP_SCR + 96 + lane] = z;
+      if (cached) s[96 + lane] = z;
     }
   }
   __syncthreads();
-  ntot = batch_stats(cl, A.scratch + 96, MP_SCR, r0, r1, 32, sm, gather, A.px, mean, var);
+  ntot = batch_stats(cl, zb + 96, ld, r0, r1, 32, sm, gather, A.px, mean, var);
   if (rank == 0) {
     update_running(A.rm[2], A.rv[2], mean, var, ntot, 32, A.momentum);
     if (threadIdx.x < 32) { A.stats[96 + threadIdx.x] = mean[threadIdx.x]; A.stats[224 + threadIdx.x] = var[threadIdx.x]; }
@@ -493,7 +511,7 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs 
     const float mu = mean[lane], rs = rstd_of(var[lane], A.eps), gg = __ldg(g6 + lane), ee = __ldg(be6 + lane);
     const float w9 = __ldg(W9 + lane), bb = __ldg(b9);
     for (int r = r0 + warp; r < r1; r += nwarps) {
-      const float h = bn_relu1(A.scratch[(long long)r * MP_SCR + 96 + lane], mu, rs, gg, ee);
+      const float h = bn_relu1(zb[(long long)r * ld + 96 + lane], mu, rs, gg, ee);
       const float sg = sigmoid_exact(__fadd_rn(wsum(__fmul_rn(w9, h)), bb));
       float bits = __fadd_rn(A.lo, __fmul_rn(__fsub_rn(A.hi, A.lo), sg));
       if (A.use_t) bits = __fmul_rn(bits, A.temperature);
@@ -504,7 +522,7 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_fwd_kernel(const MapArgs 
 }
 
 __global__ void __launch_bounds__(MAP_NT) mapper_train_bwd_kernel(const MapArgs A) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   cg::cluster_group cl = cg::this_cluster();
   float* gather = sm + MAP_SM_GATH;
   float* sv = sm + MAP_SM_MEAN;                                // [s1 64 | s2 64]: BatchNorm backward sums (+ count at [128]... see below)
@@ -522,8 +540,21 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_bwd_kernel(const MapArgs 
   float* rb = sm + MAP_SM_ROW + warp * 64;
   const int rank = (int)cl.block_rank();
   const int r0 = min(rank * A.rpc, A.N), r1 = min(r0 + A.rpc, A.N);
+  const bool cached = A.rpc <= MAP_ROWS_MAX;
+  float* rows = sm + MAP_SM_FLOATS;
+  const int ld = cached ? MAP_ROWF : MP_SCR;
+  float* zb = cached ? rows - (long long)r0 * MAP_ROWF : A.scratch;
   stage_matrix(W3, W3s, 64, 32);
   stage_matrix(W6, W6s, 32, 64);
+  if (cached) {                                                // the forward's pre-activations, once, 16 bytes per load
+    const int nrow = r1 - r0;
+    for (int i = threadIdx.x; i < nrow * 32; i += MAP_NT) {
+      const int rr = i >> 5, q = i & 31;
+      *reinterpret_cast<float4*>(rows + rr * MAP_ROWF + 4 * q) =
+          __ldg(reinterpret_cast<const float4*>(A.scratch + (long long)(r0 + rr) * MP_SCR) + q);
+    }
+    __syncthreads();
+  }
   // ---- head + BN3 sums (units = lane) ----------------------------------------------------------------------
   const float mu3 = __ldg(mean + 96 + lane), rs3 = rstd_of(__ldg(var + 96 + lane), A.eps), g6l = __ldg(g6 + lane), e6l = __ldg(be6 + lane);
   {
@@ -531,7 +562,7 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_bwd_kernel(const MapArgs 
     float dW9 = 0.f, db9 = 0.f, s1 = 0.f, s2 = 0.f;
     flush_begin(fb, 130);                                      // [dW9 32 | db9 | pad | s1 32 | s2 32 | count]
     for (int r = r0 + warp; r < r1; r += nwarps) {
-      float* s = A.scratch + (long long)r * MP_SCR;
+      float* s = zb + (long long)r * ld;
       const float z3 = s[96 + lane];
       const float h = bn_relu1(z3, mu3, rs3, g6l, e6l);
       const float sg = sigmoid_exact(__fadd_rn(wsum(__fmul_rn(w9, h)), bb));
@@ -573,7 +604,7 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_bwd_kernel(const MapArgs 
     float db = 0.f, s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
     flush_begin(fb, 2048 + 32);
     for (int r = r0 + warp; r < r1; r += nwarps) {
-      float* s = A.scratch + (long long)r * MP_SCR;
+      float* s = zb + (long long)r * ld;
       const float xh3 = __fmul_rn(__fsub_rn(s[96 + lane], mu3), rs3);
       const float gz = __fmul_rn(__fmul_rn(g6l, rs3), __fsub_rn(__fsub_rn(s[128 + lane], c1), __fmul_rn(xh3, c2)));
       const float z2a = s[32 + lane], z2b = s[64 + lane];
@@ -626,7 +657,7 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_bwd_kernel(const MapArgs 
     float dba = 0.f, dbb = 0.f, s1 = 0.f, s2 = 0.f;
     flush_begin(fb, 2048 + 64);
     for (int r = r0 + warp; r < r1; r += nwarps) {
-      float* s = A.scratch + (long long)r * MP_SCR;
+      float* s = zb + (long long)r * ld;
       const float xa = __fmul_rn(__fsub_rn(s[32 + lane], mu2a), rs2a), xb = __fmul_rn(__fsub_rn(s[64 + lane], mu2b), rs2b);
       const float gza = __fmul_rn(__fmul_rn(g3a, rs2a), __fsub_rn(__fsub_rn(s[160 + lane], c1a), __fmul_rn(xa, c2a)));
       const float gzb = __fmul_rn(__fmul_rn(g3b, rs2b), __fsub_rn(__fsub_rn(s[192 + lane], c1b), __fmul_rn(xb, c2b)));
@@ -645,7 +676,7 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_bwd_kernel(const MapArgs 
         gh = fmaf(W3s[(j + 32) * 33 + lane], __shfl_sync(0xffffffffu, gzb, j), gh);
       }
       const float gy = h1 > 0.f ? gh : 0.f;
-      s[224 + lane] = gy;
+      s[MAP_GY1 + lane] = gy;
       s1 = __fadd_rn(s1, gy);
       s2 = fmaf(gy, __fmul_rn(__fsub_rn(z1, mu1), rs1), s2);
     }
@@ -674,9 +705,9 @@ __global__ void __launch_bounds__(MAP_NT) mapper_train_bwd_kernel(const MapArgs 
     __syncthreads();
     flush_begin(fb, 128);
     for (int r = r0 + warp; r < r1; r += nwarps) {
-      const float* s = A.scratch + (long long)r * MP_SCR;
+      const float* s = zb + (long long)r * ld;
       const float xh = __fmul_rn(__fsub_rn(s[lane], mu1), rs1);
-      const float gz = __fmul_rn(__fmul_rn(g0l, rs1), __fsub_rn(__fsub_rn(s[224 + lane], c1), __fmul_rn(xh, c2)));
+      const float gz = __fmul_rn(__fmul_rn(g0l, rs1), __fsub_rn(__fsub_rn(s[MAP_GY1 + lane], c1), __fmul_rn(xh, c2)));
       const float craw = __ldg(A.c + r);
       const float c = fminf(fmaxf(craw, 0.f), 1.f);
       const float f1 = __fmul_rn(c, c), f2 = log1p_f64(c);
@@ -703,7 +734,7 @@ __global__ void __launch_bounds__(256)
 softmask_bwd_kernel(const float* __restrict__ dm, const float* __restrict__ bit_map, const float* __restrict__ act_n,
                     const float* __restrict__ P, int H, int W, int Ht, int Wt, float* __restrict__ dbit,
                     float* __restrict__ gP) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int nt = Ht * Wt, b = blockIdx.x;
   float* dmt = sm;
   float* rec = dmt + nt;
@@ -900,25 +931,44 @@ extern "C" int mcaq_complexity_train_bwd(const float* phi, const float* craw, co
   return 0;
 }
 
+static int g_map_cluster = 0;                                  // 0: not probed yet; else the cluster size in use (16 or 8)
+// debug / tuning: force the mapper kernels' cluster size (8 or 16; 0 = probe)
+extern "C" void mcaq_debug_mapper_cluster(int n) { g_map_cluster = (n == 8 || n == 16) ? n : 0; }
+
 static int launch_mapper(void (*k)(const MapArgs), MapArgs& A, cudaStream_t st) {
-  const size_t smem = (size_t)MAP_SM_FLOATS * sizeof(float);
+  const size_t smem_max = (size_t)(MAP_SM_FLOATS + MAP_ROWS_MAX * MAP_ROWF) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(mapper_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(mapper_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(mapper_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    cudaFuncSetAttribute(mapper_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    cudaFuncSetAttribute(mapper_train_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(mapper_train_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(MAP_CL);
-  cfg.blockDim = dim3(MAP_NT);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = MAP_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  A.rpc = (A.N + MAP_CL - 1) / MAP_CL;
+  auto configure = [&](int ncta) {
+    A.rpc = (A.N + ncta - 1) / ncta;
+    cfg.gridDim = dim3(ncta);
+    cfg.blockDim = dim3(MAP_NT);
+    cfg.dynamicSmemBytes = (size_t)(MAP_SM_FLOATS + (A.rpc <= MAP_ROWS_MAX ? A.rpc * MAP_ROWF : 0)) * sizeof(float);
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  };
+  if (g_map_cluster == 0) {
+    // the rows are spread over ONE cluster (the batch statistics need every row): 16 CTAs when the device can co-schedule
+    // a 16-CTA cluster at the largest footprint (a GPC with 16 free SMs), else the portable 8
+    configure(MAP_CL);
+    cfg.dynamicSmemBytes = smem_max;
+    int nclusters = 0;
+    const cudaError_t q = cudaOccupancyMaxActiveClusters(&nclusters, k, &cfg);
+    if (q != cudaSuccess) cudaGetLastError();
+    g_map_cluster = (q == cudaSuccess && nclusters >= 1) ? MAP_CL : 8;
+  }
+  configure(g_map_cluster);
   cudaError_t e = cudaLaunchKernelEx(&cfg, k, A);
   if (e != cudaSuccess) return (int)e;
   MCAQ_LAUNCH_CHECK();

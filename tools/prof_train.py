@@ -14,7 +14,10 @@ a, m, _ = M.build_fixture_modules(W, "cuda"); a.train(); m.train()
 qs = [M.build_fixture_modules(W, "cuda")[2].train() for _ in shapes]
 feats = [(torch.randn(B, C, H, Wd, device="cuda") * 2 + 0.3).bfloat16() for C, H, Wd in shapes]
 teach = [torch.randn(B, C, H, Wd, device="cuda") for C, H, Wd in shapes]
+params = [p for mod in [a, m] + qs for p in mod.parameters()]
 def step():
+    for p in params:                  # like optimizer.zero_grad(set_to_none=True): no accumulate-adds into stale grads
+        p.grad = None
     loss = 0.0
     for x0, t, q in zip(feats, teach, qs):
         x = x0.detach().requires_grad_(True)
