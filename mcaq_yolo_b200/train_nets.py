@@ -19,6 +19,19 @@ CMLP_PARAMS, MAPPER_PARAMS, SOFTMASK_PARAMS = 2881, 4609, 170
 
 
 _FLAT_CACHE = weakref.WeakKeyDictionary()
+
+
+def flat_is_cuda(t) -> bool:
+    return t.is_cuda
+
+
+def prepare_step(*owners):
+    """Build the shared parameter concatenations of `owners` (modules passed to flat_params(owner=...)) on the CURRENT
+    stream.  Call it on the main stream before the scales fork onto their own streams: autograd accumulates the
+    gradient of a shared node on the stream that created it, so a node created inside the first scale's stream would
+    make that scale's whole backward wait for the other scales' contributions."""
+    for o in owners:
+        flat_params(o.parameters(), owner=o)
 _COUNTS = {}
 
 
@@ -36,9 +49,16 @@ def flat_params(params, owner=None) -> torch.Tensor:
     key = tuple((p.data_ptr(), p._version, p.requires_grad) for p in params)
     hit = _FLAT_CACHE.get(owner)          # kept outside the module: a graph tensor in its __dict__ would break deepcopy
     if hit is not None and hit[0] == key and not hit[2]["consumed"]:
+        st = hit[2]
+        if flat_is_cuda(hit[1]) and torch.cuda.current_stream() != st["stream"]:
+            torch.cuda.current_stream().wait_event(st["event"])       # made on another stream: order this one after it
         return hit[1]
     flat = torch.cat([p.reshape(-1).float() for p in params])
     state = {"consumed": False}
+    if flat_is_cuda(flat):
+        state["stream"] = torch.cuda.current_stream()
+        state["event"] = torch.cuda.Event()
+        state["event"].record(state["stream"])
     if flat.requires_grad:
         def _mark(_g, state=state):
             state["consumed"] = True

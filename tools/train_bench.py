@@ -130,6 +130,8 @@ def train_step(i, fused_kd=True, scale_streams=False):
     for p in params:
         p.grad = None
     main = torch.cuda.current_stream()
+    if scale_streams:
+        TN.prepare_step(analyzer.complexity_mlp, mapper.mapping_network)    # shared nodes live on the main stream
     partial, bits_all = [], []
     for si, (x0, t, go, q) in enumerate(zip(feats[k], teach[k], gouts[k], quants)):
         st = SCALE_STREAMS[si] if scale_streams else main
