@@ -76,6 +76,8 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the short run of the per-GPU share of BASELINE configs[2] (YOLOv8s @ 1280, 32 images, fp32) "
                          "that the default single-GPU run appends as `secondary`")
+    ap.add_argument("--timeline", default="", help="write the CUPTI kernel timeline (start us, duration us, stream, kernel) of 16 "
+                                                   "untimed steps of the same loop to this file (tuning aid)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -515,6 +517,20 @@ def run_native(args):
             clocks["note"] = ("sampled over the timed region" if burst == 0 else
                               "sampled over the timed region plus %d untimed steps of the same load" % burst)
         value = world * B * args.steps / (ms_total * 1e-3)
+        if args.timeline and rank == 0:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                fork_slots()
+                for i in range(16):
+                    run_step(i)
+                join_slots()
+                torch.cuda.synchronize()
+            evs = [e for e in prof.events() if e.device_type.name == "CUDA" and e.time_range.end > e.time_range.start]
+            t0_ = min(e.time_range.start for e in evs)
+            with open(args.timeline, "w") as f:
+                for e in sorted(evs, key=lambda e: e.time_range.start):
+                    f.write("%9.1f %7.1f s%s %s\n" % (e.time_range.start - t0_, e.time_range.end - e.time_range.start,
+                                                      getattr(e, "device_resource_id", -1), e.name[:70]))
 
         # ---- roofline attribution: each kernel of each scale timed live with CUDA events around a
         #      CUDA-graph replay of INPUT_SETS back-to-back launches over the rotating inputs (cold
