@@ -59,9 +59,23 @@ def test_complexity_training_backward(name, M, W):
     grads_close(a.complexity_mlp, ref.complexity_mlp)
 
 
-@pytest.mark.parametrize("shape,temp", [((2, 5, 5), 1.0), ((4, 10, 10), 1.3), ((16, 10, 10), 0.7), ((3, 7, 9), None)])
-def test_mapper_training_forward_backward_and_running_stats(shape, temp, M, W):
+@pytest.fixture
+def mapper_cluster():
+    """Force the cluster size of the mapper kernels for one test (0 = the probed default), restored afterwards."""
+    from mcaq_yolo_b200 import _lib
+    lib = _lib.load()
+    yield lib.mcaq_debug_mapper_cluster
+    lib.mcaq_debug_mapper_cluster(0)
+
+
+# rows per CTA <= 218 keep the per-row records in shared memory, more fall back to the global scratch:
+# (16,10,10): 100 / 200 rows per CTA (cached either way); (40,10,10): 250 (16 CTAs) / 500 (8 CTAs): global path
+@pytest.mark.parametrize("shape,temp,cluster", [((2, 5, 5), 1.0, 0), ((4, 10, 10), 1.3, 0), ((16, 10, 10), 0.7, 0),
+                                                ((3, 7, 9), None, 0), ((16, 10, 10), 1.0, 8), ((16, 10, 10), 1.0, 16),
+                                                ((40, 10, 10), 1.0, 16), ((40, 10, 10), 0.9, 8), ((25, 10, 10), 1.0, 8)])
+def test_mapper_training_forward_backward_and_running_stats(shape, temp, cluster, M, W, mapper_cluster):
     torch.backends.cuda.matmul.allow_tf32 = False
+    mapper_cluster(cluster)
     _, m, _ = M.build_fixture_modules(W, "cuda")
     m.train()
     ref = copy.deepcopy(m)
