@@ -321,6 +321,15 @@ MCAQ_API int mcaq_softmask_train_bwd(const float* grad_mask, const float* bit_ma
 MCAQ_API int mcaq_bit_stats(const float* bit_map, int B, int ht, int wt, float* out2, const float* weights2,
                             float* grad_bit_map, void* stream);
 
+/* avg_bits = mean over scales of the per-scale mean, Lbit = (avg_bits - target)^2, Lsmooth = mean over scales of
+ * TV / edge count of S <= 4 bit maps (B_s, ht_s, wt_s), exactly as MCAQYOLO.forward / MCAQYOLOLoss form them
+ * (models/mcaq_yolo.py:575, 86-118), in ONE launch: out[0..2] = the three scalars, out[3 + 2 s], out[4 + 2 s] = the
+ * per-scale sum and total variation.  With grad_out (3 floats on the device: d/d avg_bits, d/d Lbit, d/d Lsmooth) the
+ * call is the backward instead: grads[s] receives d/d bit_map_s (out must hold the forward's values).  The pointer
+ * arrays are HOST arrays of device pointers. */
+MCAQ_API int mcaq_bit_losses(const float* const* bit_maps, const int* B, const int* ht, const int* wt, int S, float target,
+                             float* out, const float* grad_out, float* const* grads, void* stream);
+
 /* Self test of the quantiser's division (RN(x/scale) by Markstein's correction with RN(1/scale))
  * against div.rn: sweeps numerators with bit patterns first + i*stride, i < count, for every
  * scale; *mismatches must be zeroed by the caller. */

@@ -906,9 +906,110 @@ bit_stats_kernel(const float* __restrict__ bm, int ht, int wt, float* __restrict
   }
 }
 
+// ---- avg_bits / Lbit / Lsmooth of up to four scales in ONE launch each way (models/mcaq_yolo.py:575, 86-118) ------------
+// out[0] = avg_bits = mean_s mean(b_s), out[1] = (avg_bits - target)^2, out[2] = mean_s TV(b_s) / edges_s,
+// out[3 + 2 s], out[4 + 2 s]: the per-scale sum and total variation (kept for the backward and for the sharded path)
+constexpr int BL_MAX = 4;
+struct BitLossArgs {
+  const float* bm[BL_MAX]; float* grad[BL_MAX];
+  int B[BL_MAX], ht[BL_MAX], wt[BL_MAX];
+  int S; float target;
+  float* out; const float* gout;
+};
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < 8; ++w) t += red[w];                    // fixed order: deterministic
+  return t;
+}
+
+__device__ __forceinline__ float edges_of(int B, int ht, int wt) {
+  const float e = (float)B * (float)((ht - 1) * wt + ht * (wt - 1));
+  return e < 1.f ? 1.f : e;
+}
+
+__global__ void __launch_bounds__(256) bit_losses_fwd_kernel(const BitLossArgs A) {
+  __shared__ float red[8];
+  float avg = 0.f, sm = 0.f;
+  for (int s = 0; s < A.S; ++s) {
+    const int ht = A.ht[s], wt = A.wt[s], nt = ht * wt, n = A.B[s] * nt;
+    const float* p = A.bm[s];
+    float sum = 0.f, tv = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const int t = i % nt, y = t / wt, x = t - y * wt;
+      const float v = p[i];
+      sum += v;
+      if (y + 1 < ht) tv += fabsf(p[i + wt] - v);
+      if (x + 1 < wt) tv += fabsf(p[i + 1] - v);
+    }
+    sum = block_sum_256(sum, red);
+    tv = block_sum_256(tv, red);
+    avg += sum / (float)n;
+    sm += tv / edges_of(A.B[s], ht, wt);
+    if (threadIdx.x == 0) { A.out[3 + 2 * s] = sum; A.out[4 + 2 * s] = tv; }
+  }
+  if (threadIdx.x == 0) {
+    avg /= (float)A.S;
+    const float d = avg - A.target;
+    A.out[0] = avg; A.out[1] = d * d; A.out[2] = sm / (float)A.S;
+  }
+}
+
+// one CTA per (image chunk, scale): d/db of g0 * avg_bits + g1 * Lbit + g2 * Lsmooth
+__global__ void __launch_bounds__(256) bit_losses_bwd_kernel(const BitLossArgs A) {
+  const int s = blockIdx.y;
+  const int ht = A.ht[s], wt = A.wt[s], nt = ht * wt, n = A.B[s] * nt;
+  const float avg = A.out[0];
+  const float w0 = (A.gout[0] + A.gout[1] * 2.f * (avg - A.target)) / ((float)A.S * (float)n);
+  const float w1 = A.gout[2] / ((float)A.S * edges_of(A.B[s], ht, wt));
+  const float* p = A.bm[s];
+  float* g = A.grad[s];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int t = i % nt, y = t / wt, x = t - y * wt;
+    const float v = p[i];
+    float acc = w0;
+    if (y + 1 < ht) { const float d = p[i + wt] - v; acc -= w1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)); }
+    if (x + 1 < wt) { const float d = p[i + 1] - v; acc -= w1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)); }
+    if (y > 0) { const float d = v - p[i - wt]; acc += w1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)); }
+    if (x > 0) { const float d = v - p[i - 1]; acc += w1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)); }
+    g[i] = acc;
+  }
+}
+
 }  // namespace mcaq
 
 using namespace mcaq;
+
+// avg_bits, Lbit = (avg_bits - target)^2 and Lsmooth of S <= 4 bit maps (B_s, ht_s, wt_s) in one launch: out holds
+// 3 + 2 S floats (see BitLossArgs).  With grad_out (3 floats, device) and grads (S pointers): the backward launch.
+extern "C" int mcaq_bit_losses(const float* const* bit_maps, const int* B, const int* ht, const int* wt, int S, float target,
+                               float* out, const float* grad_out, float* const* grads, void* stream) {
+  if (!bit_maps || !B || !ht || !wt || S < 1 || S > BL_MAX || !out || (grad_out && !grads)) return MCAQ_EINVAL;
+  BitLossArgs A = {};
+  int nmax = 0;
+  for (int s = 0; s < S; ++s) {
+    if (!bit_maps[s] || B[s] <= 0 || ht[s] <= 0 || wt[s] <= 0 || (grad_out && !grads[s])) return MCAQ_EINVAL;
+    A.bm[s] = bit_maps[s]; A.B[s] = B[s]; A.ht[s] = ht[s]; A.wt[s] = wt[s];
+    A.grad[s] = grad_out ? grads[s] : nullptr;
+    const int n = B[s] * ht[s] * wt[s];
+    nmax = n > nmax ? n : nmax;
+  }
+  A.S = S; A.target = target; A.out = out; A.gout = grad_out;
+  if (!grad_out) {
+    bit_losses_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(A);
+  } else {
+    int gx = (nmax + 1023) / 1024;
+    gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
+    bit_losses_bwd_kernel<<<dim3(gx, S), 256, 0, (cudaStream_t)stream>>>(A);
+  }
+  MCAQ_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" long long mcaq_cmlp_train_scratch_floats(int N) { return N > 0 ? 4 : MCAQ_EINVAL; }   // none needed any more
 extern "C" long long mcaq_mapper_train_scratch_floats(int N) { return N > 0 ? (long long)N * MP_SCR : MCAQ_EINVAL; }

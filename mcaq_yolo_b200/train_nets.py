@@ -190,11 +190,50 @@ class BitStatsFn(torch.autograd.Function):
         return grad
 
 
+class BitLossesFn(torch.autograd.Function):
+    """(bit maps of S <= 4 scales) -> tensor [avg_bits, Lbit, Lsmooth] in ONE launch each way (mcaq_bit_losses): the
+    single-rank form of `bit_map_losses`."""
+
+    @staticmethod
+    def _args(maps):
+        S = len(maps)
+        ptrs = (ctypes.c_void_p * S)(*[m.data_ptr() for m in maps])
+        Bs = (ctypes.c_int * S)(*[m.shape[0] for m in maps])
+        hs = (ctypes.c_int * S)(*[m.shape[1] for m in maps])
+        ws = (ctypes.c_int * S)(*[m.shape[2] for m in maps])
+        return S, ptrs, Bs, hs, ws
+
+    @staticmethod
+    def forward(ctx, target, *bit_maps):
+        maps = [b.contiguous().float() for b in bit_maps]
+        S, ptrs, Bs, hs, ws = BitLossesFn._args(maps)
+        out = torch.empty((3 + 2 * S,), device=maps[0].device, dtype=torch.float32)
+        ops._call("mcaq_bit_losses", ptrs, Bs, hs, ws, S, float(target), out.data_ptr(), None, None, ops._stream())
+        ctx.save_for_backward(out, *maps)
+        ctx.target = float(target)
+        return out[:3]
+
+    @staticmethod
+    def backward(ctx, g):
+        out, *maps = ctx.saved_tensors
+        S, ptrs, Bs, hs, ws = BitLossesFn._args(maps)
+        grads = [torch.empty_like(m) for m in maps]
+        gptrs = (ctypes.c_void_p * S)(*[t.data_ptr() for t in grads])
+        g = g.contiguous().float()
+        ops._call("mcaq_bit_losses", ptrs, Bs, hs, ws, S, ctx.target, out.data_ptr(), g.data_ptr(), gptrs, ops._stream())
+        return (None, *grads)
+
+
 def bit_map_losses(bit_maps, target_bits: float, group=None):
     """(avg_bits, Lbit, Lsmooth) of the per-scale bit maps exactly as MCAQYOLO.forward / MCAQYOLOLoss form them
     (models/mcaq_yolo.py:575, 86-118): avg_bits = mean over scales of the per-scale mean, Lsmooth = mean over scales
     of the per-edge mean total variation.  With a process group the per-scale means are taken over the GLOBAL batch
     (one all-reduce of 2 x len(bit_maps) floats; the gradient stays local and is scaled by the global count)."""
+    import torch.distributed as dist
+    sharded = group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    if not sharded and 1 <= len(bit_maps) <= 4 and all(b.is_cuda and b.dim() == 3 for b in bit_maps):
+        r = BitLossesFn.apply(float(target_bits), *bit_maps)                 # one launch forward, one backward
+        return r[0], r[1], r[2]
     stats = torch.stack([BitStatsFn.apply(b) for b in bit_maps])             # (S, 2)
     ckey = (tuple(tuple(b.shape) for b in bit_maps), stats.device)
     counts = _COUNTS.get(ckey)          # cached: no host-to-device copy in the steady state (graph-capturable)
