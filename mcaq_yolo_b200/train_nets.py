@@ -46,13 +46,20 @@ def flat_params(params, owner=None) -> torch.Tensor:
     params = list(params)
     if owner is None or not torch.is_grad_enabled():
         return torch.cat([p.reshape(-1).float() for p in params])
-    key = tuple((p.data_ptr(), p._version, p.requires_grad) for p in params)
+    capturing = bool(params) and params[0].is_cuda and torch.cuda.is_current_stream_capturing()
+    # (a node built inside a graph capture is never reused outside it, nor the other way round)
+    key = tuple((p.data_ptr(), p._version, p.requires_grad) for p in params) + (capturing,)
     hit = _FLAT_CACHE.get(owner)          # kept outside the module: a graph tensor in its __dict__ would break deepcopy
     if hit is not None and hit[0] == key and not hit[2]["consumed"]:
         st = hit[2]
+        ok = True
         if flat_is_cuda(hit[1]) and torch.cuda.current_stream() != st["stream"]:
-            torch.cuda.current_stream().wait_event(st["event"])       # made on another stream: order this one after it
-        return hit[1]
+            try:
+                torch.cuda.current_stream().wait_event(st["event"])   # made on another stream: order this one after it
+            except RuntimeError:          # e.g. an event left behind by an aborted capture: rebuild
+                ok = False
+        if ok:
+            return hit[1]
     flat = torch.cat([p.reshape(-1).float() for p in params])
     state = {"consumed": False}
     if flat_is_cuda(flat):

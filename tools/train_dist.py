@@ -28,6 +28,9 @@ ap.add_argument("--steps", type=int, default=30)
 ap.add_argument("--warmup", type=int, default=5)
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--out", default="")
+ap.add_argument("--graph", action="store_true", help="also time the step as one captured CUDA graph per input set (NCCL "
+                                                     "all-reduces and the in-kernel peer exchange captured with it)")
+ap.add_argument("--scale-streams", action="store_true", help="with --graph: one stream per scale, forward and backward")
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -45,6 +48,9 @@ from mcaq_yolo_b200 import train_nets as TN  # noqa: E402
 from mcaq_yolo_b200.peer import RangeExchange  # noqa: E402
 from golden_util import weights  # noqa: E402
 
+# everything runs on a non-default stream: autograd binds a parameter's AccumulateGrad node to the stream of its first
+# backward, and a node bound to the legacy default stream cannot take part in a later graph capture
+torch.cuda.set_stream(torch.cuda.Stream(device=dev))
 B = a.batch
 shapes = [(64, 80, 80), (128, 40, 40), (256, 20, 20)]
 W = weights()
@@ -64,20 +70,32 @@ teach = [[torch.randn(B, C, H, Wd, device=dev, generator=gen) for C, H, Wd in sh
 gouts = [[(torch.randn(B, C, H, Wd, device=dev, generator=gen) * 1e-3).bfloat16() for C, H, Wd in shapes] for _ in range(NSETS)]
 
 
-def step(i):
+SS = [torch.cuda.Stream(device=dev) for _ in shapes]
+
+
+def step(i, scale_streams=False):
     k = i % NSETS
     for p in params:
         p.grad = None
-    loss = 0.0
-    bits = []
-    for x0, t, go, q in zip(feats[k], teach[k], gouts[k], quants):
-        x = x0.detach().requires_grad_(True)
-        q.kd_teacher = t
-        r = M.mcaq_hook_forward(x, analyzer, mapper, q, temperature=1.0, training=True)
-        loss = loss + (r["features_q"] * go).sum().float() + r["kd_feature_loss"] / len(shapes)
+    main = torch.cuda.current_stream()
+    if scale_streams:
+        TN.prepare_step(analyzer.complexity_mlp, mapper.mapping_network)
+    parts, bits = [], []
+    for si, (x0, t, go, q) in enumerate(zip(feats[k], teach[k], gouts[k], quants)):
+        st = SS[si] if scale_streams else main
+        if scale_streams:
+            st.wait_stream(main)
+        with torch.cuda.stream(st):
+            x = x0.detach().requires_grad_(True)
+            q.kd_teacher = t
+            r = M.mcaq_hook_forward(x, analyzer, mapper, q, temperature=1.0, training=True)
+            parts.append((r["features_q"] * go).sum().float() + r["kd_feature_loss"] / len(shapes))
         bits.append(r["bit_map"])
+    if scale_streams:
+        for st in SS:
+            main.wait_stream(st)
     avg, lbit, lsm = TN.bit_map_losses(bits, 4.0)           # global batch when world > 1
-    loss = loss + 0.01 * lbit + 0.1 * lsm
+    loss = torch.stack(parts).sum() + 0.01 * lbit + 0.1 * lsm
     loss.backward()
     TN.allreduce_grads(nets)                                  # one flat ~32 KB all-reduce
     return loss, avg
@@ -98,6 +116,51 @@ ms = e0.elapsed_time(e1) / a.steps
 t = torch.tensor([ms], device=dev, dtype=torch.float64)
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+graph_ms, graph_err = None, None
+if a.graph:
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                step(i, a.scale_streams)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs = []
+        for k in range(NSETS):
+            for p in params:
+                p.grad = None
+            g = torch.cuda.CUDAGraph()
+            # thread_local: the NCCL watchdog thread makes CUDA calls of its own while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                step(k, a.scale_streams)
+            graphs.append(g)
+        for g in graphs:
+            g.replay()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(a.steps):
+            graphs[i % NSETS].replay()
+        g1.record()
+        torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1) / a.steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        graph_ms = float(tg.item())
+    except Exception as e:      # noqa: BLE001 -- the eager number stands
+        graph_err = f"{type(e).__name__}: {str(e)[:200]}"
+        torch.cuda.synchronize()
+
+if a.graph:                      # the consistency check below looks at the gradients of a plain eager step
+    torch.cuda.synchronize()
+    if graph_err is not None:
+        sys.stderr.write("[train_dist] capture failed: %s\n" % graph_err)
+    _, avg = step(0)
+    torch.cuda.synchronize()
 
 # ---- consistency over ranks, outside the timed region ----------------------------------------------------------
 ok = 1
@@ -125,6 +188,9 @@ line = {"what": "MCAQ training step of the three hooks (configs[3] share: %d ima
         "exchanges": "SyncBN statistics inside the mapper kernels over peer memory; ranges MIN all-reduce; avg_bits/TV "
                      "all-reduce (6 floats); one flat gradient all-reduce" if world > 1 else "none (single GPU)",
         "rank_consistency": "ok" if ok else "FAILED"}
+if a.graph:
+    line.update({"captured_ms_per_step": graph_ms, "captured_images_per_s": None if graph_ms is None else B * world / graph_ms * 1e3,
+                 "captured_streams": "one per scale" if a.scale_streams else "one", "capture_error": graph_err})
 if rank == 0:
     os.write(out_fd, (json.dumps(line) + "\n").encode())
     if a.out:
