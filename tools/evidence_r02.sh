@@ -8,7 +8,7 @@ python bench.py > $O/bench_b64_bf16.json 2> $O/bench.err; tail -2 $O/bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 2> $O/bench_ref.err
 BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-secondary"
 $BENCH > $O/plain_bench.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_bench.csv $BENCH > $O/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"reduce_planes|morph_fused|tile_quantize" -c 2000 --csv --log-file $O/launches_bench.csv $BENCH > $O/ncu_launches.log 2>&1
 python tools/prof_step.py bf16 > $O/plain_step.log 2>&1 && \
 ncu --set full --clock-control none -k regex:"reduce_planes|morph_fused|tile_quantize" --launch-skip 36 --launch-count 9 -f -o /tmp/step_bf16 python tools/prof_step.py bf16 > $O/ncu_step.log 2>&1
 ncu -i /tmp/step_bf16.ncu-rep --page raw --csv > $O/ncu_full_step_bf16_raw.csv 2>/dev/null
