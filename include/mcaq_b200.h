@@ -291,7 +291,7 @@ MCAQ_API int mcaq_soft_mask(const float* bit_map, int Ht, int Wt, const float* a
  * (complexity MLP 2881, mapper 4609, soft mask 170 floats); gradient blocks are ACCUMULATED into.
  *   complexity: forward = mcaq_complexity (keep its raw output); mcaq_complexity_train_bwd = bilateral + clamp +
  *               MLP backward (scratch: mcaq_cmlp_train_scratch_floats(B*ht*wt) floats, grad_craw_ws: B*ht*wt)
- *   mapper    : mcaq_mapper_train_fwd / _bwd run as ONE 8-CTA thread-block cluster; BatchNorm batch statistics
+ *   mapper    : mcaq_mapper_train_fwd / _bwd run as ONE thread-block cluster (16 CTAs, or the portable 8); BatchNorm batch statistics
  *               are reduced through distributed shared memory and -- xchg_world > 1, buffers of a C = 128 range
  *               exchange -- merged with the other ranks of the node over NVLink peer memory inside the kernel
  *               (rank-ordered Chan merge: every rank gets the statistics of the unsharded batch).

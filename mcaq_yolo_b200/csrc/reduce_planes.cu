@@ -426,7 +426,7 @@ static int launch_reduce(const T* x, int B, int C, int HW, float* sp, float* ap,
   const long long total = (total_vec + 31) / 32;
   const size_t smem = (size_t)2 * G * 32 * VEC * sizeof(float) + (size_t)2 * C * sizeof(int);
   // persistent CTAs, exactly the resident wave: 512 threads per SM at <= 128 registers (16 / G CTAs).  A
-  // second wave only repeats the per-CTA prologue / epilogue (32 REDUX + 2C atomics): one wave measured
+  // second wave only repeats the per-CTA prologue / epilogue (range join + 2C atomics): one wave measured
   // 7 % (C3) to 14 % (C4) faster
   const int per_sm = 16 / G > 0 ? 16 / G : 1;
   long long grid = (long long)num_sms() * per_sm;

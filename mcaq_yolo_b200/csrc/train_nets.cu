@@ -8,7 +8,7 @@
 //
 // The problems are tiny (a few thousand rows of 8..64 features; 2.9k / 4.6k / 170 parameters): what costs in
 // the reference is ~10^3 eager autograd kernels per step.  Here a network is one or two launches per direction.
-// Rows are independent except for the mapper's BatchNorm: its kernels run as ONE thread-block cluster (8 CTAs,
+// Rows are independent except for the mapper's BatchNorm: its kernels run as ONE thread-block cluster (16 CTAs where the device co-schedules them, else 8,
 // rows split over the CTAs) that reduces the per-feature statistics through distributed shared memory and, when
 // the batch is sharded over the GPUs of a node, merges them with the other ranks over NVLink peer memory inside
 // the same kernel (peer_exchange.cuh protocol: rank-ordered Chan merge of (count, mean, M2), so every rank holds
