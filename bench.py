@@ -79,6 +79,7 @@ def parse():
     ap.add_argument("--timeline", default="", help="write the CUPTI kernel timeline (start us, duration us, stream, kernel) of 16 "
                                                    "untimed steps of the same loop to this file (tuning aid)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-budget", type=float, default=120.0, help="--impl reference: seconds of host work for the whole run")
     return ap.parse_args()
 
 
@@ -180,7 +181,7 @@ def run_reference(args):
     worker = _reference_worker if use_ref else _oracle_worker
     nimg = 2
     nsteps = max(1, args.steps + args.warmup)
-    budget = 120.0
+    budget = float(args.ref_budget)
     ctx = mp.get_context("spawn")
     vals = []
     with ctx.Pool(procs) as pool:
