@@ -4,7 +4,7 @@
 #define K3_MAGIC 0
 #endif
 #ifndef K3_MINB
-#define K3_MINB 3
+#define K3_MINB 6
 #endif
 
 #include <cuda_runtime.h>

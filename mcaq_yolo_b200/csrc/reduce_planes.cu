@@ -446,7 +446,12 @@ static int launch_reduce(const T* x, int B, int C, int HW, float* sp, float* ap,
 template <typename T, int VEC>
 static int dispatch_groups(const T* x, int B, int C, int HW, float* sp, float* ap, int* keys, cudaStream_t st) {
   const int ngroups = (C + 15) / 16;
-  if (ngroups >= 16) return launch_reduce<T, VEC, 16>(x, B, C, HW, sp, ap, keys, st);
+  // 16-warp CTAs (one pass over C >= 256, register range accumulators) take a whole SM's register file: nothing of the
+  // morphology kernel can be resident beside them.  They pay only when a CTA sees a strip or two (C5 of v8n@640);
+  // on larger maps 8-warp CTAs making two or more passes co-reside and win (v8s@1280 fp32: whole step 0.462 ->
+  // 0.445 ms, profiles/r02_coreside_sweep.txt)
+  const long long strips = ((long long)B * ((HW + VEC - 1) / VEC) + 31) / 32;
+  if (ngroups >= 16 && strips < 2LL * num_sms()) return launch_reduce<T, VEC, 16>(x, B, C, HW, sp, ap, keys, st);
   if (ngroups >= 8) return launch_reduce<T, VEC, 8>(x, B, C, HW, sp, ap, keys, st);
   if (ngroups >= 3) return launch_reduce<T, VEC, 4>(x, B, C, HW, sp, ap, keys, st);
   if (ngroups == 2) return launch_reduce<T, VEC, 2>(x, B, C, HW, sp, ap, keys, st);

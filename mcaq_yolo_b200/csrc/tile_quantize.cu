@@ -447,9 +447,9 @@ static int g_k3_chunk = 0;     // tuning aid (mcaq_debug_k3_chunk): 0 = heuristi
 static int k3_chunk(unsigned gx, int C) {
   if (g_k3_chunk == 8 || g_k3_chunk == 16) return g_k3_chunk;
   // measured (profiles/r02_k3_chunk.txt): 16 everywhere except where that leaves fewer than two CTAs per SM
-  // (C5 bf16 at batch 64: 208 CTAs), where 8 is 13 % faster; 32 is never ahead
-  const long long ctas = (long long)gx * ((C + QV_CHUNK - 1) / QV_CHUNK);
-  return ctas < 2LL * 148 ? 8 : QV_CHUNK;
+  // of 256 threads (C5 bf16 at batch 64), where 8 is 13 % faster; 32 is never ahead
+  const long long threads = (long long)gx * QV_THREADS * ((C + QV_CHUNK - 1) / QV_CHUNK);
+  return threads < 2LL * 148 * 256 ? 8 : QV_CHUNK;
 }
 
 template <typename T, int VEC>

@@ -17,7 +17,13 @@ __device__ __forceinline__ void bit_limits(int bidx, float& qmin, float& qmax) {
   qmax = (float)(half - 1);
 }
 
-constexpr int QV_THREADS = 256;
+// 128-thread CTAs, six per SM (80 registers): the same 768 resident threads as three CTAs of 256, but the finer grain
+// packs around the resident morphology CTAs (16 K registers each) -- whole step 0.0820 -> 0.0803 ms
+// (profiles/r02_k3_variants.txt)
+#ifndef K3_THREADS
+#define K3_THREADS 128
+#endif
+constexpr int QV_THREADS = K3_THREADS;
 constexpr int QV_CHUNK = 16;
 #ifndef K3_UNROLL
 #define K3_UNROLL 8

@@ -85,7 +85,7 @@ def _res_usage(obj):
 
 def test_register_caps_of_the_hot_kernels(sass):
     """K1: <= 128 registers (512 resident threads per SM), K2: <= 64 (four 256-thread CTAs), K3: <= 80
-    (three 256-thread CTAs), training forms: <= 128 (two CTAs); stack (spill) frames stay small."""
+    (six 128-thread CTAs), training forms: <= 128 (two CTAs); stack (spill) frames stay small."""
     k1 = {n: v for n, v in _res_usage("reduce_planes.o").items() if "reduce_planes_kernel" in n}
     assert k1 and all(r <= 128 for r, _ in k1.values())
     # (the four-CTA bf16 form parks one word outside the load / sum loop: one STL in the prologue, one LDL per strip)
